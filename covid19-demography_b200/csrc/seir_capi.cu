@@ -1,0 +1,632 @@
+// seir_capi.cu -- kernels' launch side and the C ABI declared in include/seir_b200.h.
+// Built into libseir_b200.so by covid19-demography_b200/build.py (nvcc, sm_100a, -lineinfo).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "seir_kernels.cuh"
+
+using namespace seir;
+
+#define SEIR_STR2(x) #x
+#define SEIR_STR(x) SEIR_STR2(x)
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(kThreads) seir_persistent_kernel(DevCtx cx)
+{
+    __shared__ TileSmem sm;
+    // the host resets the barrier counter to 0 before each launch
+    for (int t = 1; t <= cx.T; ++t) {
+        day_pass(cx, sm, t);
+        if (t < cx.T) grid_barrier(cx.barrier, (unsigned int)t * gridDim.x);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) seir_day_kernel(DevCtx cx, int t)
+{
+    __shared__ TileSmem sm;
+    day_pass(cx, sm, t);
+}
+
+// row 0 := S (padding := inert), winner := 0, inbox := 0
+__global__ void seir_init_state_kernel(DevCtx cx)
+{
+    const int64_t nvec = cx.n_pad / kVec;
+    const int64_t total = nvec * cx.n_rep;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int rep = (int)(g / nvec);
+        const int64_t vi = g % nvec;
+        const int64_t i0 = vi * kVec;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (i0 + k * 4 + b >= cx.n) x |= (uint32_t)C_PAD << (8 * b);
+            w[k] = x;
+        }
+        reinterpret_cast<uint4 *>(cx.hist + (size_t)rep * cx.T * cx.n_pad)[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+        cx.inbox[(size_t)rep * nvec + vi] = 0;
+        uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + (size_t)rep * cx.n_pad + i0);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wz[k] = z;
+    }
+}
+
+// :220-227 initial cases: E at t=0, activation time drawn at site INIT, time_to_isolate = 0
+__global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, const int64_t *init_off)
+{
+    const int rep = blockIdx.y;
+    const int64_t lo = init_off[rep], hi = init_off[rep + 1];
+    for (int64_t k = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = init_ids[k];
+        const uint64_t seed = cx.seeds[rep];
+        AgentRec r = AgentRec{};
+        r.t_exposed = 0;
+        r.tt_activation = sd_enc16(sd_lognormal_days(seed, (uint32_t)a, 0, SD_SITE_INIT, 0, cx.act_mu, cx.act_sigma));
+        store_rec(cx.rec + (size_t)rep * cx.n_pad + a, r);
+        cx.hist[(size_t)rep * cx.T * cx.n_pad + a] = C_E;
+        atomicOr(cx.inbox + (size_t)rep * (cx.n_pad / 16) + (a >> 4), inbox_infected_bit((int)(a & 15)));
+        const int age = cx.stat[a] & 127;
+        atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + age, 1u);
+    }
+}
+
+__global__ void seir_pack_home_kernel(const uint8_t *home_u8, uint32_t *bitmap, int64_t n, int64_t n_words)
+{
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t x = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int64_t i = w * 32 + b;
+            if (i < n && home_u8[i]) x |= 1u << b;
+        }
+        bitmap[w] = x;
+    }
+}
+
+__device__ __forceinline__ double dec16(uint16_t v) { return v == NEVER ? __longlong_as_double(0x7FF0000000000000ll) : (double)v; }
+
+__global__ void seir_agent_vector_kernel(DevCtx cx, int rep, int which, double *out)
+{
+    const uint32_t *inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+    const AgentRec *rec = cx.rec + (size_t)rep * cx.n_pad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cx.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool ever = (inbox[i >> 4] & inbox_infected_bit((int)(i & 15))) != 0;
+        double v;
+        if (!ever) {
+            v = (which == SEIR_VEC_NUM_INFECTED_BY || which == SEIR_VEC_TIME_EXPOSED ||
+                 which == SEIR_VEC_NUM_INFECTED_ASYMPT || which == SEIR_VEC_NUM_INFECTED_OUTSIDE) ? -1.0 : 0.0;
+        } else {
+            const AgentRec r = rec[i];
+            switch (which) {
+                case SEIR_VEC_NUM_INFECTED_BY: v = r.n_inf_by; break;
+                case SEIR_VEC_TIME_DOCUMENTED: v = r.t_documented; break;
+                case SEIR_VEC_TIME_TO_ACTIVATION: v = dec16(r.tt_activation); break;
+                case SEIR_VEC_TIME_TO_DEATH: v = dec16(r.tt_death); break;
+                case SEIR_VEC_TIME_TO_RECOVERY: v = dec16(r.tt_recovery); break;
+                case SEIR_VEC_TIME_CRITICAL: v = r.t_critical; break;
+                case SEIR_VEC_TIME_EXPOSED: v = r.t_exposed; break;
+                case SEIR_VEC_NUM_INFECTED_ASYMPT: v = r.n_inf_asympt; break;
+                case SEIR_VEC_TIME_INFECTED: v = r.t_infected; break;
+                case SEIR_VEC_TIME_TO_SEVERE: v = dec16(r.tt_severe); break;
+                case SEIR_VEC_TIME_TO_ISOLATE: v = dec16(r.tt_isolate); break;
+                case SEIR_VEC_TIME_SEVERE: v = r.t_severe; break;
+                case SEIR_VEC_TIME_TO_CRITICAL: v = dec16(r.tt_critical); break;
+                default: v = r.n_inf_outside; break;
+            }
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void seir_history_plane_kernel(const uint8_t *rows, int64_t n, int64_t n_pad, int n_rows, int which, uint8_t *out)
+{
+    const int64_t total = (int64_t)n_rows * n;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = g / n, i = g % n;
+        const uint8_t s = rows[row * n_pad + i];
+        const int comp = s & 7;
+        uint8_t v;
+        switch (which) {
+            case SEIR_H_S: v = comp == C_S; break;
+            case SEIR_H_E: v = comp == C_E; break;
+            case SEIR_H_MILD: v = comp == C_MILD; break;
+            case SEIR_H_DOCUMENTED: v = (s & ST_DOC) != 0; break;
+            case SEIR_H_SEVERE: v = comp == C_SEV; break;
+            case SEIR_H_CRITICAL: v = comp == C_CRIT; break;
+            case SEIR_H_R: v = comp == C_R; break;
+            case SEIR_H_D: v = comp == C_D; break;
+            case SEIR_H_Q: v = (s & ST_Q) != 0; break;
+            default: v = s & 0x1F; break;
+        }
+        out[g] = v;
+    }
+}
+
+__global__ void seir_probe_kernel(uint64_t seed, int64_t m, double mean, double mu, double sigma, double enlam,
+                                  double *exp_out, double *logn_out, long long *pois_out, double *log_out,
+                                  const double *log_in)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        sd_block b = sd_draw(seed, (uint32_t)i, 0, SD_SITE_ACT, 0);
+        exp_out[i] = sd_exp_days(sd_lane(b, 0), mean);
+        logn_out[i] = sd_lognormal_days(seed, (uint32_t)i, 0, SD_SITE_INIT, 0, mu, sigma);
+        pois_out[i] = sd_poisson(seed, (uint32_t)i, 0, SD_SITE_NCNT, 0, enlam, SD_MAX_CONTACTS_NATIVE);
+        log_out[i] = sd_log(log_in[i]);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char b_[512];                                                                              \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(b_);                                                                           \
+        }                                                                                              \
+    } while (0)
+
+template <class Tp> struct DevBuf {
+    Tp *p = nullptr;
+    size_t count = 0;
+    cudaError_t alloc(size_t c)
+    {
+        if (c <= count && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), (c ? c : 1) * sizeof(Tp));
+        if (e == cudaSuccess) count = c;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; count = 0; }
+};
+
+struct seir_handle {
+    int device = 0, sms = 0, n_rep = 0;
+    int grid = 0, occ = 0;
+    seir_params prm{};
+    int64_t n = 0, n_pad = 0;
+    int T_alloc = 0;
+    bool replay_tables = false;
+    std::vector<int64_t> group_sizes;  // N_age
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    float loop_ms = 0.f, total_ms = 0.f;
+    long long launches = 0;
+    DevBuf<uint16_t> stat;
+    DevBuf<int32_t> grp_off, grp_members, init_ids;
+    DevBuf<int64_t> init_off;
+    DevBuf<double> p_hh, tables, enlam, stage_d;
+    DevBuf<uint8_t> hist, stage_u8;
+    DevBuf<uint32_t> inbox, tally, home;
+    DevBuf<unsigned long long> winner, counters;
+    DevBuf<AgentRec> rec;
+    DevBuf<uint64_t> seeds;
+    DevBuf<unsigned int> barrier;
+    double p_hh_scalar = 0.0;
+    bool p_hh_uniform = true;
+    DevCtx cx{};
+};
+
+static const size_t kTabPms = 0, kTabPsc = 404, kTabPcd = 808, kTabIso = 1212, kTabIsoA = 1313, kTabNatEn = 1414,
+                    kTabCdf = 1414 + 404, kTabTotal = 1414 + 404 + 101 * 101;
+
+static int upload_tables(seir_handle *h, const seir_tables *tb)
+{
+    if (!tb || !tb->p_mild_severe || !tb->p_severe_critical || !tb->p_critical_death || !tb->iso_mean ||
+        !tb->iso_asympt_mean || !tb->nat_enlam || !tb->nat_cdf)
+        return fail("seir_tables: a required table pointer is NULL");
+    std::vector<double> host(kTabTotal);
+    memcpy(&host[kTabPms], tb->p_mild_severe, 404 * sizeof(double));
+    memcpy(&host[kTabPsc], tb->p_severe_critical, 404 * sizeof(double));
+    memcpy(&host[kTabPcd], tb->p_critical_death, 404 * sizeof(double));
+    memcpy(&host[kTabIso], tb->iso_mean, 101 * sizeof(double));
+    memcpy(&host[kTabIsoA], tb->iso_asympt_mean, 101 * sizeof(double));
+    memcpy(&host[kTabNatEn], tb->nat_enlam, 404 * sizeof(double));
+    memcpy(&host[kTabCdf], tb->nat_cdf, 101 * 101 * sizeof(double));
+    CK(h->tables.alloc(kTabTotal));
+    CK(cudaMemcpyAsync(h->tables.p, host.data(), kTabTotal * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->replay_tables = tb->enlam_pre && tb->enlam_post;
+    if (h->replay_tables) {
+        CK(h->enlam.alloc(2 * 101 * 101));
+        CK(cudaMemcpyAsync(h->enlam.p, tb->enlam_pre, 101 * 101 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->enlam.p + 101 * 101, tb->enlam_post, 101 * 101 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int check_params(const seir_params *p, int64_t n)
+{
+    if (!p) return fail("seir_params is NULL");
+    if (p->n != n) return fail("seir_params.n does not match the population");
+    if (p->T < 2 || p->T > 4000) return fail("seir_params.T must be in [2, 4000]");
+    if (p->mode != SEIR_MODE_NATIVE && p->mode != SEIR_MODE_REPLAY) return fail("seir_params.mode is invalid");
+    if (p->launch != SEIR_LAUNCH_PERSISTENT && p->launch != SEIR_LAUNCH_PER_DAY) return fail("seir_params.launch is invalid");
+    if (p->tracing_enabled && p->t_tracing_start >= 1 && p->t_tracing_start < p->T)
+        return fail("contact tracing would switch on at t_tracing_start < T: device tracing is not implemented "
+                    "(pass t_tracing_start >= T, or tracing_enabled = 0)");
+    return 0;
+}
+
+static int alloc_state(seir_handle *h)
+{
+    const size_t R = (size_t)h->n_rep, np = (size_t)h->n_pad, T = (size_t)h->prm.T;
+    CK(h->hist.alloc(R * T * np));
+    CK(h->tally.alloc(R * T * TAL_ROWS * kAges));
+    h->T_alloc = h->prm.T;
+    return 0;
+}
+
+static void fill_ctx(seir_handle *h)
+{
+    DevCtx &c = h->cx;
+    const seir_params &p = h->prm;
+    c.n = h->n; c.n_pad = h->n_pad; c.tiles_per_rep = (int)(h->n_pad / kTile); c.n_rep = h->n_rep; c.T = p.T;
+    int chunks = h->grid / h->n_rep;
+    if (chunks < 1) chunks = 1;
+    if (chunks > c.tiles_per_rep) chunks = c.tiles_per_rep;
+    c.chunks_per_rep = chunks;
+    c.stat = h->stat.p; c.grp_off = h->grp_off.p; c.grp_members = h->grp_members.p;
+    c.p_hh_vec = h->p_hh_uniform ? nullptr : h->p_hh.p; c.p_hh_scalar = h->p_hh_scalar;
+    c.p_ms = h->tables.p + kTabPms; c.p_sc = h->tables.p + kTabPsc; c.p_cd = h->tables.p + kTabPcd;
+    c.iso_mean = h->tables.p + kTabIso; c.iso_asym = h->tables.p + kTabIsoA;
+    c.nat_enlam = h->tables.p + kTabNatEn; c.nat_cdf = h->tables.p + kTabCdf;
+    c.enlam = h->replay_tables ? h->enlam.p : nullptr;
+    c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
+    c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
+    c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
+    c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
+    c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
+    c.m_sev_rec = p.mean_time_severe_recovery; c.m_crit_rec = p.mean_time_critical_recovery; c.m_death = p.mean_time_to_death;
+    c.act_mu = p.time_to_activation_mean; c.act_sigma = p.time_to_activation_std;
+}
+
+extern "C" {
+
+const char *seir_last_error(void) { return g_err.c_str(); }
+
+int seir_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+const char *seir_build_info(void)
+{
+    return "libseir_b200: CUDA kernels for sm_100a (compute_100a), nvcc " SEIR_STR(__CUDACC_VER_MAJOR__) "."
+           SEIR_STR(__CUDACC_VER_MINOR__) ", -lineinfo, tile=4096 agents, 256 threads/CTA";
+}
+
+int seir_create(const seir_params *params, const seir_population *pop, const seir_tables *tables, int n_replicas,
+                int device, seir_handle **out)
+{
+    if (!out) return fail("out handle pointer is NULL");
+    *out = nullptr;
+    if (!pop || !pop->households || !pop->age || !pop->diabetes || !pop->hypertension || !pop->group_offsets ||
+        !pop->group_members || !pop->p_infect_household)
+        return fail("seir_population: a required pointer is NULL");
+    if (n_replicas < 1 || n_replicas > 4096) return fail("n_replicas must be in [1, 4096]");
+    const int64_t n = pop->n;
+    if (n < 1 || n > 2000000000ll) return fail("population size must be in [1, 2e9]");
+    if (pop->W < 1 || pop->W > 7) return fail("households.shape[1] must be in [1, 7]");
+    if (check_params(params, n)) return 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail("no CUDA device: libseir_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("libseir_b200 is built for sm_100a (B200); this device is older");
+
+    seir_handle *h = new seir_handle();
+    h->device = device; h->sms = prop.multiProcessorCount; h->n_rep = n_replicas; h->prm = *params; h->n = n;
+    h->n_pad = (n + kTile - 1) / kTile * kTile;
+    int rc = 1;
+    do {
+        // ---- static population: verify the contiguous all-pairs household layout, pack 2 B/agent
+        const int W = pop->W;
+        std::vector<uint16_t> stat((size_t)h->n_pad, 0);
+        bool ok = true;
+        std::string why;
+        for (int64_t i = 0; i < n && ok;) {
+            // household of i: i is its first member (pos 0); size = 1 + number of row entries
+            int sz = 1;
+            const int64_t *row = pop->households + i * W;
+            while (sz - 1 < W && row[sz - 1] != -1) ++sz;
+            if (i + sz > n) { ok = false; why = "household runs past n"; break; }
+            for (int pos = 0; pos < sz && ok; ++pos) {
+                const int64_t a = i + pos;
+                const int64_t *r = pop->households + a * W;
+                for (int j = 0; j < W; ++j) {
+                    const int64_t expect = j < sz - 1 ? i + j + (j >= pos ? 1 : 0) : -1;
+                    if (r[j] != expect) { ok = false; why = "row is not the contiguous all-pairs layout"; break; }
+                }
+                const int64_t ag = pop->age[a], db = pop->diabetes[a], hy = pop->hypertension[a];
+                if (ag < 0 || ag >= kAges || (db | hy) < 0 || db > 1 || hy > 1) { ok = false; why = "age/comorbidity out of range"; break; }
+                stat[(size_t)a] = pack_static((int)ag, (int)db, (int)hy, pos, sz);
+            }
+            i += sz;
+        }
+        if (!ok) { fail("seir_population.households: " + why + " (sample_households.py:344-349 emits contiguous households)"); break; }
+        std::vector<int32_t> goff(kAges + 1), gmem((size_t)n);
+        h->group_sizes.resize(kAges);
+        bool gok = pop->group_offsets[0] == 0 && pop->group_offsets[kAges] == n;
+        for (int a = 0; a < kAges && gok; ++a) {
+            goff[a] = (int32_t)pop->group_offsets[a];
+            h->group_sizes[a] = pop->group_offsets[a + 1] - pop->group_offsets[a];
+            if (h->group_sizes[a] < 0) gok = false;
+        }
+        goff[kAges] = (int32_t)n;
+        for (int a = 0; a < kAges && gok; ++a)
+            for (int64_t k = pop->group_offsets[a]; k < pop->group_offsets[a + 1]; ++k) {
+                const int64_t m = pop->group_members[k];
+                if (m < 0 || m >= n || pop->age[m] != a) { gok = false; break; }
+                gmem[(size_t)k] = (int32_t)m;
+            }
+        if (!gok) { fail("seir_population.group_offsets/group_members do not partition the agents by age"); break; }
+        h->p_hh_scalar = pop->p_infect_household[0];
+        h->p_hh_uniform = true;
+        for (int64_t i = 1; i < n; ++i)
+            if (pop->p_infect_household[i] != h->p_hh_scalar) { h->p_hh_uniform = false; break; }
+
+        cudaError_t e;
+#define CKB(call) if ((e = (call)) != cudaSuccess) { fail(std::string(#call " failed: ") + cudaGetErrorString(e)); break; }
+        CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CKB(cudaEventCreate(&h->ev0)); CKB(cudaEventCreate(&h->ev1)); CKB(cudaEventCreate(&h->ev2));
+        CKB(h->stat.alloc((size_t)h->n_pad));
+        CKB(cudaMemcpy(h->stat.p, stat.data(), (size_t)h->n_pad * 2, cudaMemcpyHostToDevice));
+        CKB(h->grp_off.alloc(kAges + 1));
+        CKB(cudaMemcpy(h->grp_off.p, goff.data(), (kAges + 1) * 4, cudaMemcpyHostToDevice));
+        CKB(h->grp_members.alloc((size_t)n));
+        CKB(cudaMemcpy(h->grp_members.p, gmem.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        if (!h->p_hh_uniform) {
+            CKB(h->p_hh.alloc((size_t)n));
+            CKB(cudaMemcpy(h->p_hh.p, pop->p_infect_household, (size_t)n * 8, cudaMemcpyHostToDevice));
+        }
+        const size_t R = (size_t)n_replicas, np = (size_t)h->n_pad;
+        CKB(h->inbox.alloc(R * np / 16));
+        CKB(h->winner.alloc(R * np));
+        CKB(h->rec.alloc(R * np));
+        CKB(h->home.alloc(R * np / 32));
+        CKB(cudaMemset(h->home.p, 0, R * np / 32 * 4));
+        CKB(h->seeds.alloc(R));
+        CKB(h->counters.alloc(R * 4));
+        CKB(h->barrier.alloc(1));
+        CKB(h->init_off.alloc(R + 1));
+#undef CKB
+        if (alloc_state(h)) break;
+        if (upload_tables(h, tables)) break;
+        // persistent grid: every CTA must be co-resident
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel, kThreads, 0) != cudaSuccess || occ < 1) {
+            fail("occupancy query failed for seir_persistent_kernel");
+            break;
+        }
+        h->occ = occ;
+        h->grid = h->sms * occ;
+        fill_ctx(h);
+        rc = 0;
+    } while (0);
+    if (rc) { seir_destroy(h); return 1; }
+    *out = h;
+    return 0;
+}
+
+int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables *tables)
+{
+    if (!h) return fail("handle is NULL");
+    CK(cudaSetDevice(h->device));
+    if (params) {
+        if (check_params(params, h->n)) return 1;
+        h->prm = *params;
+        if (params->T > h->T_alloc && alloc_state(h)) return 1;
+    }
+    if (tables && upload_tables(h, tables)) return 1;
+    fill_ctx(h);
+    return 0;
+}
+
+int seir_run(seir_handle *h, const seir_replica *reps)
+{
+    if (!h || !reps) return fail("seir_run: NULL argument");
+    CK(cudaSetDevice(h->device));
+    if (h->prm.mode == SEIR_MODE_REPLAY && !h->replay_tables) return fail("replay mode needs enlam_pre/enlam_post tables");
+    const int R = h->n_rep;
+    const int64_t n = h->n;
+    // ---- per-run host inputs -> device
+    std::vector<uint64_t> seeds(R);
+    std::vector<int64_t> off(R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+        seeds[r] = reps[r].seed;
+        if (reps[r].n_initial < 0 || (reps[r].n_initial > 0 && !reps[r].initial_infected)) return fail("seir_replica.initial_infected is invalid");
+        off[r + 1] = off[r] + reps[r].n_initial;
+    }
+    std::vector<int32_t> ids((size_t)off[R]);
+    for (int r = 0; r < R; ++r)
+        for (int64_t k = 0; k < reps[r].n_initial; ++k) {
+            const int64_t a = reps[r].initial_infected[k];
+            if (a < 0 || a >= n) return fail("seir_replica.initial_infected holds an id outside [0, n)");
+            ids[(size_t)(off[r] + k)] = (int32_t)a;
+        }
+    CK(h->init_ids.alloc(ids.size()));
+    CK(cudaMemcpyAsync(h->seeds.p, seeds.data(), R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->init_off.p, off.data(), (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (!ids.empty()) CK(cudaMemcpyAsync(h->init_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    const int64_t n_words = h->n_pad / 32;
+    for (int r = 0; r < R; ++r) {
+        uint32_t *bm = h->home.p + (size_t)r * n_words;
+        if (reps[r].home_real) {
+            CK(h->stage_u8.alloc((size_t)n));
+            CK(cudaMemcpyAsync(h->stage_u8.p, reps[r].home_real, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+            seir_pack_home_kernel<<<h->sms * 4, 256, 0, h->stream>>>(h->stage_u8.p, bm, n, n_words);
+            CK(cudaStreamSynchronize(h->stream));  // the borrowed host buffer / staging is reused per replica
+        } else {
+            CK(cudaMemsetAsync(bm, 0, (size_t)n_words * 4, h->stream));
+        }
+    }
+    fill_ctx(h);
+    h->launches = 0;
+    // ---- init + day loop, timed on the launching stream
+    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaMemsetAsync(h->tally.p, 0, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, h->stream));
+    CK(cudaMemsetAsync(h->counters.p, 0, (size_t)R * 4 * 8, h->stream));
+    CK(cudaMemsetAsync(h->barrier.p, 0, 4, h->stream));
+    seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
+    ++h->launches;
+    if (!ids.empty()) {
+        dim3 g(32, R);
+        seir_init_infected_kernel<<<g, 128, 0, h->stream>>>(h->cx, h->init_ids.p, h->init_off.p);
+        ++h->launches;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    if (h->prm.launch == SEIR_LAUNCH_PERSISTENT) {
+        void *args[] = {&h->cx};
+        CK(cudaLaunchCooperativeKernel((const void *)seir_persistent_kernel, dim3(h->grid), dim3(kThreads), args, 0, h->stream));
+        ++h->launches;
+    } else {
+        for (int t = 1; t <= h->prm.T; ++t) {
+            seir_day_kernel<<<h->grid, kThreads, 0, h->stream>>>(h->cx, t);
+            ++h->launches;
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev2, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->loop_ms, h->ev1, h->ev2));
+    CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev2));
+    return 0;
+}
+
+int seir_last_run_ms(seir_handle *h, float *day_loop_ms, float *total_ms)
+{
+    if (!h) return fail("handle is NULL");
+    if (day_loop_ms) *day_loop_ms = h->loop_ms;
+    if (total_ms) *total_ms = h->total_ms;
+    return 0;
+}
+
+int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
+{
+    if (!h || !out) return fail("seir_get_tallies: NULL argument");
+    if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    CK(cudaSetDevice(h->device));
+    const int T = h->prm.T;
+    const size_t per = (size_t)T * TAL_ROWS * kAges;
+    std::vector<uint32_t> raw(per);
+    CK(cudaMemcpy(raw.data(), h->tally.p + (size_t)replica * per, per * 4, cudaMemcpyDeviceToHost));
+    // planes in the order of seir_individual.py:392: S,E,Mild,Documented,Severe,Critical,R,D,Q
+    std::vector<int64_t> cumE(kAges, 0), cumR(kAges, 0), cumD(kAges, 0), cumDoc(kAges, 0);
+    for (int t = 0; t < T; ++t) {
+        const uint32_t *d = raw.data() + (size_t)t * TAL_ROWS * kAges;
+        int64_t *o = out + (size_t)t * SEIR_N_TALLY * kAges;
+        for (int a = 0; a < kAges; ++a) {
+            cumE[a] += d[TAL_NEW_E * kAges + a];
+            cumR[a] += d[TAL_NEW_R * kAges + a];
+            cumD[a] += d[TAL_NEW_D * kAges + a];
+            cumDoc[a] += d[TAL_NEW_DOC * kAges + a];
+            o[0 * kAges + a] = h->group_sizes[a] - cumE[a];
+            o[1 * kAges + a] = d[TAL_E * kAges + a];
+            o[2 * kAges + a] = d[TAL_MILD * kAges + a];
+            o[3 * kAges + a] = cumDoc[a];
+            o[4 * kAges + a] = d[TAL_SEV * kAges + a];
+            o[5 * kAges + a] = d[TAL_CRIT * kAges + a];
+            o[6 * kAges + a] = cumR[a];
+            o[7 * kAges + a] = cumD[a];
+            o[8 * kAges + a] = d[TAL_QACT * kAges + a];
+        }
+    }
+    return 0;
+}
+
+int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out)
+{
+    if (!h || !out) return fail("seir_get_agent_vector: NULL argument");
+    if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    if (which < 0 || which >= SEIR_VEC_COUNT) return fail("vector id out of range");
+    CK(cudaSetDevice(h->device));
+    CK(h->stage_d.alloc((size_t)h->n));
+    seir_agent_vector_kernel<<<h->sms * 4, 256, 0, h->stream>>>(h->cx, replica, which, h->stage_d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->stage_d.p, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uint8_t *out)
+{
+    if (!h || !out) return fail("seir_get_history: NULL argument");
+    if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    if (which < 0 || which > SEIR_H_PACKED) return fail("history plane out of range");
+    if (t0 < 0 || t1 > h->prm.T || t0 > t1) return fail("day range out of bounds");
+    CK(cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    int rows_per = (int)((int64_t)(256ll << 20) / (n > 0 ? n : 1));
+    if (rows_per < 1) rows_per = 1;
+    CK(h->stage_u8.alloc((size_t)rows_per * n > (size_t)n ? (size_t)rows_per * n : (size_t)n));
+    const uint8_t *base = h->hist.p + (size_t)replica * h->prm.T * h->n_pad;
+    for (int t = t0; t < t1; t += rows_per) {
+        const int nr = t1 - t < rows_per ? t1 - t : rows_per;
+        seir_history_plane_kernel<<<h->sms * 8, 256, 0, h->stream>>>(base + (size_t)t * h->n_pad, n, h->n_pad, nr, which, h->stage_u8.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out + (size_t)(t - t0) * n, h->stage_u8.p, (size_t)nr * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
+{
+    if (!h || !out4) return fail("seir_get_counters: NULL argument");
+    if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    CK(cudaSetDevice(h->device));
+    unsigned long long c[4];
+    CK(cudaMemcpy(c, h->counters.p + (size_t)replica * 4, sizeof c, cudaMemcpyDeviceToHost));
+    out4[0] = h->launches; out4[1] = (int64_t)c[1]; out4[2] = (int64_t)c[2]; out4[3] = (int64_t)c[3];
+    return 0;
+}
+
+void seir_destroy(seir_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->stat.release(); h->grp_off.release(); h->grp_members.release(); h->init_ids.release(); h->init_off.release();
+    h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release();
+    h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
+    h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int seir_probe_draws(int device, uint64_t seed, int64_t m, double mean, double mu, double sigma, double enlam,
+                     double *exp_days_out, double *lognormal_out, int64_t *poisson_out, double *log_out,
+                     const double *log_in)
+{
+    if (m < 1) return fail("m must be positive");
+    CK(cudaSetDevice(device));
+    DevBuf<double> a, b, c, d;
+    DevBuf<long long> p;
+    CK(a.alloc(m)); CK(b.alloc(m)); CK(c.alloc(m)); CK(d.alloc(m)); CK(p.alloc(m));
+    CK(cudaMemcpy(d.p, log_in, m * 8, cudaMemcpyHostToDevice));
+    seir_probe_kernel<<<256, 256>>>(seed, m, mean, mu, sigma, enlam, a.p, b.p, p.p, c.p, d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(exp_days_out, a.p, m * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lognormal_out, b.p, m * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(poisson_out, p.p, m * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(log_out, c.p, m * 8, cudaMemcpyDeviceToHost));
+    a.release(); b.release(); c.release(); d.release(); p.release();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""Lazy stand-ins for the nine bool[T, n] history arrays `run_model` returns (seir_individual.py:392).
+
+The reference materialises 9 x T x n bools on the host (5.4 GB at n = 10 M, T = 60).  Here the
+history stays on the device as ONE packed byte per agent-day; a `HistoryPlane` fetches only what is
+asked for.  It supports what the reference's drivers do with these arrays
+(run_simulation.py:448-460, simulate_agepolicies.py:617-631, parameter_sweep.py:556-603):
+`X.sum(axis=1)`, `X[-1]`, `X[t]`, `X[-1, mask]`, `np.logical_and(X[t], m)`, `np.asarray(X)`.
+"""
+import numpy as np
+
+
+class HistoryPlane:
+    __array_priority__ = 100
+
+    def __init__(self, engine, plane, replica=0):
+        self._e, self._plane, self._rep = engine, plane, replica
+        self.shape = (engine.T, engine.n)
+        self.dtype = np.dtype(np.bool_)
+        self.ndim = 2
+
+    def __len__(self):
+        return self.shape[0]
+
+    def _rows(self, t0, t1):
+        return self._e.history(self._plane, t0, t1, self._rep)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._rows(0, self.shape[0])
+        return a if dtype is None else a.astype(dtype)
+
+    def sum(self, axis=None, **kw):
+        """Per-day counts come from the per-age tallies fused into the day step -- no history read."""
+        per_day = self._e.tallies(self._rep)[:, _PLANE_INDEX[self._plane], :].sum(axis=1)
+        if axis == 1 or axis == -1:
+            return per_day
+        if axis is None:
+            return per_day.sum()
+        return np.asarray(self).sum(axis=axis, **kw)
+
+    def __getitem__(self, key):
+        T = self.shape[0]
+        if isinstance(key, tuple):
+            row, rest = key[0], key[1:]
+        else:
+            row, rest = key, ()
+        if isinstance(row, (int, np.integer)):
+            t = int(row) + (T if row < 0 else 0)
+            if not 0 <= t < T:
+                raise IndexError("day index out of range")
+            out = self._rows(t, t + 1)[0]
+        elif isinstance(row, slice):
+            idx = range(*row.indices(T))
+            if len(idx) == 0:
+                out = np.zeros((0, self.shape[1]), dtype=np.bool_)
+            elif idx.step == 1:
+                out = self._rows(idx.start, idx.stop)
+            else:
+                out = np.stack([self._rows(t, t + 1)[0] for t in idx])
+        else:
+            out = np.asarray(self)[row]
+        return out[rest] if rest else out
+
+    def __iter__(self):
+        for t in range(self.shape[0]):
+            yield self[t]
+
+    def __repr__(self):
+        return "HistoryPlane(%s, shape=%s, device-resident)" % (self._plane, self.shape)
+
+
+_PLANE_INDEX = {"S": 0, "E": 1, "Mild": 2, "Documented": 3, "Severe": 4, "Critical": 5, "R": 6, "D": 7, "Q": 8}

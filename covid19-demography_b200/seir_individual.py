@@ -1,0 +1,104 @@
+"""Drop-in replacement of the reference's `seir_individual` module for its hot path.
+
+Same two entry points, same positional arguments, same 20-tuple result
+(/root/reference/seir_individual.py:11 `run_complete_simulation`, :91 `run_model`, return at :392),
+so `run_simulation.py`, `simulate_agepolicies.py` and `parameter_sweep.py`-style drivers keep working
+with this directory ahead of the reference on `sys.path`.  The day loop (:231-390) runs as CUDA
+kernels on a B200 through libseir_b200.so; there is no CPU fallback.
+
+Differences a caller can see (DESIGN.md has the full list):
+  * the nine histories come back as lazy `HistoryPlane` objects over the device-resident packed
+    history (`np.asarray(X)` materialises the reference's bool[T, n]);
+  * draws inside the day loop are keyed Philox draws (include/seir_draws.h), not the reference's
+    single Mersenne-Twister stream, so trajectories agree with the reference in distribution,
+    not per seed; Home_real and initial_infected ARE the reference's for the same seed;
+  * contact tracing on the device is not implemented yet: a run in which the reference, as
+    compiled, would switch tracing on (1 <= t_tracing_start < T) raises
+    unless `SEIR_B200_TRACING=off` (or tracing="off") is given, which runs the paper's
+    no-tracing semantics.
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if os.path.dirname(_HERE) not in sys.path:
+    sys.path.insert(0, os.path.dirname(_HERE))
+
+from covid19_demography_b200 import engine as _engine  # noqa: E402
+from covid19_demography_b200 import tables as _tables  # noqa: E402
+from covid19_demography_b200.history import HistoryPlane  # noqa: E402
+
+OPTIONS = {
+    "mode": os.environ.get("SEIR_B200_MODE", "native"),          # "native" | "replay"
+    "launch": os.environ.get("SEIR_B200_LAUNCH", "persistent"),  # "persistent" | "per_day"
+    "tracing": os.environ.get("SEIR_B200_TRACING", "as_reference"),  # "as_reference" | "off"
+    "device": int(os.environ.get("SEIR_B200_DEVICE", "0")),
+}
+last_engine = None
+"""The Engine of the most recent run_model call (its histories stay valid while it is alive)."""
+
+
+def run_complete_simulation(seed, country, contact_matrix, p_mild_severe, p_severe_critical, p_critical_death,
+                            mean_time_to_isolate_factor, lockdown_factor_age, p_infect_household,
+                            fraction_stay_home, params, load_population=False):
+    """seir_individual.py:11-44: build or load the population, then `run_model`.
+
+    Keeps the side effect drivers rely on: `{country}_population_{n}.pickle` in the CWD holds
+    `(age, households, diabetes, hypertension, age_groups)` (:22, :39-41).
+    """
+    n = int(params['n'])
+    n_ages = int(params['n_ages'])
+    np.random.seed(seed)
+    fname = '{}_population_{}.pickle'.format(country, n)
+    if load_population:
+        print('loading')
+        with open(fname, 'rb') as f:
+            age, households, diabetes, hypertension, age_groups = pickle.load(f)
+    else:
+        from covid19_demography_b200 import population as _population
+        households, age = _population.sample_households(country, n)
+        age_groups = tuple([np.where(age == i)[0] for i in range(0, n_ages)])
+        diabetes, hypertension = _population.sample_joint_comorbidities(age, country)
+        with open(fname, 'wb') as f:
+            pickle.dump((age, households, diabetes, hypertension, age_groups), f)
+    print('starting simulation')
+    return run_model(seed, households, age, age_groups, diabetes, hypertension, contact_matrix, p_mild_severe,
+                     p_severe_critical, p_critical_death, mean_time_to_isolate_factor, lockdown_factor_age,
+                     p_infect_household, fraction_stay_home, params)
+
+
+def run_model(seed, households, age, age_groups, diabetes, hypertension, contact_matrix, p_mild_severe,
+              p_severe_critical, p_critical_death, mean_time_to_isolate_factor, lockdown_factor_age,
+              p_infect_household, fraction_stay_home, params, **options):
+    """seir_individual.py:90-392 on the GPU.  Returns the reference's 20-tuple:
+    S, E, Mild, Documented, Severe, Critical, R, D, Q (HistoryPlane, bool[T, n] on demand),
+    num_infected_by, time_documented, time_to_activation, time_to_death, time_to_recovery,
+    time_critical, time_exposed, num_infected_asympt, age, time_infected, time_to_severe."""
+    global last_engine
+    opt = dict(OPTIONS)
+    opt.update(options)
+    p = _tables.params_to_dict(params)
+    n, T = int(p["n"]), int(p["T"])
+    age = np.asarray(age)
+    if len(age_groups) != _tables.N_AGES or int(p["n_ages"]) != _tables.N_AGES:
+        raise ValueError("n_ages must be %d" % _tables.N_AGES)
+    tracing_enabled = 0 if opt["tracing"] == "off" else 1
+    group_sizes = np.array([len(g) for g in age_groups], dtype=np.int64)
+    tb = _tables.build_tables(contact_matrix, group_sizes, p, mean_time_to_isolate_factor, p_mild_severe,
+                              p_severe_critical, p_critical_death, with_replay=(opt["mode"] == "replay"))
+    home_real, initial_infected = _tables.prologue(seed, age_groups, n, fraction_stay_home,
+                                                   p["initial_infected_fraction"])
+    eng = _engine.Engine(p, households, age, age_groups, diabetes, hypertension, p_infect_household, tb,
+                         n_replicas=1, device=opt["device"], mode=opt["mode"], launch=opt["launch"],
+                         tracing_enabled=tracing_enabled)
+    print('run_model')
+    eng.run([seed], [home_real], [initial_infected])
+    last_engine = eng
+    planes = tuple(HistoryPlane(eng, k) for k in _engine.PLANES_IN_ORDER)
+    v = eng.agent_vector
+    return planes + (v("num_infected_by"), v("time_documented"), v("time_to_activation"), v("time_to_death"),
+                     v("time_to_recovery"), v("time_critical"), v("time_exposed"), v("num_infected_asympt"),
+                     age, v("time_infected"), v("time_to_severe"))

@@ -1,0 +1,107 @@
+"""Host-side construction of the draw tables the kernels consume (include/seir_b200.h, seir_tables).
+
+Everything here is plain NumPy run once per parameter set; the kernels (and the CPU oracle in the
+parity tests) only ever COMPARE against these doubles, so no transcendental is evaluated on the
+device for them.
+"""
+import numpy as np
+
+N_AGES = 101
+
+PARAM_KEYS = (
+    "n", "n_ages", "T", "initial_infected_fraction", "t_lockdown", "lockdown_factor", "t_stayhome_start",
+    "t_tracing_start", "contact_tracing", "p_trace_household", "p_trace_outside", "p_documented_in_mild",
+    "p_infect_given_contact", "asymptomatic_transmissibility", "mean_time_to_isolate",
+    "mean_time_to_isolate_asympt", "mean_time_to_severe", "mean_time_mild_recovery", "mean_time_to_critical",
+    "mean_time_severe_recovery", "mean_time_critical_recovery", "mean_time_to_death",
+    "time_to_activation_mean", "time_to_activation_std")
+"""The 24 keys `run_model` reads (seir_individual.py:135-158)."""
+
+
+def params_to_dict(params):
+    """Accept a numba.typed.Dict or any Mapping[str, float]."""
+    out = {}
+    for k in PARAM_KEYS:
+        try:
+            out[k] = float(params[k])
+        except KeyError:
+            raise KeyError("params is missing %r (seir_individual.py:135-158)" % k)
+    return out
+
+
+def isolation_factor_lut(mean_time_to_isolate_factor, n_ages=N_AGES):
+    """`get_isolation_factor` (seir_individual.py:46-51) for every age: first matching row wins, else 1."""
+    rows = np.asarray(mean_time_to_isolate_factor)
+    lut = np.ones(n_ages, dtype=np.float64)
+    for age in range(n_ages):
+        for lo, hi, f in rows:
+            if age >= lo and age <= hi:
+                lut[age] = float(f)
+                break
+    return lut
+
+
+def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_factor, p_mild_severe,
+                 p_severe_critical, p_critical_death, with_replay=True):
+    """Returns a dict of C-contiguous float64 arrays keyed like the fields of `seir_tables`."""
+    p = params
+    C_pre = np.ascontiguousarray(contact_matrix, dtype=np.float64)
+    if C_pre.shape != (N_AGES, N_AGES):
+        raise ValueError("contact_matrix must be %dx%d" % (N_AGES, N_AGES))
+    if (C_pre < 0).any():
+        raise ValueError("poisson(): lambda < 0")  # numba/cpython/randomimpl.py:1680-1681
+    C_post = C_pre / p["lockdown_factor"]  # seir_individual.py:240
+    nonempty = np.asarray(group_sizes) > 0  # :368-369 skips empty age groups
+    lut = isolation_factor_lut(mean_time_to_isolate_factor)
+    nat_enlam = np.empty((2, N_AGES, 2), dtype=np.float64)
+    for ph, C in enumerate((C_pre, C_post)):
+        rowsum = np.where(nonempty[None, :], C, 0.0).sum(axis=1)
+        for w, weight in enumerate((1.0, p["asymptomatic_transmissibility"])):
+            nat_enlam[ph, :, w] = np.exp(-(p["p_infect_given_contact"] * weight) * rowsum)
+    Cz = np.where(nonempty[None, :], C_pre, 0.0)
+    cdf = np.ones((N_AGES, N_AGES), dtype=np.float64)
+    for a in range(N_AGES):
+        tot = Cz[a].sum()
+        if tot > 0:
+            c = np.cumsum(Cz[a]) / tot
+            last = np.nonzero(Cz[a] > 0)[0][-1]
+            c[last:] = 1.0
+            cdf[a] = c
+    out = {
+        "p_mild_severe": np.ascontiguousarray(p_mild_severe, dtype=np.float64).reshape(N_AGES, 2, 2),
+        "p_severe_critical": np.ascontiguousarray(p_severe_critical, dtype=np.float64).reshape(N_AGES, 2, 2),
+        "p_critical_death": np.ascontiguousarray(p_critical_death, dtype=np.float64).reshape(N_AGES, 2, 2),
+        "iso_mean": np.ascontiguousarray(p["mean_time_to_isolate"] * lut),           # :270
+        "iso_asympt_mean": np.ascontiguousarray(p["mean_time_to_isolate_asympt"] * lut),  # :352
+        "nat_enlam": nat_enlam,
+        "nat_cdf": cdf,
+        "enlam_pre": np.exp(-C_pre) if with_replay else None,
+        "enlam_post": np.exp(-C_post) if with_replay else None,
+    }
+    return out
+
+
+def prologue(seed, age_groups, n, fraction_stay_home, initial_infected_fraction):
+    """Host restatement of the run_model prologue (seir_individual.py:163,176-187).
+
+    The reference seeds numba's MT19937 with `seed` and draws, in this order, one
+    `np.random.choice(matches, k, replace=False)` per non-empty age and one
+    `np.random.choice(n, k, replace=False)`.  numba implements both as a Fisher-Yates shuffle with
+    masked-rejection `randint` (numba/cpython/randomimpl.py:1927-1946, 2084-2100), which is exactly
+    NumPy's legacy `RandomState.permutation`; so the SAME Home_real and initial_infected as the
+    reference come out of `np.random.RandomState(seed)`.
+    Returns (home_real bool[n], initial_infected int64[k]).
+    """
+    rs = np.random.RandomState(int(seed) & 0xFFFFFFFF)
+    home = np.zeros(n, dtype=np.bool_)
+    fsh = np.asarray(fraction_stay_home, dtype=np.float64)
+    for a, matches in enumerate(age_groups):
+        m = len(matches)
+        if m > 0:
+            perm = rs.permutation(np.asarray(matches))
+            k = int(fsh[a] * m)
+            if k > 0:
+                home[perm[:k]] = True
+    k0 = int(initial_infected_fraction * n)
+    init = rs.permutation(n)[:k0].astype(np.int64)
+    return home, init

@@ -1,0 +1,168 @@
+/*
+ * seir_b200.h -- C ABI of libseir_b200.so, the B200 (sm_100a) implementation of the daily
+ * agent-stepping path of the COVID19-Demography individual-level SEIR simulator.
+ *
+ * Drop-in boundary: the reference's `run_model(seed, households, age, age_groups, diabetes,
+ * hypertension, contact_matrix, p_mild_severe, p_severe_critical, p_critical_death,
+ * mean_time_to_isolate_factor, lockdown_factor_age, p_infect_household, fraction_stay_home, params)`
+ * at /root/reference/seir_individual.py:90-392, returning the 20-tuple of :392.  The reference has
+ * no FFI of its own (it is a numba function); the binding a maintainer adds is the ctypes stub in
+ * INTEGRATION.md / covid19-demography_b200/engine.py.
+ *
+ * Everything here is plain C: pointers, sizes, POD structs.  Host arrays are BORROWED for the
+ * duration of the call; outputs go to CALLER-allocated buffers; device memory belongs to the
+ * handle.  Every function returns 0 on success, non-zero on error (seir_last_error() gives the
+ * thread-local message).  There is no CPU fallback: without a CUDA device seir_create fails.
+ */
+#ifndef SEIR_B200_H
+#define SEIR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEIR_N_AGES 101            /* seir_individual.py:153, run_simulation.py:17 */
+#define SEIR_N_TALLY 9             /* S,E,Mild,Documented,Severe,Critical,R,D,Q -- order of :392 */
+#define SEIR_MODE_NATIVE 0         /* community: Poisson(kept contacts) + row-CDF contact age   */
+#define SEIR_MODE_REPLAY 1         /* community: 101 Poisson draws per sender-day, as :367-374  */
+#define SEIR_LAUNCH_PERSISTENT 0   /* one cooperative kernel over all days, one grid barrier per day */
+#define SEIR_LAUNCH_PER_DAY 1      /* one kernel launch per day (debug / comparison)            */
+
+/* scalar parameters: the `params` dict of seir_individual.py:135-158 */
+typedef struct {
+    int64_t n;                 /* params['n']                                   :152 */
+    int32_t T;                 /* params['T']                                   :147 */
+    int32_t t_lockdown;        /* params['t_lockdown']                          :149 */
+    int32_t t_stayhome_start;  /* params['t_stayhome_start']                    :158 */
+    int32_t t_tracing_start;   /* params['t_tracing_start']                     :157 */
+    int32_t tracing_enabled;   /* value of `tracing_enabled` at :241 (the reference as compiled: 1).
+                                  Tracing on device is not implemented yet: seir_run refuses runs in
+                                  which tracing would switch on (tracing_enabled && 1 <= t_tracing_start < T) */
+    int32_t mode;              /* SEIR_MODE_*                                         */
+    int32_t launch;            /* SEIR_LAUNCH_*                                       */
+    int32_t reserved0;
+    double p_documented_in_mild;          /* :143 */
+    double p_infect_given_contact;        /* :146 */
+    double asymptomatic_transmissibility; /* :145 */
+    double mean_time_to_severe;           /* :140 */
+    double mean_time_mild_recovery;       /* :141 */
+    double mean_time_to_critical;         /* :142 */
+    double mean_time_severe_recovery;     /* :139 */
+    double mean_time_critical_recovery;   /* :138 */
+    double mean_time_to_death;            /* :137 */
+    double time_to_activation_mean;       /* :135 */
+    double time_to_activation_std;        /* :136 */
+    double p_trace_household;             /* :156 (unused until tracing lands) */
+    double p_trace_outside;               /* :155 */
+} seir_params;
+
+/* static population: arguments households/age/age_groups/diabetes/hypertension of :91.
+ * Households must be the contiguous all-pairs layout both reference samplers emit
+ * (sample_households.py:344-349): agent i's row lists the other members of
+ * [i - pos, i - pos + size) in ascending order, -1 padded. */
+typedef struct {
+    int64_t n;
+    int32_t W;                          /* households.shape[1]                       */
+    int32_t reserved0;
+    const int64_t *households;          /* [n, W]                                    */
+    const int64_t *age;                 /* [n] in [0, 100]                           */
+    const int64_t *diabetes;            /* [n] in {0,1}                              */
+    const int64_t *hypertension;        /* [n] in {0,1}                              */
+    const int64_t *group_offsets;       /* [102]  CSR of the age_groups tuple (:36)  */
+    const int64_t *group_members;       /* [n]                                       */
+    const double *p_infect_household;   /* [n] (:108); a constant vector is detected and kept as a scalar */
+} seir_population;
+
+/* draw tables, computed by the host code (covid19-demography_b200/tables.py) */
+typedef struct {
+    const double *p_mild_severe;        /* [101,2,2]  :103 */
+    const double *p_severe_critical;    /* [101,2,2]  :104 */
+    const double *p_critical_death;     /* [101,2,2]  :105 */
+    const double *iso_mean;             /* [101] mean_time_to_isolate * get_isolation_factor(age)         :270 */
+    const double *iso_asympt_mean;      /* [101] mean_time_to_isolate_asympt * get_isolation_factor(age)  :352 */
+    const double *nat_enlam;            /* [2,101,2] exp(-p*w*rowsum) : phase (0 before lockdown, 1 after), age, w (0 symptomatic, 1 E) */
+    const double *nat_cdf;              /* [101,101] row CDF of the contact matrix over non-empty age groups */
+    const double *enlam_pre;            /* [101,101] exp(-C)                  (replay mode; may be NULL in native mode) */
+    const double *enlam_post;           /* [101,101] exp(-C/lockdown_factor)  (replay mode)                             */
+} seir_tables;
+
+/* per-run inputs (one per replica): the prologue of :176-187 is host code */
+typedef struct {
+    uint64_t seed;                      /* Philox key                                 */
+    const uint8_t *home_real;           /* [n] 0/1 shelter-in-place assignment, or NULL (nobody) */
+    const int64_t *initial_infected;    /* [n_initial] agent ids exposed at t=0 (:187)  */
+    int64_t n_initial;
+} seir_replica;
+
+/* per-agent output vectors, as doubles with the reference's sentinels (:200-218) */
+enum {
+    SEIR_VEC_NUM_INFECTED_BY = 0,
+    SEIR_VEC_TIME_DOCUMENTED = 1,
+    SEIR_VEC_TIME_TO_ACTIVATION = 2,
+    SEIR_VEC_TIME_TO_DEATH = 3,
+    SEIR_VEC_TIME_TO_RECOVERY = 4,
+    SEIR_VEC_TIME_CRITICAL = 5,
+    SEIR_VEC_TIME_EXPOSED = 6,
+    SEIR_VEC_NUM_INFECTED_ASYMPT = 7,
+    SEIR_VEC_TIME_INFECTED = 8,
+    SEIR_VEC_TIME_TO_SEVERE = 9,
+    /* not returned by the reference, exposed for parity checks */
+    SEIR_VEC_TIME_TO_ISOLATE = 10,
+    SEIR_VEC_TIME_SEVERE = 11,
+    SEIR_VEC_TIME_TO_CRITICAL = 12,
+    SEIR_VEC_NUM_INFECTED_OUTSIDE = 13,
+    SEIR_VEC_COUNT = 14
+};
+
+/* history planes for seir_get_history, in the order of the reference's return tuple (:392) */
+enum { SEIR_H_S = 0, SEIR_H_E, SEIR_H_MILD, SEIR_H_DOCUMENTED, SEIR_H_SEVERE, SEIR_H_CRITICAL,
+       SEIR_H_R, SEIR_H_D, SEIR_H_Q, SEIR_H_PACKED /* raw byte: bits0-2 compartment, bit3 Q, bit4 Documented */ };
+
+typedef struct seir_handle seir_handle;
+
+/* Upload the static population and tables; allocate state for n_replicas concurrent runs. */
+int seir_create(const seir_params *params, const seir_population *pop, const seir_tables *tables,
+                int n_replicas, int device, seir_handle **out);
+
+/* Replace the scalar parameters / tables (same population) before the next seir_run. */
+int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables *tables);
+
+/* Run all replicas for T days.  reps[n_replicas].  Blocking. */
+int seir_run(seir_handle *h, const seir_replica *reps);
+
+/* Device time of the last seir_run, CUDA events on the launching stream:
+ * *day_loop_ms = the day loop (persistent kernel or T-1 launches), *total_ms = init + day loop. */
+int seir_last_run_ms(seir_handle *h, float *day_loop_ms, float *total_ms);
+
+/* Per-day compartment counts by age, out[T][9][101] int64, planes in the order of :392
+ * (what the drivers compute with X.sum(axis=1) and the per-age-group masks). */
+int seir_get_tallies(seir_handle *h, int replica, int64_t *out);
+
+/* One per-agent vector, out[n] doubles. */
+int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out);
+
+/* History plane `which` for days [t0, t1), out[(t1-t0)*n] bytes (0/1, or the packed byte). */
+int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uint8_t *out);
+
+/* Counters of the last run: out[0]=kernels launched, out[1]=sum over days of active agents
+ * A(t-1) (E/Mild/Severe/Critical), out[2]=infections I (excluding the initial ones),
+ * out[3]=transmission hits (>= infections: same-day multiple hits count). */
+int seir_get_counters(seir_handle *h, int replica, int64_t *out4);
+
+void seir_destroy(seir_handle *h);
+const char *seir_last_error(void);
+int seir_device_count(void);
+/* library self-description (arch the kernels were compiled for, build flags) */
+const char *seir_build_info(void);
+
+/* draw-contract probes (device evaluation of include/seir_draws.h, for parity tests) */
+int seir_probe_draws(int device, uint64_t seed, int64_t m, double mean, double mu, double sigma, double enlam,
+                     double *exp_days_out, double *lognormal_out, int64_t *poisson_out, double *log_out,
+                     const double *log_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEIR_B200_H */

@@ -1,0 +1,124 @@
+"""-m gpu : the CUDA day step (through the C ABI, libseir_b200.so) against the CPU oracle under the
+SAME keyed Philox draws, bit-exact: nine histories, ten per-agent vectors, per-day per-age tallies.
+Populations / parameters come from the golden fixtures frozen from the reference."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["italy_default", "italy_seeded", "china_default", "italy_policy", "italy_fastiso", "italy_tracing"]
+
+
+def _compare(eng, tup, ex, c, T, replica=0):
+    packed = eng.history("packed", replica=replica)
+    want = util.pack_history(tup[:9])
+    if not np.array_equal(packed, want):
+        bad = np.argwhere(packed != want)
+        t, i = bad[0]
+        raise AssertionError("history differs at %d agent-days; first (t=%d, i=%d): gpu=%#x oracle=%#x"
+                             % (len(bad), t, i, packed[t, i], want[t, i]))
+    for k in util.VECS:
+        got = eng.agent_vector(k, replica=replica)
+        exp = tup[util.VEC_INDEX[k]]
+        assert np.array_equal(got, exp, equal_nan=True), "vector %s: %d mismatches" % (k, (got != exp).sum())
+    for k in ("time_to_isolate", "time_severe", "time_to_critical"):
+        got = eng.agent_vector(k, replica=replica)
+        exp = np.where(ex[k] >= 65535, np.inf, ex[k])  # the device record saturates never-reached times
+        assert np.array_equal(got, exp, equal_nan=True), "vector %s" % k
+    assert np.array_equal(eng.agent_vector("num_infected_by_outside", replica=replica),
+                          ex["num_infected_by_outside"].astype(np.float64))
+    tal = eng.tallies(replica)
+    assert np.array_equal(tal, util.tallies_from_history(tup[:9], c.age, T)), "per-day per-age tallies differ"
+    for k, name in enumerate(util.HIST):
+        plane = eng.history(name, replica=replica)
+        assert np.array_equal(plane, np.asarray(tup[k])), name
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_gpu_equals_keyed_oracle(gpu_engine_module, name, mode):
+    c = util.Case(name)
+    params = c.no_tracing_params()
+    tup, ex, home, init = c.keyed_oracle(mode, params)
+    util.check_invariants(tup, c.n, int(params["T"]))
+    eng = c.gpu_engine(gpu_engine_module, params, mode)
+    eng.run([c.seed], [home], [init])
+    _compare(eng, tup, ex, c, int(params["T"]))
+    cnt = eng.counters()
+    assert cnt["infections"] == int((tup[15] > 0).sum())
+    assert cnt["launches"] >= 2
+    eng.close()
+
+
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_per_day_launch_equals_persistent(gpu_engine_module, mode):
+    c = util.Case("italy_seeded")
+    params = c.no_tracing_params()
+    tup, ex, home, init = c.keyed_oracle(mode, params)
+    eng = c.gpu_engine(gpu_engine_module, params, mode, launch="per_day")
+    eng.run([c.seed], [home], [init])
+    _compare(eng, tup, ex, c, int(params["T"]))
+    assert eng.counters()["launches"] >= int(params["T"])
+    eng.close()
+
+
+def test_replicas_are_independent_runs(gpu_engine_module):
+    """Seed ensembles: R replicas in one launch == R single runs (no communication)."""
+    c = util.Case("italy_policy")
+    params = c.no_tracing_params()
+    seeds = [5, 6, 7]
+    eng = c.gpu_engine(gpu_engine_module, params, "native", n_replicas=len(seeds))
+    runs = [c.keyed_oracle("native", params, seed=s) for s in seeds]
+    eng.run(seeds, [r[2] for r in runs], [r[3] for r in runs])
+    for r, (tup, ex, _, _) in enumerate(runs):
+        _compare(eng, tup, ex, c, int(params["T"]), replica=r)
+    # rerun on the same handle: state is fully re-initialised
+    eng.run(seeds[::-1], [r[2] for r in runs[::-1]], [r[3] for r in runs[::-1]])
+    _compare(eng, runs[0][0], runs[0][1], c, int(params["T"]), replica=2)
+    eng.close()
+
+
+def test_draw_contract_on_device(gpu_engine_module):
+    """include/seir_draws.h evaluated by the device == by the host compiler, bit for bit."""
+    import ctypes as C
+    import oracle
+    m = 100000
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.random(m // 2), np.exp(rng.uniform(-700, 700, m - m // 2))])
+    e, l, p, g = gpu_engine_module.probe_draws(1234, m, 4.6, 1.621, 0.418, float(np.exp(-0.4)), x)
+    lib = oracle.lib()
+    y = np.empty(m)
+    lib.oracle_sd_log(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_int64(m))
+    assert np.array_equal(g, y)
+    lib.oracle_sd_lognormal_days(C.c_uint64(1234), C.c_int64(m), C.c_double(1.621), C.c_double(0.418),
+                                 C.c_void_p(y.ctypes.data))
+    assert np.array_equal(l, y)
+    yi = np.empty(m, dtype=np.int64)
+    lib.oracle_sd_poisson(C.c_uint64(1234), C.c_int64(m), C.c_double(float(np.exp(-0.4))), C.c_void_p(yi.ctypes.data))
+    assert np.array_equal(p, yi)
+    assert np.isfinite(e).all() and e.mean() == pytest.approx(4.6, rel=0.02)
+
+
+def test_tracing_is_refused_loudly(gpu_engine_module):
+    c = util.Case("italy_default")
+    with pytest.raises((RuntimeError, ValueError), match="tracing"):
+        c.gpu_engine(gpu_engine_module, c.params, "native")  # t_tracing_start = 37 < T, tracing as compiled
+    eng = c.gpu_engine(gpu_engine_module, c.params, "native", tracing_enabled=0)  # the paper's semantics
+    eng.close()
+
+
+def test_bad_inputs_raise(gpu_engine_module):
+    c = util.Case("italy_default")
+    params = c.no_tracing_params()
+    hh = c.households.copy()
+    hh[0, 0] = 7  # break the contiguous layout
+    c2 = util.Case("italy_default")
+    c2.households = hh
+    with pytest.raises((RuntimeError, ValueError), match="contiguous"):
+        c2.gpu_engine(gpu_engine_module, params, "native")
+    eng = c.gpu_engine(gpu_engine_module, params, "native")
+    with pytest.raises((RuntimeError, ValueError)):
+        eng.run([0], [None], [np.array([c.n + 5])])
+    eng.close()

@@ -1,0 +1,41 @@
+"""Build-container only: the oracle against the reference run LIVE (numba), beyond the frozen cases."""
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference is not present on this box")
+
+
+def _numba_ok():
+    try:
+        import numba  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _numba_ok(), reason="numba missing")
+def test_oracle_equals_live_reference_new_seed():
+    n = 2500
+    ns = ref_shim.driver_namespace(n, "Italy")
+    ref = ref_shim.load()
+    params = ns["params"]
+    params["initial_infected_fraction"] = 0.004
+    args = (ns["contact_matrix"], ns["p_mild_severe"], ns["p_severe_critical"], ns["p_critical_death"],
+            ns["mean_time_to_isolate_factor"], ns["lockdown_factor_age"], ns["p_infect_household"],
+            ns["fraction_stay_home"])
+    out = ref.run_complete_simulation(11, "Italy", *args, params, False)
+    age, households, diabetes, hypertension, age_groups = pickle.load(open("Italy_population_%d.pickle" % n, "rb"))
+    tup, _ = oracle.run_model(11, households, age, age_groups, diabetes, hypertension, *args, dict(params),
+                              provider="mt", tracing_enabled=1)
+    for k, a, b in zip(oracle.OUTPUT_NAMES, out, tup):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
+    # params['contact_tracing'] = 1 gives the same run (tracing is on as compiled)
+    params["contact_tracing"] = 1.0
+    out2 = ref.run_model(11, households, age, age_groups, diabetes, hypertension, *args, params)
+    for k, a, b in zip(oracle.OUTPUT_NAMES, out, out2):
+        assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
