@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- agent-days/s of the daily agent-stepping path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A "step" is ONE full simulation: the C2 workload of BASELINE.json/SURVEY.md section 8 -- n = 10 M agents
+(synthetic Lombardy-like population), T = 60 days, Italy contact matrix and severity tables,
+5 initial cases, lockdown on day 46 (/10), tracing never switching on -- i.e. n*(T-1) = 5.9e8
+agent-days.  With N > 1 (launched under torchrun, one rank per GPU) every rank runs its own seed of
+the same workload (seed ensembles need no communication): weak scaling.
+
+value      device time of the whole run (state init + day loop), CUDA events on the launching stream,
+           population and tables already resident in HBM; max over ranks.
+e2e        the same through the C ABI with HOST buffers: per-run inputs (Home_real, initial cases,
+           seed) copied from pinned host memory, the [T,9,101] tallies and counters read back, wall clock.
+roofline   seir_persistent_kernel (one launch = the whole day loop) against the measured HBM peak,
+           with the ALGORITHMIC bytes of SURVEY.md section 8d: sum_t 2n + 16 A(t-1) + 64 I(t).
+cpu_baseline  the CPU oracle (oracle/oracle_seir.c, provider "mt": the reference's algorithm and
+           Mersenne-Twister stream, bit-identical to the reference) on one host core, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_italy_default.npz")
+METRIC = "agent_days_per_sec"
+UNIT = "agent-days/s"
+
+
+def workload_params(n, T=60):
+    """C2 parameters: run_simulation.py:52-170 (Italy), as frozen in the golden fixture."""
+    fx = np.load(GOLDEN)
+    p = dict(zip(fx["param_keys"].tolist(), [float(v) for v in fx["param_vals"]]))
+    p["n"] = float(n)
+    p["T"] = float(T)
+    p["initial_infected_fraction"] = 5.0 / n          # run_simulation.py:66
+    p["t_tracing_start"] = 1.0e6                      # tier-1 semantics: tracing never switches on
+    tabs = {k: fx[k] for k in ("contact_matrix", "p_mild_severe", "p_severe_critical", "p_critical_death",
+                               "mean_time_to_isolate_factor", "lockdown_factor_age")}
+    tabs["p_infect_household"] = float(fx["p_infect_household_scalar"])
+    return p, tabs
+
+
+def algorithmic_bytes(tal, n):
+    """B_alg = sum_{t=1}^{T-1} 2 n + 16 A(t-1) + 64 I(t), from the run's own tallies."""
+    active = tal[:, [1, 2, 4, 5], :].sum(axis=(1, 2))          # E + Mild + Severe + Critical per day
+    S = tal[:, 0, :].sum(axis=1)
+    new_inf = S[:-1] - S[1:]
+    T = tal.shape[0]
+    return float(2.0 * n * (T - 1) + 16.0 * active[:-1].sum() + 64.0 * new_inf.sum()), int(active[:-1].sum()), int(new_inf.sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.stop = False
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def finish(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- CPU legs (oracle)
+_W = {}
+
+
+def _cpu_worker_init(n_sample, T):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle  # test/bench infrastructure: the reference's algorithm restated in C
+    from covid19_demography_b200 import population
+    p, tabs = workload_params(n_sample, T)
+    hh, age, diab, hyp, groups = population.synthetic_population(n_sample, seed=1)
+    _W.update(oracle=oracle, p=p, tabs=tabs, pop=(hh, age, groups, diab, hyp), n=n_sample, T=T)
+    oracle.lib()
+
+
+def _cpu_worker_run(seed):
+    o, p, tabs = _W["oracle"], _W["p"], _W["tabs"]
+    hh, age, groups, diab, hyp = _W["pop"]
+    n = _W["n"]
+    t0 = time.perf_counter()
+    o.run_model(seed, hh, age, groups, diab, hyp, tabs["contact_matrix"], tabs["p_mild_severe"],
+                tabs["p_severe_critical"], tabs["p_critical_death"], tabs["mean_time_to_isolate_factor"],
+                tabs["lockdown_factor_age"], np.full(n, tabs["p_infect_household"]), np.zeros(101), p,
+                provider="mt", tracing_enabled=1)
+    return time.perf_counter() - t0
+
+
+def _mem_available():
+    try:
+        return int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        return 16 << 30
+
+
+def _bytes_per_run(n, T):
+    return int(n * (9 * T + 400 + 200 + 6 * 8 + 60) * 1.15)
+
+
+def cpu_baseline_single(n_sample, T):
+    if n_sample <= 0:  # full C2 size when the host has the memory (about 12 GB), else a 2 M-agent sample
+        n_sample = 10_000_000 if _mem_available() > 2 * _bytes_per_run(10_000_000, T) else 2_000_000
+    _cpu_worker_init(n_sample, T)
+    dt = _cpu_worker_run(1)
+    return {"value": n_sample * (T - 1) / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/oracle_seir.c provider=mt (reference algorithm + MT19937 stream), one run of "
+                      "n=%d agents, T=%d, C2 parameters, %.1f s" % (n_sample, T, dt)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU algorithm on all host cores (independent seeds in
+    separate processes: the reference's SLURM-array mode, job.parameter_sweep.sh)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    T = 60
+    n_sample = args.cpu_sample if args.cpu_sample > 0 else 10_000_000  # the full C2 population per run
+    cores = len(os.sched_getaffinity(0))
+    workers = max(1, min(cores, int(_mem_available() * 0.6 / _bytes_per_run(n_sample, T)), args.cpu_workers or 32))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(n_sample, T)) as pool:
+        # (the pool initializer already touched the library and built the population; the warm-up
+        #  steps page the output buffers in once and are not timed)
+        for w in range(min(args.warmup, 1)):
+            pool.map(_cpu_worker_run, range(workers))
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_cpu_worker_run, [1000 + k * workers + j for j in range(workers)])
+        dt = time.perf_counter() - t0
+    value = workers * n_sample * (T - 1) * args.steps / dt
+    sample = ("oracle port of the reference (MT19937 stream, bit-identical to the reference's run_model); each step = "
+              "%d concurrent single-threaded runs of n=%d agents, T=%d, C2 parameters" % (workers, n_sample, T))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": "C2 Lombardy-like 10M agents, T=60, lockdown day 46 (/10), single seed per GPU",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from covid19_demography_b200 import engine, population, tables
+
+    n, T = args.n, 60
+    p, tabs = workload_params(n, T)
+    hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
+    gs = np.array([len(g) for g in groups])
+    tb = tables.build_tables(tabs["contact_matrix"], gs, tables.params_to_dict(p), tabs["mean_time_to_isolate_factor"],
+                             tabs["p_mild_severe"], tabs["p_severe_critical"], tabs["p_critical_death"],
+                             with_replay=(args.mode == "replay"))
+    t0 = time.perf_counter()
+    eng = engine.Engine(p, hh, age, groups, diab, hyp, np.full(n, tabs["p_infect_household"]), tb,
+                        n_replicas=args.replicas, device=local, mode=args.mode, launch=args.launch)
+    create_s = time.perf_counter() - t0
+    del hh
+    R = args.replicas
+    n_init = int(p["initial_infected_fraction"] * n)
+    rng = np.random.default_rng(100 + rank)
+    home = engine.pin(np.zeros(n, dtype=np.uint8))  # fraction_stay_home = 0 in C2 (run_simulation.py:53-54)
+
+    def inputs(step):
+        seeds = [(rank * 100003 + step) * 64 + r for r in range(R)]
+        init = [rng.choice(n, size=n_init, replace=False).astype(np.int64) for _ in range(R)]
+        return seeds, [home] * R, init
+
+    def sync_all():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    flush = None
+    if args.flush_l2:
+        import ctypes as C
+        import torch
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local)
+
+    for w in range(args.warmup):
+        eng.run(*inputs(-1 - w))
+    # ---- device-timed region
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    dev_ms = loop_ms = 0.0
+    launches = 0
+    wall0 = time.perf_counter()
+    last_tal = None
+    for k in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+            import torch
+            torch.cuda.synchronize()
+        eng.run(*inputs(k))
+        a, b = eng.last_run_ms()
+        loop_ms += a
+        dev_ms += b
+        launches += eng.counters()["launches"]
+    sync_all()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.finish()
+    last_tal = eng.tallies(0)
+    # ---- end to end through the C ABI with host buffers (wall clock)
+    ins = [inputs(10000 + k) for k in range(args.steps)]
+    for _, _, init in ins:
+        for a in init:
+            engine.pin(a)
+    sync_all()
+    e0 = time.perf_counter()
+    for k in range(args.steps):
+        eng.run(*ins[k])
+        for r in range(R):
+            eng.tallies(r)
+    sync_all()
+    e2e_s = time.perf_counter() - e0
+    h2d = R * (n + 8 * n_init + 8)
+    d2h = R * (T * 9 * 101 * 4)
+
+    agent_days_step = float(n) * (T - 1) * R
+    if dist is not None:
+        import torch
+        tt = torch.tensor([dev_ms, e2e_s, loop_ms], dtype=torch.float64, device="cuda:%d" % local)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, loop_ms = [float(x) for x in tt.tolist()]
+        ll = torch.tensor([launches], dtype=torch.int64, device="cuda:%d" % local)
+        dist.all_reduce(ll)
+        launches = int(ll.item())
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        balg, a_sum, i_sum = algorithmic_bytes(last_tal, n)
+        kern_s = loop_ms / args.steps / 1e3
+        achieved = balg * R / kern_s / 1e9
+        line = {
+            "metric": METRIC, "value": world * agent_days_step * args.steps / (dev_ms / 1e3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": {"workload": "C2 Lombardy-like %d agents, T=%d, lockdown day 46 (/10), %d seed(s) per GPU, "
+                                   "tracing never switches on" % (n, T, R),
+                       "mode": args.mode, "launch": args.launch, "replicas_per_gpu": R,
+                       "l2": ("explicit 256 MiB flush between steps" if args.flush_l2 else
+                              "per-run working set %.2f GB (history %d x %d B + state) > 126 MB L2; state re-initialised every step"
+                              % ((T * n + 46 * n) / 1e9, T, n)),
+                       "day_loop_ms_per_step": loop_ms / args.steps, "engine_create_s": create_s,
+                       "sim_runs_per_hour_device": 3600.0 * world * R / (dev_ms / args.steps / 1e3),
+                       "sim_runs_per_hour_e2e": 3600.0 * world * R / (e2e_s / args.steps),
+                       "wall_s_timed_region": wall},
+            "clocks": clocks,
+            "e2e": {"value": world * agent_days_step * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": args.traffic, "kernel": "seir_persistent_kernel" if args.launch == "persistent" else "seir_day_kernel x T",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": balg * R,
+                         "active_agent_days": a_sum, "infections": i_sum},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample, T)
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--replicas", type=int, default=1)
+    ap.add_argument("--mode", default="native", choices=["native", "replay"])
+    ap.add_argument("--launch", default="persistent", choices=["persistent", "per_day"])
+    ap.add_argument("--flush-l2", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="agents per CPU run (0 = full C2 size if memory allows)")
+    ap.add_argument("--cpu-workers", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from ncu (profiles/), if known")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 3) if os.environ.get("SEIR_BENCH_STRICT_WARMUP", "1") == "1" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,46 +13,38 @@ using namespace seir;
 #define SEIR_STR(x) SEIR_STR2(x)
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(kThreads) seir_persistent_kernel(DevCtx cx)
+__global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(const __grid_constant__ DevCtx cx)
 {
-    __shared__ TileSmem sm;
+    __shared__ PassSmem sm;
     // the host resets the barrier counter to 0 before each launch
+    stage_tables(cx, sm);
     for (int t = 1; t <= cx.T; ++t) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
         day_pass(cx, sm, t);
         if (t < cx.T) grid_barrier(cx.barrier, (unsigned int)t * gridDim.x);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[cx.T + 1] = global_timer_ns();
 }
 
-__global__ void __launch_bounds__(kThreads) seir_day_kernel(DevCtx cx, int t)
+__global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __grid_constant__ DevCtx cx, int t)
 {
-    __shared__ TileSmem sm;
+    __shared__ PassSmem sm;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
+    stage_tables(cx, sm);
     day_pass(cx, sm, t);
 }
 
-// row 0 := S (padding := inert), winner := 0, inbox := 0
+// winner := 0, inbox := 0 (the only per-run state that must be cleared; records are built on infection)
 __global__ void seir_init_state_kernel(DevCtx cx)
 {
     const int64_t nvec = cx.n_pad / kVec;
     const int64_t total = nvec * cx.n_rep;
+    const uint4 z = make_uint4(0, 0, 0, 0);
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int rep = (int)(g / nvec);
-        const int64_t vi = g % nvec;
-        const int64_t i0 = vi * kVec;
-        uint32_t w[4];
+        cx.inbox[g] = 0;
+        uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + g * kVec);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (i0 + k * 4 + b >= cx.n) x |= (uint32_t)C_PAD << (8 * b);
-            w[k] = x;
-        }
-        reinterpret_cast<uint4 *>(cx.hist + (size_t)rep * cx.T * cx.n_pad)[vi] = make_uint4(w[0], w[1], w[2], w[3]);
-        cx.inbox[(size_t)rep * nvec + vi] = 0;
-        uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + (size_t)rep * cx.n_pad + i0);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) wz[k] = z;
+        for (int k = 0; k < 8; ++k) __stcs(wz + k, z);
     }
 }
 
@@ -61,17 +53,50 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
 {
     const int rep = blockIdx.y;
     const int64_t lo = init_off[rep], hi = init_off[rep + 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cx.list_cnt[(size_t)rep * 2 * (cx.T + 2) + 1] = (uint32_t)(hi - lo);
     for (int64_t k = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = init_ids[k];
         const uint64_t seed = cx.seeds[rep];
         AgentRec r = AgentRec{};
         r.t_exposed = 0;
         r.tt_activation = sd_enc16(sd_lognormal_days(seed, (uint32_t)a, 0, SD_SITE_INIT, 0, cx.act_mu, cx.act_sigma));
+        r.t_end = NEVER;
+        r.t_q_on = NEVER;
+        r.stat = cx.stat[a];
+        r.state = C_E;
         store_rec(cx.rec + (size_t)rep * cx.n_pad + a, r);
-        cx.hist[(size_t)rep * cx.T * cx.n_pad + a] = C_E;
+        cx.winner[(size_t)rep * cx.n_pad + a] = 1ull;  // day 0, never susceptible again
         atomicOr(cx.inbox + (size_t)rep * (cx.n_pad / 16) + (a >> 4), inbox_infected_bit((int)(a & 15)));
-        const int age = cx.stat[a] & 127;
-        atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + age, 1u);
+        cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + (k - lo)] = (uint32_t)a;
+        atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat & 127), 1u);
+    }
+}
+
+// The reference's nine bool[T,n] outputs (:165-173, one row per day) as ONE packed byte per agent-day,
+// written once from the per-agent records: a streaming T*n byte write.  A thread owns 16 agents.
+__global__ void __launch_bounds__(256) seir_materialize_kernel(DevCtx cx)
+{
+    const int64_t nvec = cx.n_pad / kVec;
+    const int64_t total = nvec * cx.n_rep;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int rep = (int)(g / nvec);
+        const int64_t vi = g % nvec;
+        uint8_t *hist = cx.hist + (size_t)rep * cx.T * cx.n_pad;
+        const uint32_t ib = __ldcs(cx.inbox + g);
+        uint4 *row = reinterpret_cast<uint4 *>(hist) + vi;
+        const int64_t row_stride = cx.n_pad / kVec;
+#pragma unroll 4
+        for (int t = 0; t < cx.T; ++t) __stcs(row + (int64_t)t * row_stride, z);  // S everywhere
+        uint32_t m = ib & 0x0F0F0F0Fu;  // "ever infected" bits
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int k = (bit & 7) * 4 + (bit >> 3);  // inverse of inbox_infected_bit
+            const int64_t i = vi * kVec + k;
+            const AgentRec r = load_rec(cx.rec + (size_t)rep * cx.n_pad + i);
+            for (int t = r.t_exposed; t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t);
+        }
     }
 }
 
@@ -107,13 +132,13 @@ __global__ void seir_agent_vector_kernel(DevCtx cx, int rep, int which, double *
                 case SEIR_VEC_TIME_TO_ACTIVATION: v = dec16(r.tt_activation); break;
                 case SEIR_VEC_TIME_TO_DEATH: v = dec16(r.tt_death); break;
                 case SEIR_VEC_TIME_TO_RECOVERY: v = dec16(r.tt_recovery); break;
-                case SEIR_VEC_TIME_CRITICAL: v = r.t_critical; break;
+                case SEIR_VEC_TIME_CRITICAL: v = (r.flags & F_CRIT) ? t_critical_of(r) : 0; break;
                 case SEIR_VEC_TIME_EXPOSED: v = r.t_exposed; break;
                 case SEIR_VEC_NUM_INFECTED_ASYMPT: v = r.n_inf_asympt; break;
-                case SEIR_VEC_TIME_INFECTED: v = r.t_infected; break;
+                case SEIR_VEC_TIME_INFECTED: v = (r.flags & F_MILD) ? t_infected_of(r) : 0; break;
                 case SEIR_VEC_TIME_TO_SEVERE: v = dec16(r.tt_severe); break;
                 case SEIR_VEC_TIME_TO_ISOLATE: v = dec16(r.tt_isolate); break;
-                case SEIR_VEC_TIME_SEVERE: v = r.t_severe; break;
+                case SEIR_VEC_TIME_SEVERE: v = (r.flags & F_SEV) ? t_severe_of(r) : 0; break;
                 case SEIR_VEC_TIME_TO_CRITICAL: v = dec16(r.tt_critical); break;
                 default: v = r.n_inf_outside; break;
             }
@@ -196,15 +221,16 @@ struct seir_handle {
     std::vector<int64_t> group_sizes;  // N_age
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
-    float loop_ms = 0.f, total_ms = 0.f;
+    cudaEvent_t ev3 = nullptr;
+    float loop_ms = 0.f, total_ms = 0.f, mat_ms = 0.f;
     long long launches = 0;
     DevBuf<uint16_t> stat;
-    DevBuf<int32_t> grp_off, grp_members, init_ids;
+    DevBuf<int32_t> grp_off, grp_members, init_ids, alias_idx;
     DevBuf<int64_t> init_off;
     DevBuf<double> p_hh, tables, enlam, stage_d;
     DevBuf<uint8_t> hist, stage_u8;
-    DevBuf<uint32_t> inbox, tally, home;
-    DevBuf<unsigned long long> winner, counters;
+    DevBuf<uint32_t> inbox, tally, home, list_old, list_new, list_cnt;
+    DevBuf<unsigned long long> winner, counters, day_ns, stage_ns;
     DevBuf<AgentRec> rec;
     DevBuf<uint64_t> seeds;
     DevBuf<unsigned int> barrier;
@@ -214,12 +240,12 @@ struct seir_handle {
 };
 
 static const size_t kTabPms = 0, kTabPsc = 404, kTabPcd = 808, kTabIso = 1212, kTabIsoA = 1313, kTabNatEn = 1414,
-                    kTabCdf = 1414 + 404, kTabTotal = 1414 + 404 + 101 * 101;
+                    kTabAliasP = 1414 + 404, kTabTotal = 1414 + 404 + 101 * 101;
 
 static int upload_tables(seir_handle *h, const seir_tables *tb)
 {
     if (!tb || !tb->p_mild_severe || !tb->p_severe_critical || !tb->p_critical_death || !tb->iso_mean ||
-        !tb->iso_asympt_mean || !tb->nat_enlam || !tb->nat_cdf)
+        !tb->iso_asympt_mean || !tb->nat_enlam || !tb->nat_alias_prob || !tb->nat_alias_idx)
         return fail("seir_tables: a required table pointer is NULL");
     std::vector<double> host(kTabTotal);
     memcpy(&host[kTabPms], tb->p_mild_severe, 404 * sizeof(double));
@@ -228,7 +254,11 @@ static int upload_tables(seir_handle *h, const seir_tables *tb)
     memcpy(&host[kTabIso], tb->iso_mean, 101 * sizeof(double));
     memcpy(&host[kTabIsoA], tb->iso_asympt_mean, 101 * sizeof(double));
     memcpy(&host[kTabNatEn], tb->nat_enlam, 404 * sizeof(double));
-    memcpy(&host[kTabCdf], tb->nat_cdf, 101 * 101 * sizeof(double));
+    memcpy(&host[kTabAliasP], tb->nat_alias_prob, 101 * 101 * sizeof(double));
+    for (int k = 0; k < 101 * 101; ++k)
+        if (tb->nat_alias_idx[k] < 0 || tb->nat_alias_idx[k] > 100) return fail("seir_tables.nat_alias_idx out of range");
+    CK(h->alias_idx.alloc(101 * 101));
+    CK(cudaMemcpyAsync(h->alias_idx.p, tb->nat_alias_idx, 101 * 101 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     CK(h->tables.alloc(kTabTotal));
     CK(cudaMemcpyAsync(h->tables.p, host.data(), kTabTotal * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     h->replay_tables = tb->enlam_pre && tb->enlam_post;
@@ -259,6 +289,11 @@ static int alloc_state(seir_handle *h)
     const size_t R = (size_t)h->n_rep, np = (size_t)h->n_pad, T = (size_t)h->prm.T;
     CK(h->hist.alloc(R * T * np));
     CK(h->tally.alloc(R * T * TAL_ROWS * kAges));
+    CK(h->list_cnt.alloc(R * 2 * (T + 2)));
+    CK(h->day_ns.alloc(T + 2));
+    CK(cudaMemset(h->day_ns.p, 0, (T + 2) * 8));
+    CK(h->stage_ns.alloc((T + 2) * 8));
+    CK(cudaMemset(h->stage_ns.p, 0, (T + 2) * 8 * 8));
     h->T_alloc = h->prm.T;
     return 0;
 }
@@ -267,19 +302,21 @@ static void fill_ctx(seir_handle *h)
 {
     DevCtx &c = h->cx;
     const seir_params &p = h->prm;
-    c.n = h->n; c.n_pad = h->n_pad; c.tiles_per_rep = (int)(h->n_pad / kTile); c.n_rep = h->n_rep; c.T = p.T;
-    int chunks = h->grid / h->n_rep;
-    if (chunks < 1) chunks = 1;
-    if (chunks > c.tiles_per_rep) chunks = c.tiles_per_rep;
-    c.chunks_per_rep = chunks;
+    c.n = h->n; c.n_pad = h->n_pad; c.n_rep = h->n_rep; c.T = p.T;
+    int bpr = h->grid / h->n_rep;
+    if (bpr < 1) bpr = 1;
+    c.blocks_per_rep = bpr;
+    c.list_old = h->list_old.p; c.list_new = h->list_new.p; c.list_cnt = h->list_cnt.p;
     c.stat = h->stat.p; c.grp_off = h->grp_off.p; c.grp_members = h->grp_members.p;
     c.p_hh_vec = h->p_hh_uniform ? nullptr : h->p_hh.p; c.p_hh_scalar = h->p_hh_scalar;
     c.p_ms = h->tables.p + kTabPms; c.p_sc = h->tables.p + kTabPsc; c.p_cd = h->tables.p + kTabPcd;
     c.iso_mean = h->tables.p + kTabIso; c.iso_asym = h->tables.p + kTabIsoA;
-    c.nat_enlam = h->tables.p + kTabNatEn; c.nat_cdf = h->tables.p + kTabCdf;
+    c.nat_enlam = h->tables.p + kTabNatEn; c.nat_alias_prob = h->tables.p + kTabAliasP;
+    c.nat_alias_idx = h->alias_idx.p;
     c.enlam = h->replay_tables ? h->enlam.p : nullptr;
     c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
+    c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p;
     c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
     c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
     c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
@@ -301,7 +338,7 @@ int seir_device_count(void)
 const char *seir_build_info(void)
 {
     return "libseir_b200: CUDA kernels for sm_100a (compute_100a), nvcc " SEIR_STR(__CUDACC_VER_MAJOR__) "."
-           SEIR_STR(__CUDACC_VER_MINOR__) ", -lineinfo, tile=4096 agents, 256 threads/CTA";
+           SEIR_STR(__CUDACC_VER_MINOR__) ", -lineinfo, event-driven active lists, " SEIR_STR(SEIR_THREADS) " threads/CTA";
 }
 
 int seir_create(const seir_params *params, const seir_population *pop, const seir_tables *tables, int n_replicas,
@@ -328,7 +365,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
 
     seir_handle *h = new seir_handle();
     h->device = device; h->sms = prop.multiProcessorCount; h->n_rep = n_replicas; h->prm = *params; h->n = n;
-    h->n_pad = (n + kTile - 1) / kTile * kTile;
+    h->n_pad = (n + kPad - 1) / kPad * kPad;
     int rc = 1;
     do {
         // ---- static population: verify the contiguous all-pairs household layout, pack 2 B/agent
@@ -381,6 +418,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
 #define CKB(call) if ((e = (call)) != cudaSuccess) { fail(std::string(#call " failed: ") + cudaGetErrorString(e)); break; }
         CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CKB(cudaEventCreate(&h->ev0)); CKB(cudaEventCreate(&h->ev1)); CKB(cudaEventCreate(&h->ev2));
+        CKB(cudaEventCreate(&h->ev3));
         CKB(h->stat.alloc((size_t)h->n_pad));
         CKB(cudaMemcpy(h->stat.p, stat.data(), (size_t)h->n_pad * 2, cudaMemcpyHostToDevice));
         CKB(h->grp_off.alloc(kAges + 1));
@@ -395,6 +433,8 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(h->inbox.alloc(R * np / 16));
         CKB(h->winner.alloc(R * np));
         CKB(h->rec.alloc(R * np));
+        CKB(h->list_old.alloc(R * 2 * np));
+        CKB(h->list_new.alloc(R * 2 * np));
         CKB(h->home.alloc(R * np / 32));
         CKB(cudaMemset(h->home.p, 0, R * np / 32 * 4));
         CKB(h->seeds.alloc(R));
@@ -479,6 +519,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaMemsetAsync(h->tally.p, 0, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, h->stream));
     CK(cudaMemsetAsync(h->counters.p, 0, (size_t)R * 4 * 8, h->stream));
     CK(cudaMemsetAsync(h->barrier.p, 0, 4, h->stream));
+    CK(cudaMemsetAsync(h->list_cnt.p, 0, (size_t)R * 2 * (h->prm.T + 2) * 4, h->stream));
     seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
     ++h->launches;
     if (!ids.empty()) {
@@ -500,9 +541,14 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(h->ev2, h->stream));
+    seir_materialize_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
+    ++h->launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev3, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventElapsedTime(&h->loop_ms, h->ev1, h->ev2));
-    CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev2));
+    CK(cudaEventElapsedTime(&h->mat_ms, h->ev2, h->ev3));
+    CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev3));
     return 0;
 }
 
@@ -511,6 +557,15 @@ int seir_last_run_ms(seir_handle *h, float *day_loop_ms, float *total_ms)
     if (!h) return fail("handle is NULL");
     if (day_loop_ms) *day_loop_ms = h->loop_ms;
     if (total_ms) *total_ms = h->total_ms;
+    return 0;
+}
+
+int seir_last_run_ms3(seir_handle *h, float *init_ms, float *day_loop_ms, float *materialize_ms)
+{
+    if (!h) return fail("handle is NULL");
+    if (init_ms) *init_ms = h->total_ms - h->loop_ms - h->mat_ms;
+    if (day_loop_ms) *day_loop_ms = h->loop_ms;
+    if (materialize_ms) *materialize_ms = h->mat_ms;
     return 0;
 }
 
@@ -583,6 +638,26 @@ int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uin
     return 0;
 }
 
+int seir_get_day_times(seir_handle *h, int64_t *out)
+{
+    if (!h || !out) return fail("seir_get_day_times: NULL argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<unsigned long long> v((size_t)h->prm.T + 2);
+    CK(cudaMemcpy(v.data(), h->day_ns.p, v.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < v.size(); ++k) out[k] = (int64_t)v[k];
+    return 0;
+}
+
+int seir_get_stage_times(seir_handle *h, int64_t *out)
+{
+    if (!h || !out) return fail("seir_get_stage_times: NULL argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<unsigned long long> v(((size_t)h->prm.T + 2) * 8);
+    CK(cudaMemcpy(v.data(), h->stage_ns.p, v.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < v.size(); ++k) out[k] = (int64_t)v[k];
+    return 0;
+}
+
 int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
 {
     if (!h || !out4) return fail("seir_get_counters: NULL argument");
@@ -594,6 +669,20 @@ int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
     return 0;
 }
 
+int seir_host_register(void *ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return fail("seir_host_register: NULL / empty buffer");
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return 0;
+}
+
+int seir_host_unregister(void *ptr)
+{
+    if (!ptr) return fail("seir_host_unregister: NULL buffer");
+    CK(cudaHostUnregister(ptr));
+    return 0;
+}
+
 void seir_destroy(seir_handle *h)
 {
     if (!h) return;
@@ -602,6 +691,9 @@ void seir_destroy(seir_handle *h)
     h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release();
     h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
     h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release();
+    h->list_old.release(); h->list_new.release(); h->list_cnt.release(); h->day_ns.release();
+    h->alias_idx.release(); h->stage_ns.release();
+    if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);

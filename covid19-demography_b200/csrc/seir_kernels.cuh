@@ -1,21 +1,28 @@
 // seir_kernels.cuh -- device side of the B200 SEIR day step (sm_100a).
 //
-// One PASS per simulated day t (1 <= t <= T), one thread per 16 agents for the dense part:
-//   (a) read the packed state row t-1 (one byte per agent: bits 0-2 compartment, bit 3 Q,
-//       bit 4 Documented) as 16 B vectors plus one 32-bit "inbox" word per 16 agents;
-//   (b) carry the row to row t (the reference's nine row copies, seir_individual.py:245-253,
-//       are this one byte);
-//   (c) agents that are E/Mild/Severe/Critical at t-1, and S agents whose inbox says they were
-//       infected on day t-1, are queued in shared memory and processed one per thread:
-//       own progression (:256-337), household push (:339-359), community push (:361-390),
-//       per-day per-age tallies (run_simulation.py:448-460 and siblings).
-// All cross-agent effects of day t travel through two atomics on the INFECTEE:
-//   winner[c]  = atomicMax of (day<<48 | infector<<16 | event ordinal)  -- the reference's
-//                "last writer in agent order wins" for the infectee's timers;
-//   inbox[c]  |= "ever infected" bit, and the sticky "isolation draw was 0 => Q" bit (:353-354).
-// The infectee's own thread applies them in the NEXT pass (it reads row t as S + inbox bit +
-// winner.day == t), which is why one grid-wide barrier per day is enough and why the kernel can
-// run persistently over the whole horizon.
+// Layout in HBM (per replica unless marked shared):
+//   stat[n]        u16, shared   age(7) | diabetes | hypertension | household position(3) | household size-1 (3)
+//   grp_off/members i32, shared  CSR of the reference's age_groups tuple (seir_individual.py:36)
+//   winner[n]      u64           0 = never hit; else day<<48 | infector<<16 | event ordinal of the LAST hit
+//                                in the reference's agent order (atomicMax).  winner is also the
+//                                susceptibility oracle: S[t-1,c]  <=>  winner[c]==0 || day(winner[c])==t.
+//   inbox[n/16]    u32           2 bits per agent: "ever infected", "an isolation draw of a hit was 0 => Q" (:353-354)
+//   rec[n]         32 B          one sector per EVER-INFECTED agent: state byte, static word, every event day and
+//                                drawn time-to-event; the whole T-day history of the agent is a function of it.
+//   list_old/new[2][n] u32       active lists: agents that are E/Mild/Severe/Critical, and agents infected yesterday
+//   hist[T][n]     u8            packed state rows (bits 0-2 compartment, bit 3 Q, bit 4 Documented): the
+//                                reference's nine bool[T,n] outputs, written ONCE by the materialise kernel.
+//
+// Day pass t (1 <= t <= T; pass T only finalises day T-1): one thread per entry of the day's lists, in
+//   ROUNDS of kThreads entries that move through four convergent stages with shared-memory work queues:
+//   A own progression (:256-337) + which household members / how many contacts may be infected,
+//   C one candidate contact per thread (:373-375), H one hit per thread (:347-356,:376-385),
+//   W write-back of the infector's counters (:357-359,:386-390) and re-append to tomorrow's list.
+//   The FIRST sender that hits a susceptible c on day t (atomicMax returns a record of an earlier day)
+//   appends c to tomorrow's "new" list.
+//   S, R and D agents are never touched by a day pass (the reference's iteration is a no-op for them).
+// All cross-agent effects of a day go through atomics on the infectee (winner, inbox), so ONE grid-wide
+// barrier per day suffices and the kernel runs persistently over the whole horizon.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,35 +33,49 @@
 namespace seir {
 
 constexpr int kAges = SEIR_N_AGES;
-constexpr int kThreads = 256;                 // threads per CTA
-constexpr int kVec = 16;                      // agents per thread (one 16 B vector of state bytes)
-constexpr int kTile = kThreads * kVec;        // agents per tile = 4096
+#ifndef SEIR_THREADS
+#define SEIR_THREADS 512
+#endif
+#ifndef SEIR_MIN_BLOCKS
+#define SEIR_MIN_BLOCKS 2
+#endif
+constexpr int kThreads = SEIR_THREADS;   // threads per CTA of the day-step kernels
+constexpr int kMinBlocks = SEIR_MIN_BLOCKS;
+constexpr int kVec = 16;                 // agents per 16 B vector of state bytes
+constexpr int kPad = 4096;               // row stride is a multiple of this many agents
+constexpr int kOutCap = 3 * kThreads;    // per-CTA staging of list appends
+
 // device tally rows (per day, per age)
 enum { TAL_E = 0, TAL_MILD, TAL_SEV, TAL_CRIT, TAL_QACT, TAL_NEW_E, TAL_NEW_R, TAL_NEW_D, TAL_NEW_DOC, TAL_ROWS };
-constexpr int kTalLagRows = TAL_NEW_E + 1;    // rows [0, kTalLagRows) describe day t-1, the rest day t
+constexpr int kTalLagRows = TAL_NEW_E + 1;  // rows [0, kTalLagRows) describe day t-1, the rest day t
 
 // compartments (bits 0-2 of the state byte)
-enum { C_S = 0, C_E = 1, C_MILD = 2, C_SEV = 3, C_CRIT = 4, C_R = 5, C_D = 6, C_PAD = 7 };
+enum { C_S = 0, C_E = 1, C_MILD = 2, C_SEV = 3, C_CRIT = 4, C_R = 5, C_D = 6 };
 constexpr uint8_t ST_Q = 0x08, ST_DOC = 0x10;
+constexpr uint8_t F_MILD = 1, F_SEV = 2, F_CRIT = 4;  // stages the agent has reached
 constexpr uint16_t NEVER = 0xFFFFu;
 
-// 32 B per-agent record: one sector, touched only while the agent is active.
+// 32 B per-agent record.  Derived days: t_infected = t_exposed + tt_activation (F_MILD),
+// t_severe = t_infected + tt_severe (F_SEV), t_critical = t_severe + tt_critical (F_CRIT) -- the reference
+// fires those transitions exactly when `t - t0 == tt` (:257,:291,:312).
 struct __align__(16) AgentRec {
-    uint16_t t_exposed;      // :200,:355  (0xFFFF == -1 never)
+    uint16_t t_exposed;      // :200,:355
     uint16_t tt_activation;  // :218,:356
-    uint16_t t_infected;     // :201,:259
     uint16_t tt_severe;      // :213,:263  (0xFFFF == inf)
     uint16_t tt_recovery;    // :214
-    uint16_t t_severe;       // :202,:305
     uint16_t tt_critical;    // :215
-    uint16_t t_critical;     // :203,:315
     uint16_t tt_death;       // :216
     uint16_t tt_isolate;     // :217
     uint16_t t_documented;   // :204
     uint16_t n_inf_by;       // :207
     uint16_t n_inf_asympt;   // :209
     uint16_t n_inf_outside;  // :208
-    uint16_t pad0, pad1;
+    uint16_t t_end;          // day of R or D (0xFFFF: none yet)
+    uint16_t t_q_on;         // first day with Q set (0xFFFF: never)
+    uint16_t stat;           // copy of the static word
+    uint8_t state;           // current packed state byte
+    uint8_t flags;           // F_*
+    uint16_t spare;
 };
 static_assert(sizeof(AgentRec) == 32, "AgentRec must be one 32 B sector");
 
@@ -65,19 +86,19 @@ __host__ __device__ inline uint16_t pack_static(int age, int diab, int hyp, int 
 }
 
 // inbox word (16 agents): byte b holds agents b, b+4, b+8, b+12 -- "infected" in bits 0-3,
-// "Q on infection" in bits 4-7 -- so that (word >> w) & 0x01010101 lines the infected bits of
-// state word w (agents 4w..4w+3) up with that word's bytes.
+// "Q on infection" in bits 4-7 -- so that (word >> w) & 0x01010101 lines the infected bits of agents
+// 4w..4w+3 up with the bytes of a 32-bit word of four state bytes (used by the materialise kernel).
 __host__ __device__ inline uint32_t inbox_infected_bit(int k) { return 1u << (8 * (k & 3) + (k >> 2)); }
 __host__ __device__ inline uint32_t inbox_q_bit(int k) { return 1u << (8 * (k & 3) + 4 + (k >> 2)); }
 
 struct DevCtx {
     // population, shared by all replicas
     int64_t n;            // agents
-    int64_t n_pad;        // row stride, multiple of kTile
-    int tiles_per_rep;
+    int64_t n_pad;        // row stride, multiple of kPad
     int n_rep;
-    int chunks_per_rep;   // work items per replica and day (contiguous tile ranges)
+    int blocks_per_rep;   // CTAs that share one replica's list in a pass (>= 1)
     int T;
+    int mode;
     const uint16_t *stat;
     const int32_t *grp_off;      // [102]
     const int32_t *grp_members;  // [n]
@@ -87,20 +108,26 @@ struct DevCtx {
     const double *p_ms, *p_sc, *p_cd;  // [101*4]
     const double *iso_mean, *iso_asym; // [101]
     const double *nat_enlam;           // [2][101][2]
-    const double *nat_cdf;             // [101][101]
+    const double *nat_alias_prob;      // [101][101]
+    const int32_t *nat_alias_idx;      // [101][101]
     const double *enlam;               // [2][101][101] (replay) or nullptr
     // per-replica state
     uint8_t *hist;                 // [rep][T][n_pad]
     uint32_t *inbox;               // [rep][n_pad/16]
     unsigned long long *winner;    // [rep][n_pad]
     AgentRec *rec;                 // [rep][n_pad]
+    uint32_t *list_old;            // [rep][2][n_pad]  agents that were active yesterday and still are
+    uint32_t *list_new;            // [rep][2][n_pad]  agents infected yesterday (record not built yet)
+    uint32_t *list_cnt;            // [rep][2][T+2]    entries of the old / new list consumed by pass t
     uint32_t *tally;               // [rep][T][TAL_ROWS][101]
     const uint32_t *home;          // [rep][n_pad/32] bitmap of Home_real
     const uint64_t *seeds;         // [rep]
     unsigned long long *counters;  // [rep][4]
     unsigned int *barrier;         // grid barrier counter
+    unsigned long long *day_ns;    // [T+2] %globaltimer at the start of pass t (CTA 0), [T+1] = end of the loop
+    unsigned long long *stage_ns;  // [T+2][8] CTA 0, first round of pass t: stamps after init / A / C / H / W / flush / end
     // scalars
-    int t_lockdown, t_stayhome, mode;
+    int t_lockdown, t_stayhome;
     double p_doc, p_contact, asym;
     double m_sev, m_mild_rec, m_crit, m_sev_rec, m_crit_rec, m_death, act_mu, act_sigma;
 };
@@ -111,9 +138,13 @@ __device__ __forceinline__ uint16_t add_sat16(uint16_t a, uint16_t b)
     uint32_t s = (uint32_t)a + (uint32_t)b;
     return (a == NEVER || b == NEVER || s >= 0xFFFFu) ? NEVER : (uint16_t)s;
 }
-__device__ __forceinline__ uint16_t inc_sat16(uint16_t a) { return a >= 0xFFFEu ? a : (uint16_t)(a + 1); }
+__device__ __forceinline__ uint16_t inc_sat16(uint16_t a, uint32_t by)
+{
+    uint32_t s = (uint32_t)a + by;
+    return s >= 0xFFFEu ? (uint16_t)0xFFFEu : (uint16_t)s;
+}
 // `t - t0 == tt` of the reference on integer-valued doubles; tt == NEVER encodes inf/nan
-__device__ __forceinline__ bool due(int t, uint16_t t0, uint16_t tt) { return tt != NEVER && (int)t0 + (int)tt == t; }
+__device__ __forceinline__ bool due(int t, int t0, uint16_t tt) { return tt != NEVER && t0 + (int)tt == t; }
 
 __device__ __forceinline__ AgentRec load_rec(const AgentRec *p)
 {
@@ -128,106 +159,180 @@ __device__ __forceinline__ void store_rec(AgentRec *p, const AgentRec &r)
     union { AgentRec r; uint4 v[2]; } u;
     u.r = r;
     uint4 *q = reinterpret_cast<uint4 *>(p);
-    q[0] = u.v[0];
-    q[1] = u.v[1];
+    __stcg(q, u.v[0]);
+    __stcg(q + 1, u.v[1]);
+}
+__device__ __forceinline__ int t_infected_of(const AgentRec &r) { return (int)r.t_exposed + (int)r.tt_activation; }
+__device__ __forceinline__ int t_severe_of(const AgentRec &r) { return t_infected_of(r) + (int)r.tt_severe; }
+__device__ __forceinline__ int t_critical_of(const AgentRec &r) { return t_severe_of(r) + (int)r.tt_critical; }
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+
+// per-CTA shared state of a day pass.  A ROUND takes kThreads list entries through four
+// convergent stages separated by __syncthreads(): A agents -> C contacts -> H hits -> W write-back.
+constexpr int kConCap = 2 * kThreads;  // contact queue entries per round
+constexpr int kHitCap = 2 * kThreads;  // hit queue entries per round
+struct __align__(16) PassSmem {
+    uint32_t out_old[kOutCap];   // staged appends: survivors
+    uint32_t out_new[kOutCap];   // staged appends: agents infected today
+    uint2 hitq[kHitCap];         // .x = infectee, .y = slot<<23 | age_c<<16 | ord   (age 127 = look it up)
+    uint32_t conq[kConCap];      // slot<<23 | payload (native: k; replay: age<<8 | j)
+    uint32_t slot_agent[kThreads];
+    uint32_t slot_info[kThreads];  // age | E<<7
+    uint32_t hit_n[kThreads];      // hits of the slot's agent this round: total | outside<<16
+    uint32_t tally[TAL_ROWS * kAges];
+    // small per-age tables staged once per kernel (the grid barrier's acquire loads keep flushing L1)
+    double iso_asym[kAges], iso_mean[kAges];
+    double nat_enlam[2 * kAges * 2];
+    int32_t grp_off[kAges + 1];
+    uint32_t cnt[4];
+    uint32_t n_old, n_new, n_hit, n_con, base_old, base_new;
+};
+
+__device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
+{
+    for (int k = threadIdx.x; k < kAges; k += kThreads) {
+        sm.iso_asym[k] = cx.iso_asym[k];
+        sm.iso_mean[k] = cx.iso_mean[k];
+    }
+    for (int k = threadIdx.x; k < 4 * kAges; k += kThreads) sm.nat_enlam[k] = cx.nat_enlam[k];
+    for (int k = threadIdx.x; k <= kAges; k += kThreads) sm.grp_off[k] = cx.grp_off[k];
+    __syncthreads();
 }
 
 struct RepView {
-    const uint8_t *prev;  // row t-1
-    uint8_t *cur;         // row t (nullptr in the finalize pass)
-    uint8_t *prev_w;      // row t-1, writable (fix-up patch)
     uint32_t *inbox;
     unsigned long long *winner;
     AgentRec *rec;
     const uint32_t *home;
+    uint32_t *next_old, *next_new;          // tomorrow's lists
+    uint32_t *next_old_cnt, *next_new_cnt;
     uint64_t seed;
     bool home_on;
     int phase;
 };
 
-// S[t-1, c] of the reference, seen from another agent's thread during pass t.
-__device__ __forceinline__ bool was_susceptible(const RepView &v, int64_t c, int t)
-{
-    uint8_t s = __ldcg(v.prev + c);
-    if ((s & 7) != C_S) return false;
-    uint32_t ib = __ldcg(v.inbox + (c >> 4));
-    if (!(ib & inbox_infected_bit((int)(c & 15)))) return true;
-    unsigned long long w = __ldcg(v.winner + c);
-    return (int)(w >> 48) == t;  // hit earlier today: still S in row t-1
-}
 __device__ __forceinline__ bool at_home(const RepView &v, int64_t c)
 {
     return v.home_on && ((__ldg(v.home + (c >> 5)) >> (c & 31)) & 1u);
 }
 
-// One successful transmission i -> c on day t (:347-359 / :376-390, infectee side).
-__device__ __forceinline__ void hit(const DevCtx &cx, const RepView &v, int64_t i, int64_t c, int t, uint32_t ord)
+// ---- stage H: one successful transmission slot's agent -> c on day t (:347-359 / :376-390) ----------
+__device__ __forceinline__ void process_hit(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t c, uint32_t meta, int t)
 {
-    unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)(uint32_t)i << 16) | ord;
-    atomicMax(v.winner + c, key);
-    int age_c = __ldg(cx.stat + c) & 127;
-    double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_INF, ord << 8), 0),
-                              __ldg(cx.iso_asym + age_c));
-    uint32_t bits = inbox_infected_bit((int)(c & 15));
+    const uint32_t slot = meta >> 23, ord = meta & 0xFFFFu;
+    int age_c = (meta >> 16) & 127;
+    const uint32_t i = sm.slot_agent[slot];
+    const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
+    if (age_c == 127) age_c = __ldg(cx.stat + c) & 127;  // (independent of the atomic below: one round trip)
+    const unsigned long long old = atomicMax(v.winner + c, key);
+    const double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
+    uint32_t bits = 0;
+    if ((int)(old >> 48) != t) {  // first hit of c today: announce it, queue it for tomorrow
+        bits = inbox_infected_bit((int)(c & 15));
+        const uint32_t pos = atomicAdd(&sm.n_new, 1u);
+        if (pos < (uint32_t)kOutCap) sm.out_new[pos] = c;
+        else v.next_new[atomicAdd(v.next_new_cnt, 1u)] = c;
+    }
     if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
-    __threadfence();  // the winner must be visible before the bit that announces it
-    atomicOr(v.inbox + (c >> 4), bits);
+    if (bits) atomicOr(v.inbox + (c >> 4), bits);
+    atomicAdd(&sm.hit_n[slot], ord >= 16u ? 0x10001u : 1u);  // ord >= 16: community (:386-388)
 }
 
-// ---------------------------------------------------------------------------------------
-// One queued agent, pass t.  `st0` is its byte in row t-1 as staged by the dense phase.
-__device__ void process_agent(const DevCtx &cx, const RepView &v, int64_t i, int t, uint8_t st0, uint32_t ib_word,
-                              uint32_t *s_tally, unsigned long long *s_cnt)
+__device__ __forceinline__ void push_hit(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t c, uint32_t meta, int t)
 {
+    const uint32_t pos = atomicAdd(&sm.n_hit, 1u);
+    if (pos < (uint32_t)kHitCap) sm.hitq[pos] = make_uint2(c, meta);
+    else process_hit(cx, v, sm, c, meta, t);  // queue full: handle in place
+}
+
+// ---- stage C: one candidate contact of slot's agent (:373-375) ---------------------------------------
+__device__ __forceinline__ void process_contact(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t item, int t)
+{
+    const uint32_t slot = item >> 23, payload = item & 0x7FFFFFu;
+    const uint32_t i = sm.slot_agent[slot];
+    const uint32_t info = sm.slot_info[slot];
+    int a;
+    uint32_t ord;
+    sd_block b;
+    if (cx.mode == SEIR_MODE_NATIVE) {
+        b = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_NPICK, payload);
+        // contact age: one alias-table look-up in the sender's row (same arithmetic as sd_alias_pick)
+        const double x = SD_MUL(sd_lane(b, 0), (double)kAges);
+        int col = (int)x;
+        if (col > kAges - 1) col = kAges - 1;
+        const int row = (int)(info & 127u) * kAges + col;
+        const double pr = __ldg(cx.nat_alias_prob + row);
+        const int al = __ldg(cx.nat_alias_idx + row);
+        a = (SD_SUB(x, (double)col) < pr) ? col : al;
+        ord = SD_ORD_COMM_NATIVE(payload);
+    } else {
+        a = (int)(payload >> 8);
+        const uint32_t j = payload & 255u;
+        b = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_KEEP, payload);
+        double p_c = cx.p_contact;
+        if (info & 128u) p_c = SD_MUL(p_c, cx.asym);
+        if (!(sd_lane(b, 0) < p_c)) return;  // :373
+        ord = SD_ORD_COMM_REPLAY(a, j);
+    }
+    const int g0 = sm.grp_off[a], glen = sm.grp_off[a + 1] - g0;
+    if (glen == 0) return;
+    const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
+    const unsigned long long w = __ldcg(v.winner + c);
+    if ((w == 0ull || (int)(w >> 48) == t) && !at_home(v, c))  // :375
+        push_hit(cx, v, sm, c, (slot << 23) | ((uint32_t)a << 16) | ord, t);
+}
+
+__device__ __forceinline__ void push_contact(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t item, int t)
+{
+    const uint32_t pos = atomicAdd(&sm.n_con, 1u);
+    if (pos < (uint32_t)kConCap) sm.conq[pos] = item;
+    else process_contact(cx, v, sm, item, t);
+}
+
+// ---- stage A: the agent's own day (:256-337) and the draws that decide whom it may infect -------------
+// Returns the record (possibly modified; `dirty`), and whether the agent transmits today.
+struct AgentOut { bool dirty; int ncomp; };
+
+__device__ __forceinline__ void build_new_record(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t i, int t, AgentRec &r)
+{
+    // infected on day t-1 by the winner of that day's hits (:347-356)
+    const unsigned long long w = __ldcg(v.winner + i);
+    const uint32_t ib = __ldcg(v.inbox + (i >> 4));
     const uint16_t stt = __ldg(cx.stat + i);
+    const uint32_t inf = (uint32_t)(w >> 16), ord = (uint32_t)(w & 0xFFFFu);
+    const int tx = t - 1;
+    const double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8), 0),
+                                    sm.iso_asym[stt & 127]);
+    const double tact = sd_lognormal_days(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+    r = AgentRec{};
+    r.t_exposed = (uint16_t)tx;
+    r.tt_isolate = sd_enc16(tiso);
+    r.tt_activation = sd_enc16(tact);
+    r.t_end = NEVER;
+    r.t_q_on = NEVER;
+    r.stat = stt;
+    r.state = C_E;
+    if (ib & inbox_q_bit((int)(i & 15))) { r.state |= ST_Q; r.t_q_on = (uint16_t)tx; }
+    atomicAdd(&sm.tally[TAL_NEW_E * kAges + (stt & 127)], 1u);
+}
+
+// rare events of the agent's own progression; kept out of line so the common path stays short
+__device__ __noinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
+                                                AgentRec &r, int comp, int &ncomp, bool &nq, bool &ndoc)
+{
+    const uint16_t stt = r.stat;
     const int age = stt & 127;
     const int k3 = age * 4 + ((stt >> 7) & 1) * 2 + ((stt >> 8) & 1);
-    AgentRec r;
-    uint8_t st = st0;
-    bool dirty = false;
-
-    if ((st & 7) == C_S) {
-        // infected by someone's push: apply it if it happened on day t-1
-        unsigned long long w = __ldcg(v.winner + i);
-        if ((int)(w >> 48) != t - 1) return;  // hit today by a racing sender: still S in row t-1
-        const uint32_t inf = (uint32_t)(w >> 16), ord = (uint32_t)(w & 0xFFFFu);
-        const double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, inf, (uint32_t)(t - 1), SD_SITE_INF, ord << 8), 0),
-                                        __ldg(cx.iso_asym + age));
-        const double tact = sd_lognormal_days(v.seed, inf, (uint32_t)(t - 1), SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
-        r = AgentRec{};
-        r.t_exposed = (uint16_t)(t - 1);
-        r.tt_isolate = sd_enc16(tiso);
-        r.tt_activation = sd_enc16(tact);
-        st = C_E | ((ib_word & inbox_q_bit((int)(i & 15))) ? ST_Q : 0);
-        v.prev_w[i] = st;  // patch row t-1 (:347,:351,:354)
-        atomicAdd(&s_tally[TAL_NEW_E * kAges + age], 1u);
-        atomicAdd(&s_cnt[1], 1ull);
-        dirty = true;
-    } else {
-        r = load_rec(v.rec + i);
-    }
-
-    const int comp = st & 7;
-    // state tallies of day t-1
-    atomicAdd(&s_tally[(comp - C_E) * kAges + age], 1u);
-    if (st & ST_Q) atomicAdd(&s_tally[TAL_QACT * kAges + age], 1u);
-    atomicAdd(&s_cnt[0], 1ull);
-
-    if (v.cur == nullptr) {  // finalize pass (t == T): nothing moves
-        if (dirty) store_rec(v.rec + i, r);
-        return;
-    }
-
-    const bool Ep = comp == C_E, Mp = comp == C_MILD, Sevp = comp == C_SEV, Cp = comp == C_CRIT;
-    const bool Qp = (st & ST_Q) != 0, Dp = (st & ST_DOC) != 0;
-    int ncomp = comp;
-    bool nq = Qp, ndoc = Dp;
-    bool transmit = true;
-
-    if (Ep && due(t, r.t_exposed, r.tt_activation)) {  // :256-272
+    if (comp == C_E) {  // :256-272 activation
         ncomp = C_MILD;
-        r.t_infected = (uint16_t)t;
-        sd_block b = sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_ACT, 0);
+        r.flags |= F_MILD;
+        sd_block b = sd_draw(seed, i, (uint32_t)t, SD_SITE_ACT, 0);
         if (sd_lane(b, 0) < __ldg(cx.p_ms + k3)) {
             r.tt_severe = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_sev));
             r.tt_recovery = NEVER;
@@ -235,255 +340,317 @@ __device__ void process_agent(const DevCtx &cx, const RepView &v, int64_t i, int
             r.tt_recovery = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_mild_rec));
             r.tt_severe = NEVER;
         }
-        double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_ACT, 1), 0),
-                                  __ldg(cx.iso_mean + age));
+        const double tiso = sd_exp_days(sd_lane(sd_draw(seed, i, (uint32_t)t, SD_SITE_ACT, 1), 0), sm.iso_mean[age]);
         r.tt_isolate = sd_enc16(tiso);
         if (tiso == 0.0) nq = true;
-        dirty = true;
-    }
-    if (Mp || Sevp || Cp) {  // :274-327
-        if (due(t, r.t_infected, r.tt_recovery)) {  // :276-279
-            ncomp = C_R;
-            nq = false;
-            transmit = false;
-            atomicAdd(&s_tally[TAL_NEW_R * kAges + age], 1u);
-            goto write_back;
+    } else if (comp == C_MILD) {  // :291-311 Mild -> Severe
+        ncomp = C_SEV;
+        r.flags |= F_SEV;
+        if (!ndoc) {
+            ndoc = true;
+            r.t_documented = (uint16_t)t;
         }
-        if (Mp && !Dp) {  // :280-289
-            if (sd_lane(sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_DOC, 0), 0) < cx.p_doc) {
-                ndoc = true;
-                r.t_documented = (uint16_t)t;
-                dirty = true;
-            }
+        nq = true;
+        sd_block b = sd_draw(seed, i, (uint32_t)t, SD_SITE_SEV, 0);
+        if (sd_lane(b, 0) < __ldg(cx.p_sc + k3)) {
+            r.tt_critical = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_crit));
+            r.tt_recovery = NEVER;
+        } else {
+            r.tt_recovery = add_sat16(sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_sev_rec)), r.tt_severe);
+            r.tt_critical = NEVER;
         }
-        if (Mp && due(t, r.t_infected, r.tt_severe)) {  // :291-311
-            ncomp = C_SEV;
-            if (!Dp) {
-                ndoc = true;
-                r.t_documented = (uint16_t)t;
-            }
-            nq = true;
-            r.t_severe = (uint16_t)t;
-            sd_block b = sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_SEV, 0);
-            if (sd_lane(b, 0) < __ldg(cx.p_sc + k3)) {
-                r.tt_critical = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_crit));
-                r.tt_recovery = NEVER;
-            } else {
-                r.tt_recovery = add_sat16(sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_sev_rec)), r.tt_severe);
-                r.tt_critical = NEVER;
-            }
-            dirty = true;
-        } else if (Sevp && due(t, r.t_severe, r.tt_critical)) {  // :312-321
-            ncomp = C_CRIT;
-            r.t_critical = (uint16_t)t;
-            sd_block b = sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_CRIT, 0);
-            if (sd_lane(b, 0) < __ldg(cx.p_cd + k3)) {
-                r.tt_death = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_death));
-                r.tt_recovery = NEVER;
-            } else {
-                r.tt_recovery = add_sat16(add_sat16(sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_crit_rec)), r.tt_severe),
-                                          r.tt_critical);
-                r.tt_death = NEVER;
-            }
-            dirty = true;
-        } else if (Cp) {  // :323-327
-            if (due(t, r.t_critical, r.tt_death)) {
-                ncomp = C_D;
-                nq = false;
-                atomicAdd(&s_tally[TAL_NEW_D * kAges + age], 1u);
-            }
+    } else {  // :312-321 Severe -> Critical
+        ncomp = C_CRIT;
+        r.flags |= F_CRIT;
+        sd_block b = sd_draw(seed, i, (uint32_t)t, SD_SITE_CRIT, 0);
+        if (sd_lane(b, 0) < __ldg(cx.p_cd + k3)) {
+            r.tt_death = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_death));
+            r.tt_recovery = NEVER;
+        } else {
+            r.tt_recovery = add_sat16(add_sat16(sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_crit_rec)), r.tt_severe), r.tt_critical);
+            r.tt_death = NEVER;
         }
-    }
-    if (ndoc && !Dp) atomicAdd(&s_tally[TAL_NEW_DOC * kAges + age], 1u);
-
-    // :328-337
-    if (Qp) transmit = false;
-    if (transmit) {
-        if (!Ep && due(t, r.t_infected, r.tt_isolate)) { nq = true; transmit = false; }
-        else if (Ep && due(t, r.t_exposed, r.tt_isolate)) { nq = true; transmit = false; }
-    }
-    if (transmit) {
-        uint32_t hits = 0, hits_out = 0;
-        // ---- household push :339-359.  Households are contiguous ranges [i-pos, i-pos+size).
-        {
-            const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
-            double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
-            if (Ep) p_h = SD_MUL(p_h, cx.asym);
-            const int64_t base = i - pos;
-            for (int j = 0; j < size - 1; ++j) {
-                const int64_t c = base + j + (j >= pos ? 1 : 0);
-                if (!was_susceptible(v, c, t)) continue;
-                if (sd_lane(sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_HH, (uint32_t)j), 0) < p_h) {
-                    hit(cx, v, i, c, t, SD_ORD_HH(j));
-                    ++hits;
-                }
-            }
-        }
-        // ---- community push :361-390
-        if (!at_home(v, i)) {
-            if (cx.mode == SEIR_MODE_NATIVE) {
-                const double en = __ldg(cx.nat_enlam + ((v.phase * kAges + age) * 2 + (Ep ? 1 : 0)));
-                const uint32_t kept = sd_poisson(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_NCNT, 0, en, SD_MAX_CONTACTS_NATIVE);
-                const double *cdf = cx.nat_cdf + age * kAges;
-                for (uint32_t k = 0; k < kept; ++k) {
-                    sd_block b = sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_NPICK, k);
-                    const double u = sd_lane(b, 0);
-                    int lo = 0, hi = kAges - 1;
-                    while (lo < hi) {
-                        int mid = (lo + hi) >> 1;
-                        if (u < __ldg(cdf + mid)) hi = mid; else lo = mid + 1;
-                    }
-                    const int g0 = __ldg(cx.grp_off + lo), glen = __ldg(cx.grp_off + lo + 1) - g0;
-                    if (glen == 0) continue;
-                    const int64_t c = __ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));
-                    if (was_susceptible(v, c, t) && !at_home(v, c)) {
-                        hit(cx, v, i, c, t, SD_ORD_COMM_NATIVE(k));
-                        ++hits;
-                        ++hits_out;
-                    }
-                }
-            } else {
-                double p_c = cx.p_contact;
-                if (Ep) p_c = SD_MUL(p_c, cx.asym);
-                const double *en = cx.enlam + ((size_t)v.phase * kAges + age) * kAges;
-                for (int a = 0; a < kAges; ++a) {
-                    const int g0 = __ldg(cx.grp_off + a), glen = __ldg(cx.grp_off + a + 1) - g0;
-                    if (glen == 0) continue;  // :368-369
-                    const uint32_t nc = sd_poisson(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_POIS, (uint32_t)a << 8,
-                                                   __ldg(en + a), SD_MAX_CONTACTS_PER_AGE);
-                    for (uint32_t j = 0; j < nc; ++j) {
-                        sd_block b = sd_draw(v.seed, (uint32_t)i, (uint32_t)t, SD_SITE_KEEP, ((uint32_t)a << 8) | j);
-                        if (!(sd_lane(b, 0) < p_c)) continue;  // :373
-                        const int64_t c = __ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
-                        if (was_susceptible(v, c, t) && !at_home(v, c)) {  // :375
-                            hit(cx, v, i, c, t, SD_ORD_COMM_REPLAY(a, j));
-                            ++hits;
-                            ++hits_out;
-                        }
-                    }
-                }
-            }
-        }
-        if (hits) {
-            for (uint32_t h = 0; h < hits; ++h) {
-                r.n_inf_by = inc_sat16(r.n_inf_by);
-                if (Ep) r.n_inf_asympt = inc_sat16(r.n_inf_asympt);
-            }
-            for (uint32_t h = 0; h < hits_out; ++h) r.n_inf_outside = inc_sat16(r.n_inf_outside);
-            atomicAdd(&s_cnt[2], (unsigned long long)hits);
-            dirty = true;
-        }
-    }
-
-write_back:
-    {
-        const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
-        if (nst != st0) v.cur[i] = nst;  // the dense phase already carried st0 into row t
-        if (dirty) store_rec(v.rec + i, r);
     }
 }
 
 // ---------------------------------------------------------------------------------------
-struct __align__(16) TileSmem {
-    uint8_t prev[kTile];      // staged row t-1 of this tile
-    uint32_t ib[kThreads];    // staged inbox words
-    uint16_t queue[kTile];    // local indices of agents that need work
-    uint32_t tally[TAL_ROWS * kAges];
-    unsigned long long cnt[4];
-    uint32_t q_count;
-};
-
-// One work item: tiles [tile_lo, tile_hi) of replica `rep`, pass t.
-__device__ void run_item(const DevCtx &cx, TileSmem &sm, int rep, int tile_lo, int tile_hi, int t)
+// Pass t over all replicas.  CTA b serves replica (b / blocks_per_rep) [+ k * reps_per_sweep].
+#define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
+__device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
 {
     const int tid = threadIdx.x;
-    RepView v;
-    uint8_t *hist = cx.hist + (size_t)rep * cx.T * cx.n_pad;
-    v.prev = hist + (size_t)(t - 1) * cx.n_pad;
-    v.prev_w = hist + (size_t)(t - 1) * cx.n_pad;
-    v.cur = (t < cx.T) ? hist + (size_t)t * cx.n_pad : nullptr;
-    v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
-    v.winner = cx.winner + (size_t)rep * cx.n_pad;
-    v.rec = cx.rec + (size_t)rep * cx.n_pad;
-    v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
-    v.seed = cx.seeds[rep];
-    v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;   // :243-244
-    v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
+    bool stamped = false;
+    const int lane = tid & 31;
+    const bool finalize = t >= cx.T;
+    const int bpr = cx.blocks_per_rep;
+    const int reps_per_sweep = gridDim.x / bpr;  // >= 1
+    const int my_slot = blockIdx.x / bpr, my_part = blockIdx.x % bpr;
+    // (CTAs beyond the last full group idle through the pass; they must still reach the grid barrier)
+    for (int rep = my_slot; rep < cx.n_rep && my_slot < reps_per_sweep; rep += reps_per_sweep) {
+        RepView v;
+        v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+        v.winner = cx.winner + (size_t)rep * cx.n_pad;
+        v.rec = cx.rec + (size_t)rep * cx.n_pad;
+        v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
+        const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
+        uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 2 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2);
+        v.next_old = cx.list_old + lrow;
+        v.next_new = cx.list_new + lrow;
+        v.next_old_cnt = cnt_old + (t + 1);
+        v.next_new_cnt = cnt_new + (t + 1);
+        v.seed = cx.seeds[rep];
+        v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;          // :243-244
+        v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
+        const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
+        const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t);
+        const uint32_t count = n_new + n_old;  // new infectees first: their record build stays convergent
 
-    for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
-    if (tid < 4) sm.cnt[tid] = 0;
-    if (tid == 0) sm.q_count = 0;
-    __syncthreads();
+        for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
+        if (tid < 4) sm.cnt[tid] = 0;
+        if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; }
+        __syncthreads();
 
-    for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        const int64_t base = (int64_t)tile * kTile;
-        const int64_t vi = base / kVec + tid;
-        // ---- dense phase: 16 agents per thread
-        const uint4 sv = __ldcg(reinterpret_cast<const uint4 *>(v.prev) + vi);
-        const uint32_t ib = __ldcg(v.inbox + vi);
-        if (v.cur) reinterpret_cast<uint4 *>(v.cur)[vi] = sv;
-        reinterpret_cast<uint4 *>(sm.prev)[tid] = sv;
-        sm.ib[tid] = ib;
-        const uint32_t wds[4] = {sv.x, sv.y, sv.z, sv.w};
-        uint32_t work[4];
-        uint32_t any = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t c = wds[w] & 0x07070707u;
-            const uint32_t active = ((c + 0x03030303u) & 0x04040404u) >> 2;               // bit0 of byte: comp in 1..4
-            const uint32_t is_s = (~(c + 0x07070707u) & 0x08080808u) >> 3;                // bit0 of byte: comp == 0
-            const uint32_t infected = (ib >> w) & 0x01010101u;                            // bit0 of byte: inbox bit
-            work[w] = active | (is_s & infected);
-            any |= work[w];
-        }
-        if (any) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                uint32_t m = work[w];
-                while (m) {
-                    const int b = (__ffs(m) - 1) >> 3;
-                    m &= m - 1;
-                    const uint32_t slot = atomicAdd(&sm.q_count, 1u);
-                    sm.queue[slot] = (uint16_t)(tid * kVec + w * 4 + b);
+        SEIR_STAMP(0);
+        uint32_t c_active = 0, c_inf = 0, c_hits = 0;
+        const uint32_t stride = (uint32_t)bpr * kThreads;
+        for (uint32_t e0 = (uint32_t)my_part * kThreads; e0 < count; e0 += stride) {
+            // ================= stage A: one list entry per thread =================
+            const uint32_t e = e0 + tid;
+            const bool valid = e < count;
+            uint32_t i = 0;
+            AgentRec r;
+            bool dirty = false, keep = false;
+            uint8_t st = 0;
+            int ncomp = 0;
+            bool nq = false, ndoc = false;
+            sm.hit_n[tid] = 0;
+            if (valid) {
+                if (e < n_new) {
+                    i = __ldcg(cur_new + e);
+                    build_new_record(cx, v, sm, i, t, r);
+                    ++c_inf;
+                    dirty = true;
+                } else {
+                    i = __ldcg(cur_old + (e - n_new));
+                    r = load_rec(v.rec + i);
                 }
+                const uint16_t stt = r.stat;
+                const int age = stt & 127;
+                st = r.state;
+                const int comp = st & 7;
+                const bool Ep = comp == C_E, Mp = comp == C_MILD, Sevp = comp == C_SEV, Cp = comp == C_CRIT;
+                const bool Qp = (st & ST_Q) != 0, Dp = (st & ST_DOC) != 0;
+                sm.slot_agent[tid] = i;
+                sm.slot_info[tid] = (uint32_t)age | (Ep ? 128u : 0u);
+                // state tallies of day t-1
+                atomicAdd(&sm.tally[(comp - C_E) * kAges + age], 1u);
+                if (Qp) atomicAdd(&sm.tally[TAL_QACT * kAges + age], 1u);
+                ++c_active;
+                ncomp = comp;
+                nq = Qp;
+                ndoc = Dp;
+                if (!finalize) {
+                    // the agent's day block: documentation draw + first uniform of the contact count
+                    const sd_block db = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
+                    bool transmit = !Qp;
+                    const int t_inf = t_infected_of(r);
+                    if (!Ep && due(t, t_inf, r.tt_recovery)) {  // :276-279
+                        ncomp = C_R;
+                        nq = false;
+                        transmit = false;
+                        atomicAdd(&sm.tally[TAL_NEW_R * kAges + age], 1u);
+                    } else {
+                        if (Mp && !Dp && sd_lane(db, 0) < cx.p_doc) {  // :280-289
+                            ndoc = true;
+                            r.t_documented = (uint16_t)t;
+                        }
+                        const bool ev = (Ep && due(t, r.t_exposed, r.tt_activation)) || (Mp && due(t, t_inf, r.tt_severe)) ||
+                                        (Sevp && due(t, t_severe_of(r), r.tt_critical));
+                        if (ev) {
+                            progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc);
+                            dirty = true;
+                        } else if (Cp && due(t, t_critical_of(r), r.tt_death)) {  // :323-327
+                            ncomp = C_D;
+                            nq = false;
+                            atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], 1u);
+                        }
+                        if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], 1u);
+                    }
+                    // :328-337 isolation entry (time_to_isolate may just have been redrawn at :270)
+                    if (transmit) {
+                        if (!Ep && due(t, t_infected_of(r), r.tt_isolate)) { nq = true; transmit = false; }
+                        else if (Ep && due(t, r.t_exposed, r.tt_isolate)) { nq = true; transmit = false; }
+                    }
+                    if (transmit) {
+                        // ---- household push :339-359; households are contiguous ranges [i-pos, i-pos+size)
+                        const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
+                        const uint32_t base = i - (uint32_t)pos;
+                        uint32_t smask = 0;
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) {  // independent loads: one round trip for the household
+                            if (j < size - 1) {
+                                const unsigned long long w = __ldcg(v.winner + base + j + (j >= pos ? 1 : 0));
+                                if (w == 0ull || (int)(w >> 48) == t) smask |= 1u << j;  // S[t-1,c] (:346)
+                            }
+                        }
+                        if (smask) {
+                            double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
+                            if (Ep) p_h = SD_MUL(p_h, cx.asym);
+#pragma unroll 1
+                            for (int jb = 0; jb < 4; ++jb) {
+                                if (!((smask >> (2 * jb)) & 3u)) continue;
+                                const sd_block hb = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_HH, (uint32_t)jb);
+#pragma unroll
+                                for (int l = 0; l < 2; ++l) {
+                                    const int j = 2 * jb + l;
+                                    if (((smask >> j) & 1u) && sd_lane(hb, l) < p_h)
+                                        push_hit(cx, v, sm, base + j + (j >= pos ? 1 : 0), ((uint32_t)tid << 23) | (127u << 16) | SD_ORD_HH(j), t);
+                                }
+                            }
+                        }
+                        // ---- community push :361-390: decide HOW MANY candidate contacts, queue them
+                        if (!at_home(v, i)) {
+                            if (cx.mode == SEIR_MODE_NATIVE) {
+                                const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
+                                const uint32_t kept = sd_poisson_day(v.seed, i, (uint32_t)t, db, en, SD_MAX_CONTACTS_NATIVE);
+                                for (uint32_t k = 0; k < kept; ++k) push_contact(cx, v, sm, ((uint32_t)tid << 23) | k, t);
+                            } else {
+                                const double *en = cx.enlam + ((size_t)v.phase * kAges + age) * kAges;
+#pragma unroll 1
+                                for (int a = 0; a < kAges; ++a) {
+                                    if (sm.grp_off[a + 1] == sm.grp_off[a]) continue;  // :368-369
+                                    const uint32_t nc = sd_poisson(v.seed, i, (uint32_t)t, SD_SITE_POIS, (uint32_t)a << 8,
+                                                                   __ldg(en + a), SD_MAX_CONTACTS_PER_AGE);
+                                    for (uint32_t j = 0; j < nc; ++j)
+                                        push_contact(cx, v, sm, ((uint32_t)tid << 23) | ((uint32_t)a << 8) | j, t);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            SEIR_STAMP(1);
+            // ================= stage C: candidate contacts, one per thread =================
+            {
+                const uint32_t nc = sm.n_con < (uint32_t)kConCap ? sm.n_con : (uint32_t)kConCap;
+                for (uint32_t q = tid; q < nc; q += kThreads) process_contact(cx, v, sm, sm.conq[q], t);
+            }
+            __syncthreads();
+            SEIR_STAMP(2);
+            // ================= stage H: hits, one per thread =================
+            {
+                const uint32_t nh = sm.n_hit < (uint32_t)kHitCap ? sm.n_hit : (uint32_t)kHitCap;
+                for (uint32_t q = tid; q < nh; q += kThreads) {
+                    const uint2 h = sm.hitq[q];
+                    process_hit(cx, v, sm, h.x, h.y, t);
+                }
+            }
+            __syncthreads();
+            SEIR_STAMP(3);
+            // ================= stage W: write back, re-append survivors =================
+            if (valid && !finalize) {
+                const uint32_t hn = sm.hit_n[tid];
+                if (hn) {
+                    const uint32_t hits = hn & 0xFFFFu, hits_out = hn >> 16;
+                    r.n_inf_by = inc_sat16(r.n_inf_by, hits);                             // :357,:386
+                    if ((st & 7) == C_E) r.n_inf_asympt = inc_sat16(r.n_inf_asympt, hits);  // :358-359,:389-390
+                    r.n_inf_outside = inc_sat16(r.n_inf_outside, hits_out);               // :388
+                    c_hits += hits;
+                    dirty = true;
+                }
+                const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
+                if (nst != st) {
+                    r.state = nst;
+                    if (nq && !(st & ST_Q) && r.t_q_on == NEVER) r.t_q_on = (uint16_t)t;
+                    if (ncomp == C_R || ncomp == C_D) r.t_end = (uint16_t)t;
+                    dirty = true;
+                }
+                keep = ncomp >= C_E && ncomp <= C_CRIT;
+            }
+            if (valid && dirty) store_rec(v.rec + i, r);
+            {   // survivors re-append themselves: one shared-memory atomic per warp
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                if (m) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.n_old, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (keep) {
+                        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < (uint32_t)kOutCap) sm.out_old[pos] = i;
+                        else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
+                    }
+                }
+            }
+            __syncthreads();
+            // flush the staging buffers when the next round could overflow them
+            {
+                const uint32_t so = sm.n_old < (uint32_t)kOutCap ? sm.n_old : (uint32_t)kOutCap;
+                const uint32_t sn = sm.n_new < (uint32_t)kOutCap ? sm.n_new : (uint32_t)kOutCap;
+                const bool fo = so > (uint32_t)(kOutCap - kThreads), fn = sn > (uint32_t)(kOutCap - 2 * kThreads);
+                if (fo || fn) {
+                    if (tid == 0) {
+                        if (fo) sm.base_old = atomicAdd(v.next_old_cnt, so);
+                        if (fn) sm.base_new = atomicAdd(v.next_new_cnt, sn);
+                    }
+                    __syncthreads();
+                    if (fo) for (uint32_t k = tid; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
+                    if (fn) for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (fo) sm.n_old = 0;
+                        if (fn) sm.n_new = 0;
+                    }
+                }
+                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; }
+                __syncthreads();
+            }
+            SEIR_STAMP(4);
+            stamped = true;
+        }
+        stamped = false;
+        SEIR_STAMP(5);
+        {   // per-thread counters -> one shared atomic per warp
+            uint32_t a = c_active, b = c_inf, c = c_hits;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+                c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+            }
+            if (lane == 0) {
+                if (a) atomicAdd(&sm.cnt[0], a);
+                if (b) atomicAdd(&sm.cnt[1], b);
+                if (c) atomicAdd(&sm.cnt[2], c);
             }
         }
         __syncthreads();
-        // ---- agent phase: one queued agent per thread
-        const uint32_t qn = sm.q_count;
-        for (uint32_t e = tid; e < qn; e += kThreads) {
-            const int li = sm.queue[e];
-            process_agent(cx, v, base + li, t, sm.prev[li], sm.ib[li >> 4], sm.tally, sm.cnt);
+        {
+            const uint32_t so = sm.n_old < (uint32_t)kOutCap ? sm.n_old : (uint32_t)kOutCap;
+            const uint32_t sn = sm.n_new < (uint32_t)kOutCap ? sm.n_new : (uint32_t)kOutCap;
+            if (so | sn) {
+                if (tid == 0) {
+                    if (so) sm.base_old = atomicAdd(v.next_old_cnt, so);
+                    if (sn) sm.base_new = atomicAdd(v.next_new_cnt, sn);
+                }
+                __syncthreads();
+                for (uint32_t k = tid; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
+                for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
+            }
         }
-        __syncthreads();
-        if (tid == 0) sm.q_count = 0;
-        // (the next iteration's first __syncthreads orders this reset before the next agent phase;
-        //  queue pushes of the next dense phase need it: fence below)
-        __syncthreads();
-    }
-
-    // ---- flush the per-item tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
-    uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
-    for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
-        const uint32_t val = sm.tally[k];
-        if (val) {
-            const int row = k / kAges;
-            const int day = row < kTalLagRows ? t - 1 : t;
-            if (day < cx.T) atomicAdd(&tal[(size_t)day * TAL_ROWS * kAges + k], val);
+        // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
+        uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
+        for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
+            const uint32_t val = sm.tally[k];
+            if (val) {
+                const int row = k / kAges;
+                const int day = row < kTalLagRows ? t - 1 : t;
+                if (day < cx.T) atomicAdd(&tal[(size_t)day * TAL_ROWS * kAges + k], val);
+            }
         }
-    }
-    if (tid < 3 && sm.cnt[tid]) atomicAdd(&cx.counters[rep * 4 + 1 + tid], sm.cnt[tid]);
-    __syncthreads();
-}
-
-__device__ __forceinline__ void day_pass(const DevCtx &cx, TileSmem &sm, int t)
-{
-    const int items = cx.n_rep * cx.chunks_per_rep;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int rep = it / cx.chunks_per_rep, chunk = it % cx.chunks_per_rep;
-        const int lo = (int)((int64_t)cx.tiles_per_rep * chunk / cx.chunks_per_rep);
-        const int hi = (int)((int64_t)cx.tiles_per_rep * (chunk + 1) / cx.chunks_per_rep);
-        run_item(cx, sm, rep, lo, hi, t);
+        if (tid < 3 && sm.cnt[tid]) atomicAdd(&cx.counters[rep * 4 + 1 + tid], (unsigned long long)sm.cnt[tid]);
+        __syncthreads();
+        SEIR_STAMP(6);
     }
 }
 
@@ -501,6 +668,24 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
         __threadfence();
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// packed state byte of an ever-infected agent on day t, from its record
+__device__ __forceinline__ uint8_t state_on_day(const AgentRec &r, int t)
+{
+    if (t < (int)r.t_exposed) return C_S;
+    const bool ended = r.t_end != NEVER && t >= (int)r.t_end;
+    int comp;
+    if (ended) comp = r.state & 7;
+    else if ((r.flags & F_CRIT) && t >= t_critical_of(r)) comp = C_CRIT;
+    else if ((r.flags & F_SEV) && t >= t_severe_of(r)) comp = C_SEV;
+    else if ((r.flags & F_MILD) && t >= t_infected_of(r)) comp = C_MILD;
+    else comp = C_E;
+    uint8_t s = (uint8_t)comp;
+    if (r.t_q_on != NEVER && t >= (int)r.t_q_on && !ended) s |= ST_Q;
+    if (r.t_documented != 0 && t >= (int)r.t_documented) s |= ST_DOC;
+    return s;
 }
 
 }  // namespace seir

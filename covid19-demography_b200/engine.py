@@ -26,7 +26,9 @@ PLANES_IN_ORDER = ("S", "E", "Mild", "Documented", "Severe", "Critical", "R", "D
 
 EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "seir_get_tallies",
            "seir_get_agent_vector", "seir_get_history", "seir_get_counters", "seir_destroy",
-           "seir_last_error", "seir_device_count", "seir_build_info", "seir_probe_draws")
+           "seir_last_error", "seir_device_count", "seir_build_info", "seir_probe_draws",
+           "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
+           "seir_get_stage_times")
 
 
 class SeirParams(C.Structure):
@@ -49,8 +51,8 @@ class SeirPopulation(C.Structure):
 
 class SeirTables(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("p_mild_severe", "p_severe_critical", "p_critical_death",
-                                          "iso_mean", "iso_asympt_mean", "nat_enlam", "nat_cdf",
-                                          "enlam_pre", "enlam_post")]
+                                          "iso_mean", "iso_asympt_mean", "nat_enlam", "nat_alias_prob",
+                                          "nat_alias_idx", "enlam_pre", "enlam_post")]
 
 
 class SeirReplica(C.Structure):
@@ -74,15 +76,20 @@ def load_library():
     lib.seir_set_params.argtypes = [H, C.POINTER(SeirParams), C.POINTER(SeirTables)]
     lib.seir_run.argtypes = [H, C.POINTER(SeirReplica)]
     lib.seir_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.seir_last_run_ms3.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.seir_get_tallies.argtypes = [H, C.c_int, C.c_void_p]
     lib.seir_get_agent_vector.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.seir_get_history.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.seir_get_counters.argtypes = [H, C.c_int, C.c_void_p]
+    lib.seir_get_day_times.argtypes = [H, C.c_void_p]
+    lib.seir_get_stage_times.argtypes = [H, C.c_void_p]
     lib.seir_destroy.argtypes = [H]
     lib.seir_destroy.restype = None
     lib.seir_last_error.restype = C.c_char_p
     lib.seir_build_info.restype = C.c_char_p
     lib.seir_device_count.restype = C.c_int
+    lib.seir_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    lib.seir_host_unregister.argtypes = [C.c_void_p]
     lib.seir_probe_draws.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -171,7 +178,7 @@ class Engine:
         for k, _ in SeirTables._fields_:
             v = tables.get(k)
             if v is not None:
-                v = np.ascontiguousarray(v, dtype=np.float64)
+                v = np.ascontiguousarray(v, dtype=np.int32 if k == "nat_alias_idx" else np.float64)
             keep[k] = v
             setattr(tb, k, _ptr(v))
         self._tables_keep = keep
@@ -226,6 +233,12 @@ class Engine:
         _check(self.lib.seir_last_run_ms(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def last_run_ms3(self):
+        """(state init, day loop, history materialisation) device milliseconds of the last run."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(self.lib.seir_last_run_ms3(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def tallies(self, replica=0):
         """int64[T, 9, 101]: per-day counts by age, planes S,E,Mild,Documented,Severe,Critical,R,D,Q."""
         out = np.empty((self.T, 9, _tables.N_AGES), dtype=np.int64)
@@ -245,6 +258,22 @@ class Engine:
                                          t0, t1, _ptr(out)))
         return out if which in ("packed", 9) else out.view(np.bool_)
 
+    def day_times_us(self):
+        """Duration of every day pass of the last persistent run in microseconds (index t-1 = pass t)."""
+        out = np.zeros(self.T + 2, dtype=np.int64)
+        _check(self.lib.seir_get_day_times(self._h, _ptr(out)))
+        return np.diff(out[1:]) / 1e3
+
+    def stage_times_us(self):
+        """[T+2, 8] stage stamps (us, relative to the start of each pass) of CTA 0's first round."""
+        out = np.zeros((self.T + 2) * 8, dtype=np.int64)
+        _check(self.lib.seir_get_stage_times(self._h, _ptr(out)))
+        day = np.zeros(self.T + 2, dtype=np.int64)
+        _check(self.lib.seir_get_day_times(self._h, _ptr(day)))
+        st = out.reshape(self.T + 2, 8).astype(np.float64)
+        rel = np.where(st > 0, (st - day[:, None]) / 1e3, np.nan)
+        return rel
+
     def counters(self, replica=0):
         out = np.zeros(4, dtype=np.int64)
         _check(self.lib.seir_get_counters(self._h, replica, _ptr(out)))
@@ -261,6 +290,16 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def pin(array):
+    """Page-lock a NumPy buffer (per-run inputs of Engine.run then move by DMA)."""
+    _check(load_library().seir_host_register(_ptr(array), array.nbytes))
+    return array
+
+
+def unpin(array):
+    _check(load_library().seir_host_unregister(_ptr(array)))
 
 
 def probe_draws(seed, m, mean, mu, sigma, enlam, log_in, device=0):

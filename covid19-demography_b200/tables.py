@@ -41,6 +41,33 @@ def isolation_factor_lut(mean_time_to_isolate_factor, n_ages=N_AGES):
     return lut
 
 
+def alias_table(weights):
+    """Walker/Vose alias table of a non-negative weight vector: (prob float64[K], alias int32[K]).
+    A column b is drawn as: x = u*K, j = floor(x); j if x - j < prob[j] else alias[j]
+    (include/seir_draws.h, sd_alias_pick).  Zero-weight columns get prob 0 and are never returned."""
+    w = np.asarray(weights, dtype=np.float64)
+    K = len(w)
+    scaled = w * (K / w.sum())
+    prob = np.zeros(K, dtype=np.float64)
+    alias = np.arange(K, dtype=np.int32)
+    small = [i for i in range(K) if scaled[i] < 1.0]
+    large = [i for i in range(K) if scaled[i] >= 1.0]
+    scaled = scaled.copy()
+    while small and large:
+        s_, l_ = small.pop(), large.pop()
+        prob[s_] = scaled[s_]
+        alias[s_] = l_
+        scaled[l_] = (scaled[l_] + scaled[s_]) - 1.0
+        (small if scaled[l_] < 1.0 else large).append(l_)
+    for i in large:
+        prob[i] = 1.0
+    for i in small:  # numerical leftovers: weight ~1
+        prob[i] = 1.0 if w[i] > 0 else 0.0
+        if w[i] == 0:  # a zero-weight column must never be returned: alias it to the heaviest column
+            alias[i] = int(np.argmax(w))
+    return prob, alias
+
+
 def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_factor, p_mild_severe,
                  p_severe_critical, p_critical_death, with_replay=True):
     """Returns a dict of C-contiguous float64 arrays keyed like the fields of `seir_tables`."""
@@ -59,14 +86,11 @@ def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_facto
         for w, weight in enumerate((1.0, p["asymptomatic_transmissibility"])):
             nat_enlam[ph, :, w] = np.exp(-(p["p_infect_given_contact"] * weight) * rowsum)
     Cz = np.where(nonempty[None, :], C_pre, 0.0)
-    cdf = np.ones((N_AGES, N_AGES), dtype=np.float64)
+    alias_prob = np.ones((N_AGES, N_AGES), dtype=np.float64)
+    alias_idx = np.tile(np.arange(N_AGES, dtype=np.int32), (N_AGES, 1))
     for a in range(N_AGES):
-        tot = Cz[a].sum()
-        if tot > 0:
-            c = np.cumsum(Cz[a]) / tot
-            last = np.nonzero(Cz[a] > 0)[0][-1]
-            c[last:] = 1.0
-            cdf[a] = c
+        if Cz[a].sum() > 0:
+            alias_prob[a], alias_idx[a] = alias_table(Cz[a])
     out = {
         "p_mild_severe": np.ascontiguousarray(p_mild_severe, dtype=np.float64).reshape(N_AGES, 2, 2),
         "p_severe_critical": np.ascontiguousarray(p_severe_critical, dtype=np.float64).reshape(N_AGES, 2, 2),
@@ -74,7 +98,8 @@ def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_facto
         "iso_mean": np.ascontiguousarray(p["mean_time_to_isolate"] * lut),           # :270
         "iso_asympt_mean": np.ascontiguousarray(p["mean_time_to_isolate_asympt"] * lut),  # :352
         "nat_enlam": nat_enlam,
-        "nat_cdf": cdf,
+        "nat_alias_prob": alias_prob,
+        "nat_alias_idx": alias_idx,
         "enlam_pre": np.exp(-C_pre) if with_replay else None,
         "enlam_post": np.exp(-C_post) if with_replay else None,
     }

@@ -25,7 +25,7 @@ extern "C" {
 
 #define SEIR_N_AGES 101            /* seir_individual.py:153, run_simulation.py:17 */
 #define SEIR_N_TALLY 9             /* S,E,Mild,Documented,Severe,Critical,R,D,Q -- order of :392 */
-#define SEIR_MODE_NATIVE 0         /* community: Poisson(kept contacts) + row-CDF contact age   */
+#define SEIR_MODE_NATIVE 0         /* community: Poisson(kept contacts) + alias-table contact age   */
 #define SEIR_MODE_REPLAY 1         /* community: 101 Poisson draws per sender-day, as :367-374  */
 #define SEIR_LAUNCH_PERSISTENT 0   /* one cooperative kernel over all days, one grid barrier per day */
 #define SEIR_LAUNCH_PER_DAY 1      /* one kernel launch per day (debug / comparison)            */
@@ -83,7 +83,8 @@ typedef struct {
     const double *iso_mean;             /* [101] mean_time_to_isolate * get_isolation_factor(age)         :270 */
     const double *iso_asympt_mean;      /* [101] mean_time_to_isolate_asympt * get_isolation_factor(age)  :352 */
     const double *nat_enlam;            /* [2,101,2] exp(-p*w*rowsum) : phase (0 before lockdown, 1 after), age, w (0 symptomatic, 1 E) */
-    const double *nat_cdf;              /* [101,101] row CDF of the contact matrix over non-empty age groups */
+    const double *nat_alias_prob;       /* [101,101] alias table (Vose) of each contact-matrix row over non-empty age groups */
+    const int32_t *nat_alias_idx;       /* [101,101] alias column                                                 */
     const double *enlam_pre;            /* [101,101] exp(-C)                  (replay mode; may be NULL in native mode) */
     const double *enlam_post;           /* [101,101] exp(-C/lockdown_factor)  (replay mode)                             */
 } seir_tables;
@@ -133,8 +134,11 @@ int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables
 int seir_run(seir_handle *h, const seir_replica *reps);
 
 /* Device time of the last seir_run, CUDA events on the launching stream:
- * *day_loop_ms = the day loop (persistent kernel or T-1 launches), *total_ms = init + day loop. */
+ * *day_loop_ms = the day loop (persistent kernel or T launches),
+ * *total_ms = state init + day loop + materialisation of the T x n packed history. */
 int seir_last_run_ms(seir_handle *h, float *day_loop_ms, float *total_ms);
+/* The three timed segments of the last run: state init, day loop, history materialisation. */
+int seir_last_run_ms3(seir_handle *h, float *init_ms, float *day_loop_ms, float *materialize_ms);
 
 /* Per-day compartment counts by age, out[T][9][101] int64, planes in the order of :392
  * (what the drivers compute with X.sum(axis=1) and the per-age-group masks). */
@@ -150,6 +154,17 @@ int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uin
  * A(t-1) (E/Mild/Severe/Critical), out[2]=infections I (excluding the initial ones),
  * out[3]=transmission hits (>= infections: same-day multiple hits count). */
 int seir_get_counters(seir_handle *h, int replica, int64_t *out4);
+
+/* %globaltimer (ns) stamped by CTA 0 at the start of every day pass of the last run: out[T+2],
+ * out[t] = start of pass t (1 <= t <= T), out[T+1] = end of the persistent day loop (0 in per-day mode). */
+int seir_get_day_times(seir_handle *h, int64_t *out);
+/* Stage stamps of CTA 0 in the first round of every pass: out[(T+2)*8], per pass t the 7 stamps
+ * pass set-up done / stage A / C / H / W done / lists flushed / tallies flushed (0 where not reached). */
+int seir_get_stage_times(seir_handle *h, int64_t *out);
+
+/* Page-lock / unlock a caller-owned host buffer so the per-run copies in seir_run are DMA transfers. */
+int seir_host_register(void *ptr, uint64_t bytes);
+int seir_host_unregister(void *ptr);
 
 void seir_destroy(seir_handle *h);
 const char *seir_last_error(void);

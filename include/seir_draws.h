@@ -61,16 +61,18 @@
 /* ---- draw sites ------------------------------------------------------- */
 enum {
     SD_SITE_ACT = 1,    /* E->Mild   (seir_individual.py:262-270) sub0: lane0=D1 lane1=D2; sub1: lane0=D3 */
-    SD_SITE_DOC = 2,    /* Mild documentation (:282)              lane0=D4                              */
+    SD_SITE_DAY = 2,    /* the agent's day block, sub0: lane0 = D4 Mild documentation (:282),
+                           lane1 = first Knuth uniform of the native kept-contact count              */
     SD_SITE_SEV = 3,    /* Mild->Severe (:306-310)                lane0=D5 lane1=D6                     */
     SD_SITE_CRIT = 4,   /* Severe->Critical (:316-320)            lane0=D7 lane1=D8                     */
-    SD_SITE_HH = 5,     /* household push (:346)  sub=slot j      lane0=D9                              */
+    SD_SITE_HH = 5,     /* household push (:346)  slot j: sub = j>>1, lane = j&1   (D9)                 */
     SD_SITE_INF = 6,    /* infectee timers (:352,356,381,385) agent=INFECTOR, sub=(ord<<8)|call:
                            call0 lane0 = time_to_isolate exponential, calls 1.. = polar normal tries   */
     SD_SITE_POIS = 7,   /* replay community Poisson (:370) sub=(contact_age<<8)|call, Knuth products    */
     SD_SITE_KEEP = 8,   /* replay contact (:373,374) sub=(contact_age<<8)|j lane0=D13, words2,3=D14     */
-    SD_SITE_NCNT = 9,   /* native community: kept-contact count, sub=call                               */
-    SD_SITE_NPICK = 10, /* native community: sub=k, lane0 -> contact age, words2,3 -> member index      */
+    SD_SITE_NCNT = 9,   /* native community: kept-contact count, Knuth uniforms 2,3,.. (sub=call, lanes 0,1);
+                           uniform 1 is lane1 of the day block                                         */
+    SD_SITE_NPICK = 10, /* native community: sub=k, lane0 -> contact age (alias table), words2,3 -> member index */
     SD_SITE_TR_HH = 11, /* tracing, household edge (:72)  agent=tracer sub=slot j lane0                 */
     SD_SITE_TR_OUT = 12,/* tracing, outside edge (:83)    agent=tracer sub=log slot j lane0             */
     SD_SITE_INIT = 13   /* prologue (:227) activation time of an initially infected agent, polar calls  */
@@ -275,6 +277,35 @@ SD_FN uint32_t sd_poisson(uint64_t seed, uint32_t agent, uint32_t day, uint32_t 
         if (prod <= enlam || X >= cap) return X;
         X += 1;
     }
+}
+
+/* native kept-contact count: Knuth product whose FIRST uniform is lane 1 of the agent's day block
+ * `day` (so that most agent-days need a single Philox block), the rest come from SD_SITE_NCNT */
+SD_FN uint32_t sd_poisson_day(uint64_t seed, uint32_t agent, uint32_t day, sd_block day_block, double enlam, uint32_t cap)
+{
+    double prod = sd_lane(day_block, 1);
+    if (prod <= enlam) return 0;
+    uint32_t X = 1;
+    for (uint32_t call = 0;; ++call) {
+        sd_block b = sd_draw(seed, agent, day, SD_SITE_NCNT, call);
+        prod = SD_MUL(prod, sd_lane(b, 0));
+        if (prod <= enlam || X >= cap) return X;
+        X += 1;
+        prod = SD_MUL(prod, sd_lane(b, 1));
+        if (prod <= enlam || X >= cap) return X;
+        X += 1;
+    }
+}
+
+/* contact age of a kept contact: Walker/Vose alias table of the sender's contact-matrix row
+ * (n_ages columns: prob[b] in [0,1], alias[b]); one table look-up instead of a CDF search */
+SD_FN int sd_alias_pick(double u, const double *prob_row, const int32_t *alias_row, int n_ages)
+{
+    double x = SD_MUL(u, (double)n_ages);
+    int b = (int)x;
+    if (b > n_ages - 1) b = n_ages - 1;
+    double frac = SD_SUB(x, (double)b);
+    return (frac < prob_row[b]) ? b : (int)alias_row[b];
 }
 
 /* saturating day encoding used by the device records: nan/inf/>=65535 -> 0xFFFF ("never") */

@@ -46,7 +46,7 @@ class Params(C.Structure):
 _IN_FIELDS = ["households", "age", "diabetes", "hypertension", "group_offsets", "group_members",
               "contact_matrix", "p_mild_severe", "p_severe_critical", "p_critical_death", "iso_factor",
               "p_infect_household", "fraction_stay_home", "home_real", "initial_infected",
-              "enlam_pre", "enlam_post", "nat_enlam", "nat_cdf"]
+              "enlam_pre", "enlam_post", "nat_enlam", "nat_alias_prob", "nat_alias_idx"]
 _OUT_FIELDS = ["S", "E", "Mild", "Documented", "Severe", "Critical", "R", "D", "Q",
                "num_infected_by", "time_documented", "time_to_activation", "time_to_death",
                "time_to_recovery", "time_critical", "time_exposed", "num_infected_asympt",
@@ -98,7 +98,7 @@ def run_model(seed, households, age, age_groups, diabetes, hypertension, contact
     provider "mt": numba-compatible MT19937 stream, bit-identical to the reference.
     provider "replay"/"native": keyed Philox draws (include/seir_draws.h); the prologue results
     `home_real`, `initial_infected` and the draw tables `tables` (dict with enlam_pre, enlam_post,
-    nat_enlam, nat_cdf) come from the host code under test.
+    nat_enlam, nat_alias_prob, nat_alias_idx) come from the host code under test.
     """
     prov = PROVIDERS[provider]
     n = int(params["n"]); T = int(params["T"]); n_ages = int(params["n_ages"])
@@ -142,10 +142,13 @@ def run_model(seed, households, age, age_groups, diabetes, hypertension, contact
         P.n_initial = ii.shape[0]
         I.home_real, I.initial_infected = _ptr(hr), _ptr(ii)
         tb = {k: np.ascontiguousarray(tables[k], dtype=np.float64)
-              for k in ("enlam_pre", "enlam_post", "nat_enlam", "nat_cdf")}
+              for k in ("enlam_pre", "enlam_post", "nat_enlam", "nat_alias_prob")}
+        tb["nat_alias_idx"] = np.ascontiguousarray(tables["nat_alias_idx"], dtype=np.int32)
         assert tb["enlam_pre"].shape == (n_ages, n_ages) and tb["nat_enlam"].shape == (2, n_ages, 2)
+        assert tb["nat_alias_prob"].shape == (n_ages, n_ages) and tb["nat_alias_idx"].shape == (n_ages, n_ages)
         I.enlam_pre, I.enlam_post = _ptr(tb["enlam_pre"]), _ptr(tb["enlam_post"])
-        I.nat_enlam, I.nat_cdf = _ptr(tb["nat_enlam"]), _ptr(tb["nat_cdf"])
+        I.nat_enlam = _ptr(tb["nat_enlam"])
+        I.nat_alias_prob, I.nat_alias_idx = _ptr(tb["nat_alias_prob"]), _ptr(tb["nat_alias_idx"])
         keep += [hr, ii, tb]
         n_init = ii.shape[0]
     else:

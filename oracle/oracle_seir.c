@@ -26,7 +26,7 @@
  * include/seir_draws.h; those are what the CUDA kernels are compared with.
  * NATIVE replaces the per-sender loop over 101 Poisson draws (:367-374) by the
  * distribution-identical "Poisson number of kept contacts, then contact age
- * from the row CDF" (Poisson superposition + thinning).
+ * from the row's alias table" (Poisson superposition + thinning).
  */
 #include <math.h>
 #include <stdint.h>
@@ -206,9 +206,10 @@ typedef struct {
     const int64_t *initial_infected; /* [n_initial] */
     /* keyed replay: exp(-C) before / after lockdown, [n_ages,n_ages] each */
     const double *enlam_pre, *enlam_post;
-    /* keyed native: exp(-p*w*rowsum) [2 phases][n_ages][2: 0=symptomatic,1=E], row CDF [n_ages,n_ages] */
+    /* keyed native: exp(-p*w*rowsum) [2 phases][n_ages][2: 0=symptomatic,1=E], row alias tables */
     const double *nat_enlam;
-    const double *nat_cdf;
+    const double *nat_alias_prob;   /* [n_ages,n_ages] */
+    const int32_t *nat_alias_idx;   /* [n_ages,n_ages] */
 } oracle_inputs;
 
 typedef struct {
@@ -487,7 +488,7 @@ int oracle_run_model(const oracle_params *p, const oracle_inputs *in, oracle_out
                     continue;
                 }
                 if (Mp[i] && !Dp[i]) { /* :280-289 */
-                    if (U(c, i, t, SD_SITE_DOC, 0, 0) < p->p_documented_in_mild) {
+                    if (U(c, i, t, SD_SITE_DAY, 0, 0) < p->p_documented_in_mild) {
                         Dn[i] = 1;
                         time_documented[i] = td;
                         traced[i] = 1;
@@ -559,7 +560,7 @@ int oracle_run_model(const oracle_params *p, const oracle_inputs *in, oracle_out
                         int64_t contact = households[i * W + j];
                         double infectiousness = in->p_infect_household[i];
                         if (Ep[i]) infectiousness *= p->asymptomatic_transmissibility;
-                        if (Sp[contact] && U(c, i, t, SD_SITE_HH, (uint32_t)j, 0) < infectiousness) {
+                        if (Sp[contact] && U(c, i, t, SD_SITE_HH, (uint32_t)j >> 1, (int)(j & 1)) < infectiousness) {
                             infect(c, i, contact, t, SD_ORD_HH(j));
                             num_infected_by[i] += 1;
                             if (Ep[i]) num_infected_asympt[i] += 1;
@@ -608,24 +609,16 @@ int oracle_run_model(const oracle_params *p, const oracle_inputs *in, oracle_out
                         } else {
                             /* distribution-identical aggregation of :367-374:
                                kept contacts ~ Poisson(p*w*rowsum(C[age_i,:] over non-empty groups)),
-                               each kept contact's age ~ C[age_i,:]/rowsum, member uniform in that group */
+                               each kept contact's age ~ C[age_i,:]/rowsum (alias table), member uniform in that group */
                             const double en = in->nat_enlam[((int64_t)phase * n_ages + age[i]) * 2 + (Ep[i] ? 1 : 0)];
-                            c->blocks++;
-                            uint32_t kept = sd_poisson(p->seed, (uint32_t)i, (uint32_t)t, SD_SITE_NCNT, 0, en,
-                                                       SD_MAX_CONTACTS_NATIVE);
-                            const double *cdf = in->nat_cdf + age[i] * n_ages;
+                            uint32_t kept = sd_poisson_day(p->seed, (uint32_t)i, (uint32_t)t,
+                                                           K(c, i, t, SD_SITE_DAY, 0), en, SD_MAX_CONTACTS_NATIVE);
                             for (uint32_t k = 0; k < kept; k++) {
                                 sd_block b = K(c, i, t, SD_SITE_NPICK, k);
-                                double u = sd_lane(b, 0);
-                                /* first age with u < cdf (binary search over the non-decreasing row) */
-                                int64_t lo = 0, hi = n_ages - 1;
-                                while (lo < hi) {
-                                    int64_t mid = (lo + hi) >> 1;
-                                    if (u < cdf[mid]) hi = mid; else lo = mid + 1;
-                                }
-                                int64_t contact_age = lo;
+                                int64_t contact_age = sd_alias_pick(sd_lane(b, 0), in->nat_alias_prob + age[i] * n_ages,
+                                                                    in->nat_alias_idx + age[i] * n_ages, (int)n_ages);
                                 int64_t glen = in->group_offsets[contact_age + 1] - in->group_offsets[contact_age];
-                                if (glen == 0) continue; /* only reachable through rounding of the last CDF step */
+                                if (glen == 0) continue; /* zero-weight columns are never picked; belt and braces */
                                 int64_t contact = in->group_members[in->group_offsets[contact_age] +
                                                                     (int64_t)sd_index(b, (uint64_t)glen)];
                                 if (Sp[contact] && !(Home && Home[contact])) {

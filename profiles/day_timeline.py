@@ -1,0 +1,29 @@
+"""Per-day device timeline of one C2 run (persistent kernel, %globaltimer stamps of CTA 0) next to the
+day's active-agent count.   python profiles/day_timeline.py [n] [replicas]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import bench
+from covid19_demography_b200 import engine, population, tables
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+p, tabs = bench.workload_params(n, 60)
+hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
+tb = tables.build_tables(tabs["contact_matrix"], np.array([len(g) for g in groups]), tables.params_to_dict(p),
+                         tabs["mean_time_to_isolate_factor"], tabs["p_mild_severe"], tabs["p_severe_critical"],
+                         tabs["p_critical_death"], with_replay=False)
+eng = engine.Engine(p, hh, age, groups, diab, hyp, np.full(n, tabs["p_infect_household"]), tb, n_replicas=R)
+rng = np.random.default_rng(100)
+for k in range(4):
+    init = [rng.choice(n, size=int(os.environ.get("NINIT", "5")), replace=False).astype(np.int64) for _ in range(R)]
+    eng.run([k * 64 + r for r in range(R)], None, init)
+us = eng.day_times_us()
+tal = eng.tallies(0)
+act = tal[:, [1, 2, 4, 5], :].sum(axis=(1, 2))
+print("init/loop/materialize ms:", eng.last_run_ms3(), "sum of passes us: %.1f" % us.sum())
+st = eng.stage_times_us()
+for t in range(1, len(us) + 1):
+    print("pass %2d  %7.2f us   active(t-1)=%-7d stages(setup,A,C,H,W,lists,tallies): %s"
+          % (t, us[t - 1], act[t - 1] if t - 1 < len(act) else -1, " ".join("%6.2f" % x for x in st[t, :7])))
