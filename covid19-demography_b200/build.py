@@ -31,7 +31,7 @@ def is_stale():
 def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + SOURCES
+    cmd = [NVCC] + FLAGS + os.environ.get("SEIR_NVCC_EXTRA", "").split() + ["-o", LIB] + SOURCES
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)

@@ -13,9 +13,11 @@ using namespace seir;
 #define SEIR_STR(x) SEIR_STR2(x)
 
 // ------------------------------------------------------------------ kernels
+extern __shared__ __align__(16) unsigned char seir_smem_raw[];
+
 __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(const __grid_constant__ DevCtx cx)
 {
-    __shared__ PassSmem sm;
+    PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     // the host resets the barrier counter to 0 before each launch
     stage_tables(cx, sm);
     for (int t = 1; t <= cx.T; ++t) {
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
 
 __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __grid_constant__ DevCtx cx, int t)
 {
-    __shared__ PassSmem sm;
+    PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
     stage_tables(cx, sm);
     day_pass(cx, sm, t);
@@ -57,18 +59,19 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
     for (int64_t k = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = init_ids[k];
         const uint64_t seed = cx.seeds[rep];
-        AgentRec r = AgentRec{};
-        r.t_exposed = 0;
-        r.tt_activation = sd_enc16(sd_lognormal_days(seed, (uint32_t)a, 0, SD_SITE_INIT, 0, cx.act_mu, cx.act_sigma));
-        r.t_end = NEVER;
-        r.t_q_on = NEVER;
-        r.stat = cx.stat[a];
-        r.state = C_E;
+        AgentRec r;
+        r.clear();
+        r.set_t_exposed(0);
+        r.set_tt_activation(sd_enc16(sd_lognormal_days(seed, (uint32_t)a, 0, SD_SITE_INIT, 0, cx.act_mu, cx.act_sigma)));
+        r.set_t_end(NEVER);
+        r.set_t_q_on(NEVER);
+        r.set_stat(cx.stat[a]);
+        r.set_state(C_E);
         store_rec(cx.rec + (size_t)rep * cx.n_pad + a, r);
         cx.winner[(size_t)rep * cx.n_pad + a] = 1ull;  // day 0, never susceptible again
         atomicOr(cx.inbox + (size_t)rep * (cx.n_pad / 16) + (a >> 4), inbox_infected_bit((int)(a & 15)));
         cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + (k - lo)] = (uint32_t)a;
-        atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat & 127), 1u);
+        atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat() & 127), 1u);
     }
 }
 
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) seir_materialize_kernel(DevCtx cx)
             const int k = (bit & 7) * 4 + (bit >> 3);  // inverse of inbox_infected_bit
             const int64_t i = vi * kVec + k;
             const AgentRec r = load_rec(cx.rec + (size_t)rep * cx.n_pad + i);
-            for (int t = r.t_exposed; t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t);
+            for (int t = r.t_exposed(); t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t);
         }
     }
 }
@@ -127,20 +130,20 @@ __global__ void seir_agent_vector_kernel(DevCtx cx, int rep, int which, double *
         } else {
             const AgentRec r = rec[i];
             switch (which) {
-                case SEIR_VEC_NUM_INFECTED_BY: v = r.n_inf_by; break;
-                case SEIR_VEC_TIME_DOCUMENTED: v = r.t_documented; break;
-                case SEIR_VEC_TIME_TO_ACTIVATION: v = dec16(r.tt_activation); break;
-                case SEIR_VEC_TIME_TO_DEATH: v = dec16(r.tt_death); break;
-                case SEIR_VEC_TIME_TO_RECOVERY: v = dec16(r.tt_recovery); break;
-                case SEIR_VEC_TIME_CRITICAL: v = (r.flags & F_CRIT) ? t_critical_of(r) : 0; break;
-                case SEIR_VEC_TIME_EXPOSED: v = r.t_exposed; break;
-                case SEIR_VEC_NUM_INFECTED_ASYMPT: v = r.n_inf_asympt; break;
-                case SEIR_VEC_TIME_INFECTED: v = (r.flags & F_MILD) ? t_infected_of(r) : 0; break;
-                case SEIR_VEC_TIME_TO_SEVERE: v = dec16(r.tt_severe); break;
-                case SEIR_VEC_TIME_TO_ISOLATE: v = dec16(r.tt_isolate); break;
-                case SEIR_VEC_TIME_SEVERE: v = (r.flags & F_SEV) ? t_severe_of(r) : 0; break;
-                case SEIR_VEC_TIME_TO_CRITICAL: v = dec16(r.tt_critical); break;
-                default: v = r.n_inf_outside; break;
+                case SEIR_VEC_NUM_INFECTED_BY: v = r.n_inf_by(); break;
+                case SEIR_VEC_TIME_DOCUMENTED: v = r.t_documented(); break;
+                case SEIR_VEC_TIME_TO_ACTIVATION: v = dec16(r.tt_activation()); break;
+                case SEIR_VEC_TIME_TO_DEATH: v = dec16(r.tt_death()); break;
+                case SEIR_VEC_TIME_TO_RECOVERY: v = dec16(r.tt_recovery()); break;
+                case SEIR_VEC_TIME_CRITICAL: v = (r.flags() & F_CRIT) ? t_critical_of(r) : 0; break;
+                case SEIR_VEC_TIME_EXPOSED: v = r.t_exposed(); break;
+                case SEIR_VEC_NUM_INFECTED_ASYMPT: v = r.n_inf_asympt(); break;
+                case SEIR_VEC_TIME_INFECTED: v = (r.flags() & F_MILD) ? t_infected_of(r) : 0; break;
+                case SEIR_VEC_TIME_TO_SEVERE: v = dec16(r.tt_severe()); break;
+                case SEIR_VEC_TIME_TO_ISOLATE: v = dec16(r.tt_isolate()); break;
+                case SEIR_VEC_TIME_SEVERE: v = (r.flags() & F_SEV) ? t_severe_of(r) : 0; break;
+                case SEIR_VEC_TIME_TO_CRITICAL: v = dec16(r.tt_critical()); break;
+                default: v = r.n_inf_outside(); break;
             }
         }
         out[i] = v;
@@ -230,7 +233,7 @@ struct seir_handle {
     DevBuf<double> p_hh, tables, enlam, stage_d;
     DevBuf<uint8_t> hist, stage_u8;
     DevBuf<uint32_t> inbox, tally, home, list_old, list_new, list_cnt;
-    DevBuf<unsigned long long> winner, counters, day_ns, stage_ns;
+    DevBuf<unsigned long long> winner, counters, day_ns, stage_ns, fine_ns;
     DevBuf<AgentRec> rec;
     DevBuf<uint64_t> seeds;
     DevBuf<unsigned int> barrier;
@@ -292,6 +295,8 @@ static int alloc_state(seir_handle *h)
     CK(h->list_cnt.alloc(R * 2 * (T + 2)));
     CK(h->day_ns.alloc(T + 2));
     CK(cudaMemset(h->day_ns.p, 0, (T + 2) * 8));
+    CK(h->fine_ns.alloc((T + 2) * 16));
+    CK(cudaMemset(h->fine_ns.p, 0, (T + 2) * 16 * 8));
     CK(h->stage_ns.alloc((T + 2) * 8));
     CK(cudaMemset(h->stage_ns.p, 0, (T + 2) * 8 * 8));
     h->T_alloc = h->prm.T;
@@ -316,7 +321,7 @@ static void fill_ctx(seir_handle *h)
     c.enlam = h->replay_tables ? h->enlam.p : nullptr;
     c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
-    c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p;
+    c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
     c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
     c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
     c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
@@ -446,7 +451,12 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         if (upload_tables(h, tables)) break;
         // persistent grid: every CTA must be co-resident
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel, kThreads, 0) != cudaSuccess || occ < 1) {
+        if (cudaFuncSetAttribute(seir_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_day_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess) {
+            fail("cannot reserve shared memory for the day-step kernels");
+            break;
+        }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel, kThreads, sizeof(PassSmem)) != cudaSuccess || occ < 1) {
             fail("occupancy query failed for seir_persistent_kernel");
             break;
         }
@@ -531,11 +541,11 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaEventRecord(h->ev1, h->stream));
     if (h->prm.launch == SEIR_LAUNCH_PERSISTENT) {
         void *args[] = {&h->cx};
-        CK(cudaLaunchCooperativeKernel((const void *)seir_persistent_kernel, dim3(h->grid), dim3(kThreads), args, 0, h->stream));
+        CK(cudaLaunchCooperativeKernel((const void *)seir_persistent_kernel, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
         ++h->launches;
     } else {
         for (int t = 1; t <= h->prm.T; ++t) {
-            seir_day_kernel<<<h->grid, kThreads, 0, h->stream>>>(h->cx, t);
+            seir_day_kernel<<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
             ++h->launches;
         }
         CK(cudaGetLastError());
@@ -658,6 +668,16 @@ int seir_get_stage_times(seir_handle *h, int64_t *out)
     return 0;
 }
 
+int seir_get_fine_times(seir_handle *h, int64_t *out)
+{
+    if (!h || !out) return fail("seir_get_fine_times: NULL argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<unsigned long long> v(((size_t)h->prm.T + 2) * 16);
+    CK(cudaMemcpy(v.data(), h->fine_ns.p, v.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < v.size(); ++k) out[k] = (int64_t)v[k];
+    return 0;
+}
+
 int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
 {
     if (!h || !out4) return fail("seir_get_counters: NULL argument");
@@ -692,7 +712,7 @@ void seir_destroy(seir_handle *h)
     h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
     h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release();
     h->list_old.release(); h->list_new.release(); h->list_cnt.release(); h->day_ns.release();
-    h->alias_idx.release(); h->stage_ns.release();
+    h->alias_idx.release(); h->stage_ns.release(); h->fine_ns.release();
     if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -58,24 +58,40 @@ constexpr uint16_t NEVER = 0xFFFFu;
 // 32 B per-agent record.  Derived days: t_infected = t_exposed + tt_activation (F_MILD),
 // t_severe = t_infected + tt_severe (F_SEV), t_critical = t_severe + tt_critical (F_CRIT) -- the reference
 // fires those transitions exactly when `t - t0 == tt` (:257,:291,:312).
+// Kept as eight 32-bit words with constant-index accessors so that it lives in REGISTERS (a struct of
+// sixteen uint16 fields ends up in local memory as soon as its address is taken).
 struct __align__(16) AgentRec {
-    uint16_t t_exposed;      // :200,:355
-    uint16_t tt_activation;  // :218,:356
-    uint16_t tt_severe;      // :213,:263  (0xFFFF == inf)
-    uint16_t tt_recovery;    // :214
-    uint16_t tt_critical;    // :215
-    uint16_t tt_death;       // :216
-    uint16_t tt_isolate;     // :217
-    uint16_t t_documented;   // :204
-    uint16_t n_inf_by;       // :207
-    uint16_t n_inf_asympt;   // :209
-    uint16_t n_inf_outside;  // :208
-    uint16_t t_end;          // day of R or D (0xFFFF: none yet)
-    uint16_t t_q_on;         // first day with Q set (0xFFFF: never)
-    uint16_t stat;           // copy of the static word
-    uint8_t state;           // current packed state byte
-    uint8_t flags;           // F_*
-    uint16_t spare;
+    uint32_t w[8];
+#define SEIR_FIELD(name, idx)                                                                                          \
+    __host__ __device__ __forceinline__ uint16_t name() const { return (uint16_t)(w[(idx) >> 1] >> (((idx)&1) * 16)); } \
+    __host__ __device__ __forceinline__ void set_##name(uint32_t v)                                                    \
+    {                                                                                                                  \
+        w[(idx) >> 1] = ((idx)&1) ? ((w[(idx) >> 1] & 0x0000FFFFu) | (v << 16)) : ((w[(idx) >> 1] & 0xFFFF0000u) | (v & 0xFFFFu)); \
+    }
+    SEIR_FIELD(t_exposed, 0)      // :200,:355
+    SEIR_FIELD(tt_activation, 1)  // :218,:356
+    SEIR_FIELD(tt_severe, 2)      // :213,:263  (0xFFFF == inf)
+    SEIR_FIELD(tt_recovery, 3)    // :214
+    SEIR_FIELD(tt_critical, 4)    // :215
+    SEIR_FIELD(tt_death, 5)       // :216
+    SEIR_FIELD(tt_isolate, 6)     // :217
+    SEIR_FIELD(t_documented, 7)   // :204
+    SEIR_FIELD(n_inf_by, 8)       // :207
+    SEIR_FIELD(n_inf_asympt, 9)   // :209
+    SEIR_FIELD(n_inf_outside, 10) // :208
+    SEIR_FIELD(t_end, 11)         // day of R or D (0xFFFF: none yet)
+    SEIR_FIELD(t_q_on, 12)        // first day with Q set (0xFFFF: never)
+    SEIR_FIELD(stat, 13)          // copy of the static word
+#undef SEIR_FIELD
+    __host__ __device__ __forceinline__ uint8_t state() const { return (uint8_t)(w[7] & 0xFFu); }         // packed state byte
+    __host__ __device__ __forceinline__ uint8_t flags() const { return (uint8_t)((w[7] >> 8) & 0xFFu); }  // F_*
+    __host__ __device__ __forceinline__ void set_state(uint32_t v) { w[7] = (w[7] & ~0xFFu) | (v & 0xFFu); }
+    __host__ __device__ __forceinline__ void set_flags(uint32_t v) { w[7] = (w[7] & ~0xFF00u) | ((v & 0xFFu) << 8); }
+    __host__ __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = 0;
+    }
 };
 static_assert(sizeof(AgentRec) == 32, "AgentRec must be one 32 B sector");
 
@@ -125,6 +141,7 @@ struct DevCtx {
     unsigned long long *counters;  // [rep][4]
     unsigned int *barrier;         // grid barrier counter
     unsigned long long *day_ns;    // [T+2] %globaltimer at the start of pass t (CTA 0), [T+1] = end of the loop
+    unsigned long long *fine_ns;   // [T+2][16] debug stamps inside stage A (only with -DSEIR_FINE_STAMPS)
     unsigned long long *stage_ns;  // [T+2][8] CTA 0, first round of pass t: stamps after init / A / C / H / W / flush / end
     // scalars
     int t_lockdown, t_stayhome;
@@ -148,23 +165,22 @@ __device__ __forceinline__ bool due(int t, int t0, uint16_t tt) { return tt != N
 
 __device__ __forceinline__ AgentRec load_rec(const AgentRec *p)
 {
-    union { AgentRec r; uint4 v[2]; } u;
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    u.v[0] = __ldcg(q);
-    u.v[1] = __ldcg(q + 1);
-    return u.r;
+    const uint4 a = __ldcg(q), b = __ldcg(q + 1);
+    AgentRec r;
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+    r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+    return r;
 }
 __device__ __forceinline__ void store_rec(AgentRec *p, const AgentRec &r)
 {
-    union { AgentRec r; uint4 v[2]; } u;
-    u.r = r;
     uint4 *q = reinterpret_cast<uint4 *>(p);
-    __stcg(q, u.v[0]);
-    __stcg(q + 1, u.v[1]);
+    __stcg(q, make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]));
+    __stcg(q + 1, make_uint4(r.w[4], r.w[5], r.w[6], r.w[7]));
 }
-__device__ __forceinline__ int t_infected_of(const AgentRec &r) { return (int)r.t_exposed + (int)r.tt_activation; }
-__device__ __forceinline__ int t_severe_of(const AgentRec &r) { return t_infected_of(r) + (int)r.tt_severe; }
-__device__ __forceinline__ int t_critical_of(const AgentRec &r) { return t_severe_of(r) + (int)r.tt_critical; }
+__device__ __forceinline__ int t_infected_of(const AgentRec &r) { return (int)r.t_exposed() + (int)r.tt_activation(); }
+__device__ __forceinline__ int t_severe_of(const AgentRec &r) { return t_infected_of(r) + (int)r.tt_severe(); }
+__device__ __forceinline__ int t_critical_of(const AgentRec &r) { return t_severe_of(r) + (int)r.tt_critical(); }
 
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
@@ -173,18 +189,90 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return v;
 }
 
-// per-CTA shared state of a day pass.  A ROUND takes kThreads list entries through four
-// convergent stages separated by __syncthreads(): A agents -> C contacts -> H hits -> W write-back.
-constexpr int kConCap = 2 * kThreads;  // contact queue entries per round
-constexpr int kHitCap = 2 * kThreads;  // hit queue entries per round
+#ifdef SEIR_FINE_STAMPS
+#define SEIR_FINE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && slot == 0) cx.fine_ns[(size_t)t * 16 + (k)] = global_timer_ns(); } while (0)
+#else
+#define SEIR_FINE(k) do { } while (0)
+#endif
+// ---- out-of-line draw helpers ----------------------------------------------------------------------------
+// The day step is latency-bound and its code is executed by few warps per pass, so instruction fetch is
+// on the critical path: every heavy piece of the draw contract exists ONCE in the kernel image.
+__device__ __noinline__ uint4 draw4(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub)
+{
+    const sd_block b = sd_draw(seed, agent, day, site, sub);
+    return make_uint4(b.w[0], b.w[1], b.w[2], b.w[3]);
+}
+__device__ __forceinline__ sd_block as_block(uint4 v)
+{
+    sd_block b;
+    b.w[0] = v.x; b.w[1] = v.y; b.w[2] = v.z; b.w[3] = v.w;
+    return b;
+}
+__device__ __forceinline__ sd_block draw_block(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub)
+{
+    return as_block(draw4(seed, agent, day, site, sub));
+}
+__device__ __noinline__ double exp_days_ni(double u, double mean) { return sd_exp_days(u, mean); }
+__device__ __noinline__ double lognormal_days_ni(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub_base,
+                                                 double mu, double sigma)
+{
+    return sd_lognormal_days(seed, agent, day, site, sub_base, mu, sigma);
+}
+// continuation of sd_poisson_day after the first uniform (lane 1 of the day block) did not end the product
+__device__ __noinline__ uint32_t poisson_day_more(uint64_t seed, uint32_t agent, uint32_t day, double prod, double enlam, uint32_t cap)
+{
+    uint32_t X = 1;
+    for (uint32_t call = 0;; ++call) {
+        const sd_block b = sd_draw(seed, agent, day, SD_SITE_NCNT, call);
+        prod = SD_MUL(prod, sd_lane(b, 0));
+        if (prod <= enlam || X >= cap) return X;
+        X += 1;
+        prod = SD_MUL(prod, sd_lane(b, 1));
+        if (prod <= enlam || X >= cap) return X;
+        X += 1;
+    }
+}
+__device__ __noinline__ uint32_t poisson_ni(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub_base,
+                                            double enlam, uint32_t cap)
+{
+    return sd_poisson(seed, agent, day, site, sub_base, enlam, cap);
+}
+
+// per-CTA shared state of a day pass.  A ROUND takes up to kSlots list entries through four convergent
+// stages separated by __syncthreads(): A agents -> C contacts -> H hits -> W infector counters.
+// No per-thread state survives a stage: stages talk through the queues below and the records in L2.
+#ifndef SEIR_ENTRIES_PER_THREAD
+#define SEIR_ENTRIES_PER_THREAD 4
+#endif
+constexpr int kPerThread = SEIR_ENTRIES_PER_THREAD;  // list entries a thread takes through stage A per round
+constexpr int kSlots = kPerThread * kThreads;        // agents per round and CTA
+constexpr int kConCap = kSlots;                      // contact queue entries per round
+constexpr int kHitCap = kSlots / 2;                  // hit queue entries per round
+constexpr int kOutOld = 2 * kSlots;                  // staged survivors
+constexpr int kOutNew = kSlots;                      // staged new infectees
+struct RepView {
+    uint32_t *inbox;
+    unsigned long long *winner;
+    AgentRec *rec;
+    const uint32_t *home;
+    uint32_t *next_old, *next_new;          // tomorrow's lists
+    uint32_t *next_old_cnt, *next_new_cnt;
+    uint64_t seed;
+    bool home_on;
+    int phase;
+};
+
 struct __align__(16) PassSmem {
-    uint32_t out_old[kOutCap];   // staged appends: survivors
-    uint32_t out_new[kOutCap];   // staged appends: agents infected today
-    uint2 hitq[kHitCap];         // .x = infectee, .y = slot<<23 | age_c<<16 | ord   (age 127 = look it up)
-    uint32_t conq[kConCap];      // slot<<23 | payload (native: k; replay: age<<8 | j)
-    uint32_t slot_agent[kThreads];
-    uint32_t slot_info[kThreads];  // age | E<<7
-    uint32_t hit_n[kThreads];      // hits of the slot's agent this round: total | outside<<16
+    RepView v;                     // the replica this CTA serves in the current pass (uniform per CTA)
+    uint32_t out_old[kOutOld];
+    uint32_t out_new[kOutNew];
+    uint32_t hit_c[kHitCap];       // infectee
+    uint32_t hit_meta[kHitCap];    // slot<<16 | ord
+    uint8_t hit_age[kHitCap];      // age of the infectee, 127 = look it up
+    uint32_t conq[kConCap];        // slot<<16 | payload (native: k; replay: age<<8 | j)
+    uint32_t slot_agent[kSlots];
+    uint32_t hit_n[kSlots];        // hits of the slot's agent this round: total | outside<<16
+    uint8_t slot_info[kSlots];     // age | E<<7
     uint32_t tally[TAL_ROWS * kAges];
     // small per-age tables staged once per kernel (the grid barrier's acquire loads keep flushing L1)
     double iso_asym[kAges], iso_mean[kAges];
@@ -205,38 +293,27 @@ __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
     __syncthreads();
 }
 
-struct RepView {
-    uint32_t *inbox;
-    unsigned long long *winner;
-    AgentRec *rec;
-    const uint32_t *home;
-    uint32_t *next_old, *next_new;          // tomorrow's lists
-    uint32_t *next_old_cnt, *next_new_cnt;
-    uint64_t seed;
-    bool home_on;
-    int phase;
-};
-
 __device__ __forceinline__ bool at_home(const RepView &v, int64_t c)
 {
     return v.home_on && ((__ldg(v.home + (c >> 5)) >> (c & 31)) & 1u);
 }
 
 // ---- stage H: one successful transmission slot's agent -> c on day t (:347-359 / :376-390) ----------
-__device__ __forceinline__ void process_hit(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t c, uint32_t meta, int t)
+__device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
+                                            int age_c, int t)
 {
-    const uint32_t slot = meta >> 23, ord = meta & 0xFFFFu;
-    int age_c = (meta >> 16) & 127;
+    const RepView &v = sm.v;
+    const uint32_t slot = meta >> 16, ord = meta & 0xFFFFu;
     const uint32_t i = sm.slot_agent[slot];
     const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
     if (age_c == 127) age_c = __ldg(cx.stat + c) & 127;  // (independent of the atomic below: one round trip)
     const unsigned long long old = atomicMax(v.winner + c, key);
-    const double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
+    const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
     uint32_t bits = 0;
     if ((int)(old >> 48) != t) {  // first hit of c today: announce it, queue it for tomorrow
         bits = inbox_infected_bit((int)(c & 15));
         const uint32_t pos = atomicAdd(&sm.n_new, 1u);
-        if (pos < (uint32_t)kOutCap) sm.out_new[pos] = c;
+        if (pos < (uint32_t)kOutNew) sm.out_new[pos] = c;
         else v.next_new[atomicAdd(v.next_new_cnt, 1u)] = c;
     }
     if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
@@ -244,24 +321,32 @@ __device__ __forceinline__ void process_hit(const DevCtx &cx, const RepView &v, 
     atomicAdd(&sm.hit_n[slot], ord >= 16u ? 0x10001u : 1u);  // ord >= 16: community (:386-388)
 }
 
-__device__ __forceinline__ void push_hit(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t c, uint32_t meta, int t)
+__device__ __forceinline__ void push_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
+                                         int age_c, int t)
 {
+    const RepView &v = sm.v;
     const uint32_t pos = atomicAdd(&sm.n_hit, 1u);
-    if (pos < (uint32_t)kHitCap) sm.hitq[pos] = make_uint2(c, meta);
-    else process_hit(cx, v, sm, c, meta, t);  // queue full: handle in place
+    if (pos < (uint32_t)kHitCap) {
+        sm.hit_c[pos] = c;
+        sm.hit_meta[pos] = meta;
+        sm.hit_age[pos] = (uint8_t)age_c;
+    } else {
+        process_hit(cx, sm, c, meta, age_c, t);  // queue full: handle in place
+    }
 }
 
 // ---- stage C: one candidate contact of slot's agent (:373-375) ---------------------------------------
-__device__ __forceinline__ void process_contact(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t item, int t)
+__device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
-    const uint32_t slot = item >> 23, payload = item & 0x7FFFFFu;
+    const RepView &v = sm.v;
+    const uint32_t slot = item >> 16, payload = item & 0xFFFFu;
     const uint32_t i = sm.slot_agent[slot];
     const uint32_t info = sm.slot_info[slot];
     int a;
     uint32_t ord;
     sd_block b;
     if (cx.mode == SEIR_MODE_NATIVE) {
-        b = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_NPICK, payload);
+        b = draw_block(v.seed, i, (uint32_t)t, SD_SITE_NPICK, payload);
         // contact age: one alias-table look-up in the sender's row (same arithmetic as sd_alias_pick)
         const double x = SD_MUL(sd_lane(b, 0), (double)kAges);
         int col = (int)x;
@@ -274,7 +359,7 @@ __device__ __forceinline__ void process_contact(const DevCtx &cx, const RepView 
     } else {
         a = (int)(payload >> 8);
         const uint32_t j = payload & 255u;
-        b = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_KEEP, payload);
+        b = draw_block(v.seed, i, (uint32_t)t, SD_SITE_KEEP, payload);
         double p_c = cx.p_contact;
         if (info & 128u) p_c = SD_MUL(p_c, cx.asym);
         if (!(sd_lane(b, 0) < p_c)) return;  // :373
@@ -285,247 +370,297 @@ __device__ __forceinline__ void process_contact(const DevCtx &cx, const RepView 
     const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
     const unsigned long long w = __ldcg(v.winner + c);
     if ((w == 0ull || (int)(w >> 48) == t) && !at_home(v, c))  // :375
-        push_hit(cx, v, sm, c, (slot << 23) | ((uint32_t)a << 16) | ord, t);
+        push_hit(cx, sm, c, (slot << 16) | ord, a, t);
 }
 
-__device__ __forceinline__ void push_contact(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t item, int t)
+__device__ __forceinline__ void push_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
+    const RepView &v = sm.v;
     const uint32_t pos = atomicAdd(&sm.n_con, 1u);
     if (pos < (uint32_t)kConCap) sm.conq[pos] = item;
-    else process_contact(cx, v, sm, item, t);
+    else process_contact(cx, sm, item, t);
 }
 
-// ---- stage A: the agent's own day (:256-337) and the draws that decide whom it may infect -------------
-// Returns the record (possibly modified; `dirty`), and whether the agent transmits today.
-struct AgentOut { bool dirty; int ncomp; };
-
-__device__ __forceinline__ void build_new_record(const DevCtx &cx, const RepView &v, PassSmem &sm, uint32_t i, int t, AgentRec &r)
+__device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm, uint32_t i, int t, AgentRec &r)
 {
+    const RepView &v = sm.v;
     // infected on day t-1 by the winner of that day's hits (:347-356)
     const unsigned long long w = __ldcg(v.winner + i);
     const uint32_t ib = __ldcg(v.inbox + (i >> 4));
     const uint16_t stt = __ldg(cx.stat + i);
     const uint32_t inf = (uint32_t)(w >> 16), ord = (uint32_t)(w & 0xFFFFu);
     const int tx = t - 1;
-    const double tiso = sd_exp_days(sd_lane(sd_draw(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8), 0),
+    const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8), 0),
                                     sm.iso_asym[stt & 127]);
-    const double tact = sd_lognormal_days(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
-    r = AgentRec{};
-    r.t_exposed = (uint16_t)tx;
-    r.tt_isolate = sd_enc16(tiso);
-    r.tt_activation = sd_enc16(tact);
-    r.t_end = NEVER;
-    r.t_q_on = NEVER;
-    r.stat = stt;
-    r.state = C_E;
-    if (ib & inbox_q_bit((int)(i & 15))) { r.state |= ST_Q; r.t_q_on = (uint16_t)tx; }
+    const double tact = lognormal_days_ni(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+    r.clear();
+    r.set_t_exposed((uint16_t)tx);
+    r.set_tt_isolate(sd_enc16(tiso));
+    r.set_tt_activation(sd_enc16(tact));
+    r.set_t_end(NEVER);
+    r.set_t_q_on(NEVER);
+    r.set_stat(stt);
+    r.set_state(C_E);
+    if (ib & inbox_q_bit((int)(i & 15))) { r.set_state(r.state() | ST_Q); r.set_t_q_on((uint16_t)tx); }
     atomicAdd(&sm.tally[TAL_NEW_E * kAges + (stt & 127)], 1u);
 }
 
-// rare events of the agent's own progression; kept out of line so the common path stays short
-__device__ __noinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
+// rare events of the agent's own progression
+__device__ __forceinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
                                                 AgentRec &r, int comp, int &ncomp, bool &nq, bool &ndoc)
 {
-    const uint16_t stt = r.stat;
+    const uint16_t stt = r.stat();
     const int age = stt & 127;
     const int k3 = age * 4 + ((stt >> 7) & 1) * 2 + ((stt >> 8) & 1);
     if (comp == C_E) {  // :256-272 activation
         ncomp = C_MILD;
-        r.flags |= F_MILD;
-        sd_block b = sd_draw(seed, i, (uint32_t)t, SD_SITE_ACT, 0);
+        r.set_flags(r.flags() | F_MILD);
+        sd_block b = draw_block(seed, i, (uint32_t)t, SD_SITE_ACT, 0);
         if (sd_lane(b, 0) < __ldg(cx.p_ms + k3)) {
-            r.tt_severe = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_sev));
-            r.tt_recovery = NEVER;
+            r.set_tt_severe(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_sev)));
+            r.set_tt_recovery(NEVER);
         } else {
-            r.tt_recovery = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_mild_rec));
-            r.tt_severe = NEVER;
+            r.set_tt_recovery(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_mild_rec)));
+            r.set_tt_severe(NEVER);
         }
-        const double tiso = sd_exp_days(sd_lane(sd_draw(seed, i, (uint32_t)t, SD_SITE_ACT, 1), 0), sm.iso_mean[age]);
-        r.tt_isolate = sd_enc16(tiso);
+        const double tiso = exp_days_ni(sd_lane(draw_block(seed, i, (uint32_t)t, SD_SITE_ACT, 1), 0), sm.iso_mean[age]);
+        r.set_tt_isolate(sd_enc16(tiso));
         if (tiso == 0.0) nq = true;
     } else if (comp == C_MILD) {  // :291-311 Mild -> Severe
         ncomp = C_SEV;
-        r.flags |= F_SEV;
+        r.set_flags(r.flags() | F_SEV);
         if (!ndoc) {
             ndoc = true;
-            r.t_documented = (uint16_t)t;
+            r.set_t_documented((uint16_t)t);
         }
         nq = true;
-        sd_block b = sd_draw(seed, i, (uint32_t)t, SD_SITE_SEV, 0);
+        sd_block b = draw_block(seed, i, (uint32_t)t, SD_SITE_SEV, 0);
         if (sd_lane(b, 0) < __ldg(cx.p_sc + k3)) {
-            r.tt_critical = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_crit));
-            r.tt_recovery = NEVER;
+            r.set_tt_critical(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_crit)));
+            r.set_tt_recovery(NEVER);
         } else {
-            r.tt_recovery = add_sat16(sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_sev_rec)), r.tt_severe);
-            r.tt_critical = NEVER;
+            r.set_tt_recovery(add_sat16(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_sev_rec)), r.tt_severe()));
+            r.set_tt_critical(NEVER);
         }
     } else {  // :312-321 Severe -> Critical
         ncomp = C_CRIT;
-        r.flags |= F_CRIT;
-        sd_block b = sd_draw(seed, i, (uint32_t)t, SD_SITE_CRIT, 0);
+        r.set_flags(r.flags() | F_CRIT);
+        sd_block b = draw_block(seed, i, (uint32_t)t, SD_SITE_CRIT, 0);
         if (sd_lane(b, 0) < __ldg(cx.p_cd + k3)) {
-            r.tt_death = sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_death));
-            r.tt_recovery = NEVER;
+            r.set_tt_death(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_death)));
+            r.set_tt_recovery(NEVER);
         } else {
-            r.tt_recovery = add_sat16(add_sat16(sd_enc16(sd_exp_days(sd_lane(b, 1), cx.m_crit_rec)), r.tt_severe), r.tt_critical);
-            r.tt_death = NEVER;
+            r.set_tt_recovery(add_sat16(add_sat16(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_crit_rec)), r.tt_severe()), r.tt_critical()));
+            r.set_tt_death(NEVER);
         }
     }
 }
 
+// ---- stage A: one list entry.  The agent's own day (:256-337), then WHICH household members and HOW MANY
+// community contacts it may infect today (queued for stages C / H).  Returns true if it stays on the list.
+__device__ __forceinline__ bool stage_a_entry(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i,
+                                              bool is_new, int t, bool finalize)
+{
+    const RepView &v = sm.v;
+    AgentRec r;
+    bool dirty = false;
+    SEIR_FINE(0);
+    if (is_new) {
+        build_new_record(cx, sm, i, t, r);
+        dirty = true;
+    } else {
+        r = load_rec(v.rec + i);
+    }
+    const uint16_t stt = r.stat();
+    if (stt == 0xFFFF) return false;  // (never; keeps the load above the stamp)
+    SEIR_FINE(1);
+    const int age = stt & 127;
+    const uint8_t st = r.state();
+    const int comp = st & 7;
+    const bool Ep = comp == C_E, Mp = comp == C_MILD, Sevp = comp == C_SEV, Cp = comp == C_CRIT;
+    const bool Qp = (st & ST_Q) != 0, Dp = (st & ST_DOC) != 0;
+    sm.slot_agent[slot] = i;
+    sm.slot_info[slot] = (uint8_t)(age | (Ep ? 128 : 0));
+    sm.hit_n[slot] = 0;
+    // state tallies of day t-1
+    atomicAdd(&sm.tally[(comp - C_E) * kAges + age], 1u);
+    if (Qp) atomicAdd(&sm.tally[TAL_QACT * kAges + age], 1u);
+    if (finalize) {  // pass T: nothing moves
+        if (dirty) store_rec(v.rec + i, r);
+        return false;
+    }
+    int ncomp = comp;
+    bool nq = Qp, ndoc = Dp;
+    // the agent's day block: documentation draw + first uniform of the contact count
+    SEIR_FINE(2);
+    const sd_block db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
+    if (db.w[0] == 0x12345678u && db.w[1] == 0x9abcdef0u) return false;  // (never)
+    SEIR_FINE(3);
+    bool transmit = !Qp;
+    const int t_inf = t_infected_of(r);
+    if (!Ep && due(t, t_inf, r.tt_recovery())) {  // :276-279
+        ncomp = C_R;
+        nq = false;
+        transmit = false;
+        atomicAdd(&sm.tally[TAL_NEW_R * kAges + age], 1u);
+    } else {
+        if (Mp && !Dp && sd_lane(db, 0) < cx.p_doc) {  // :280-289
+            ndoc = true;
+            r.set_t_documented((uint16_t)t);
+        }
+        const bool ev = (Ep && due(t, r.t_exposed(), r.tt_activation())) || (Mp && due(t, t_inf, r.tt_severe())) ||
+                        (Sevp && due(t, t_severe_of(r), r.tt_critical()));
+        if (ev) {
+            progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc);
+            dirty = true;
+        } else if (Cp && due(t, t_critical_of(r), r.tt_death())) {  // :323-327
+            ncomp = C_D;
+            nq = false;
+            atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], 1u);
+        }
+        if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], 1u);
+    }
+    // :328-337 isolation entry (time_to_isolate may just have been redrawn at :270)
+    if (transmit) {
+        if (!Ep && due(t, t_infected_of(r), r.tt_isolate())) { nq = true; transmit = false; }
+        else if (Ep && due(t, r.t_exposed(), r.tt_isolate())) { nq = true; transmit = false; }
+    }
+    // the agent's own record is final for today except for the infector counters (stage W)
+    const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
+    if (nst != st) {
+        r.set_state(nst);
+        if (nq && !Qp && r.t_q_on() == NEVER) r.set_t_q_on((uint16_t)t);
+        if (ncomp == C_R || ncomp == C_D) r.set_t_end((uint16_t)t);
+        dirty = true;
+    }
+    SEIR_FINE(4);
+    if (dirty) store_rec(v.rec + i, r);
+    SEIR_FINE(5);
+
+    if (transmit) {
+        // ---- household push :339-359; households are contiguous ranges [i-pos, i-pos+size)
+        const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
+        const uint32_t base = i - (uint32_t)pos;
+        uint32_t smask = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {  // independent loads: one round trip for the household
+            if (j < size - 1) {
+                const unsigned long long w = __ldcg(v.winner + base + j + (j >= pos ? 1 : 0));
+                if (w == 0ull || (int)(w >> 48) == t) smask |= 1u << j;  // S[t-1,c] (:346)
+            }
+        }
+        SEIR_FINE(6);
+        if (smask) {
+            double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
+            if (Ep) p_h = SD_MUL(p_h, cx.asym);
+#pragma unroll 1
+            for (int jb = 0; jb < 4; ++jb) {
+                if (!((smask >> (2 * jb)) & 3u)) continue;
+                const sd_block hb = draw_block(v.seed, i, (uint32_t)t, SD_SITE_HH, (uint32_t)jb);
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    const int j = 2 * jb + l;
+                    if (((smask >> j) & 1u) && sd_lane(hb, l) < p_h)
+                        push_hit(cx, sm, base + j + (j >= pos ? 1 : 0), (slot << 16) | SD_ORD_HH(j), 127, t);
+                }
+            }
+        }
+        SEIR_FINE(7);
+        // ---- community push :361-390: decide HOW MANY candidate contacts, queue them
+        if (!at_home(v, i)) {
+            if (cx.mode == SEIR_MODE_NATIVE) {
+                const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
+                const double u1 = sd_lane(db, 1);  // sd_poisson_day: the first Knuth uniform is lane 1 of the day block
+                const uint32_t kept = (u1 <= en) ? 0u : poisson_day_more(v.seed, i, (uint32_t)t, u1, en, SD_MAX_CONTACTS_NATIVE);
+                for (uint32_t k = 0; k < kept; ++k) push_contact(cx, sm, (slot << 16) | k, t);
+            } else {
+                const double *en = cx.enlam + ((size_t)v.phase * kAges + age) * kAges;
+#pragma unroll 1
+                for (int a = 0; a < kAges; ++a) {
+                    if (sm.grp_off[a + 1] == sm.grp_off[a]) continue;  // :368-369
+                    const uint32_t nc = poisson_ni(v.seed, i, (uint32_t)t, SD_SITE_POIS, (uint32_t)a << 8, __ldg(en + a),
+                                                   SD_MAX_CONTACTS_PER_AGE);
+                    for (uint32_t j = 0; j < nc; ++j) push_contact(cx, sm, (slot << 16) | ((uint32_t)a << 8) | j, t);
+                }
+            }
+        }
+    }
+    SEIR_FINE(8);
+    return ncomp >= C_E && ncomp <= C_CRIT;
+}
+
 // ---------------------------------------------------------------------------------------
-// Pass t over all replicas.  CTA b serves replica (b / blocks_per_rep) [+ k * reps_per_sweep].
+// Pass t over all replicas.  CTA b serves replica (b / blocks_per_rep) [+ k * reps_per_sweep]; the CTAs of a
+// replica split its list into equal contiguous chunks, kPerThread entries per thread and round.
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
 __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
 {
     const int tid = threadIdx.x;
-    bool stamped = false;
     const int lane = tid & 31;
+    bool stamped = false;
     const bool finalize = t >= cx.T;
     const int bpr = cx.blocks_per_rep;
     const int reps_per_sweep = gridDim.x / bpr;  // >= 1
     const int my_slot = blockIdx.x / bpr, my_part = blockIdx.x % bpr;
     // (CTAs beyond the last full group idle through the pass; they must still reach the grid barrier)
     for (int rep = my_slot; rep < cx.n_rep && my_slot < reps_per_sweep; rep += reps_per_sweep) {
-        RepView v;
-        v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
-        v.winner = cx.winner + (size_t)rep * cx.n_pad;
-        v.rec = cx.rec + (size_t)rep * cx.n_pad;
-        v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
         const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
         uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 2 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2);
-        v.next_old = cx.list_old + lrow;
-        v.next_new = cx.list_new + lrow;
-        v.next_old_cnt = cnt_old + (t + 1);
-        v.next_new_cnt = cnt_new + (t + 1);
-        v.seed = cx.seeds[rep];
-        v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;          // :243-244
-        v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
+        const RepView &v = sm.v;
+        if (tid == 0) {
+            sm.v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+            sm.v.winner = cx.winner + (size_t)rep * cx.n_pad;
+            sm.v.rec = cx.rec + (size_t)rep * cx.n_pad;
+            sm.v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
+            sm.v.next_old = cx.list_old + lrow;
+            sm.v.next_new = cx.list_new + lrow;
+            sm.v.next_old_cnt = cnt_old + (t + 1);
+            sm.v.next_new_cnt = cnt_new + (t + 1);
+            sm.v.seed = cx.seeds[rep];
+            sm.v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;          // :243-244
+            sm.v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
+        }
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
         const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t);
         const uint32_t count = n_new + n_old;  // new infectees first: their record build stays convergent
+        // this CTA's contiguous chunk, a multiple of 32 entries
+        const uint32_t chunk = ((count + (uint32_t)bpr - 1) / (uint32_t)bpr + 31u) & ~31u;
+        const uint32_t lo = (uint32_t)my_part * chunk;
+        const uint32_t hi = lo + chunk < count ? lo + chunk : count;
 
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
         if (tid < 4) sm.cnt[tid] = 0;
         if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; }
         __syncthreads();
-
         SEIR_STAMP(0);
-        uint32_t c_active = 0, c_inf = 0, c_hits = 0;
-        const uint32_t stride = (uint32_t)bpr * kThreads;
-        for (uint32_t e0 = (uint32_t)my_part * kThreads; e0 < count; e0 += stride) {
-            // ================= stage A: one list entry per thread =================
-            const uint32_t e = e0 + tid;
-            const bool valid = e < count;
-            uint32_t i = 0;
-            AgentRec r;
-            bool dirty = false, keep = false;
-            uint8_t st = 0;
-            int ncomp = 0;
-            bool nq = false, ndoc = false;
-            sm.hit_n[tid] = 0;
-            if (valid) {
-                if (e < n_new) {
-                    i = __ldcg(cur_new + e);
-                    build_new_record(cx, v, sm, i, t, r);
-                    ++c_inf;
-                    dirty = true;
-                } else {
-                    i = __ldcg(cur_old + (e - n_new));
-                    r = load_rec(v.rec + i);
+
+        for (uint32_t e0 = lo; e0 < hi; e0 += (uint32_t)kSlots) {
+            // ================= stage A: up to kPerThread list entries per thread =================
+#pragma unroll 1
+            for (int sub = 0; sub < kPerThread; ++sub) {
+                const uint32_t eb = e0 + (uint32_t)sub * kThreads;
+                if (eb >= hi) break;
+                const uint32_t e = eb + tid;
+                bool keep = false;
+                uint32_t i = 0;
+                if (e < hi) {
+                    const bool is_new = e < n_new;
+                    i = is_new ? __ldcg(cur_new + e) : __ldcg(cur_old + (e - n_new));
+                    keep = stage_a_entry(cx, sm, (uint32_t)sub * kThreads + tid, i, is_new, t, finalize);
+#ifdef SEIR_FINE_STAMPS
+                    if (blockIdx.x == 0 && tid == 0 && sub == 0) cx.fine_ns[(size_t)t * 16 + 9] = global_timer_ns();
+#endif
                 }
-                const uint16_t stt = r.stat;
-                const int age = stt & 127;
-                st = r.state;
-                const int comp = st & 7;
-                const bool Ep = comp == C_E, Mp = comp == C_MILD, Sevp = comp == C_SEV, Cp = comp == C_CRIT;
-                const bool Qp = (st & ST_Q) != 0, Dp = (st & ST_DOC) != 0;
-                sm.slot_agent[tid] = i;
-                sm.slot_info[tid] = (uint32_t)age | (Ep ? 128u : 0u);
-                // state tallies of day t-1
-                atomicAdd(&sm.tally[(comp - C_E) * kAges + age], 1u);
-                if (Qp) atomicAdd(&sm.tally[TAL_QACT * kAges + age], 1u);
-                ++c_active;
-                ncomp = comp;
-                nq = Qp;
-                ndoc = Dp;
-                if (!finalize) {
-                    // the agent's day block: documentation draw + first uniform of the contact count
-                    const sd_block db = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
-                    bool transmit = !Qp;
-                    const int t_inf = t_infected_of(r);
-                    if (!Ep && due(t, t_inf, r.tt_recovery)) {  // :276-279
-                        ncomp = C_R;
-                        nq = false;
-                        transmit = false;
-                        atomicAdd(&sm.tally[TAL_NEW_R * kAges + age], 1u);
-                    } else {
-                        if (Mp && !Dp && sd_lane(db, 0) < cx.p_doc) {  // :280-289
-                            ndoc = true;
-                            r.t_documented = (uint16_t)t;
-                        }
-                        const bool ev = (Ep && due(t, r.t_exposed, r.tt_activation)) || (Mp && due(t, t_inf, r.tt_severe)) ||
-                                        (Sevp && due(t, t_severe_of(r), r.tt_critical));
-                        if (ev) {
-                            progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc);
-                            dirty = true;
-                        } else if (Cp && due(t, t_critical_of(r), r.tt_death)) {  // :323-327
-                            ncomp = C_D;
-                            nq = false;
-                            atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], 1u);
-                        }
-                        if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], 1u);
-                    }
-                    // :328-337 isolation entry (time_to_isolate may just have been redrawn at :270)
-                    if (transmit) {
-                        if (!Ep && due(t, t_infected_of(r), r.tt_isolate)) { nq = true; transmit = false; }
-                        else if (Ep && due(t, r.t_exposed, r.tt_isolate)) { nq = true; transmit = false; }
-                    }
-                    if (transmit) {
-                        // ---- household push :339-359; households are contiguous ranges [i-pos, i-pos+size)
-                        const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
-                        const uint32_t base = i - (uint32_t)pos;
-                        uint32_t smask = 0;
-#pragma unroll
-                        for (int j = 0; j < 7; ++j) {  // independent loads: one round trip for the household
-                            if (j < size - 1) {
-                                const unsigned long long w = __ldcg(v.winner + base + j + (j >= pos ? 1 : 0));
-                                if (w == 0ull || (int)(w >> 48) == t) smask |= 1u << j;  // S[t-1,c] (:346)
-                            }
-                        }
-                        if (smask) {
-                            double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
-                            if (Ep) p_h = SD_MUL(p_h, cx.asym);
-#pragma unroll 1
-                            for (int jb = 0; jb < 4; ++jb) {
-                                if (!((smask >> (2 * jb)) & 3u)) continue;
-                                const sd_block hb = sd_draw(v.seed, i, (uint32_t)t, SD_SITE_HH, (uint32_t)jb);
-#pragma unroll
-                                for (int l = 0; l < 2; ++l) {
-                                    const int j = 2 * jb + l;
-                                    if (((smask >> j) & 1u) && sd_lane(hb, l) < p_h)
-                                        push_hit(cx, v, sm, base + j + (j >= pos ? 1 : 0), ((uint32_t)tid << 23) | (127u << 16) | SD_ORD_HH(j), t);
-                                }
-                            }
-                        }
-                        // ---- community push :361-390: decide HOW MANY candidate contacts, queue them
-                        if (!at_home(v, i)) {
-                            if (cx.mode == SEIR_MODE_NATIVE) {
-                                const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
-                                const uint32_t kept = sd_poisson_day(v.seed, i, (uint32_t)t, db, en, SD_MAX_CONTACTS_NATIVE);
-                                for (uint32_t k = 0; k < kept; ++k) push_contact(cx, v, sm, ((uint32_t)tid << 23) | k, t);
-                            } else {
-                                const double *en = cx.enlam + ((size_t)v.phase * kAges + age) * kAges;
-#pragma unroll 1
-                                for (int a = 0; a < kAges; ++a) {
-                                    if (sm.grp_off[a + 1] == sm.grp_off[a]) continue;  // :368-369
-                                    const uint32_t nc = sd_poisson(v.seed, i, (uint32_t)t, SD_SITE_POIS, (uint32_t)a << 8,
-                                                                   __ldg(en + a), SD_MAX_CONTACTS_PER_AGE);
-                                    for (uint32_t j = 0; j < nc; ++j)
-                                        push_contact(cx, v, sm, ((uint32_t)tid << 23) | ((uint32_t)a << 8) | j, t);
-                                }
-                            }
-                        }
+                // survivors re-append themselves: one shared-memory atomic per warp
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                if (m) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&sm.n_old, (uint32_t)__popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (keep) {
+                        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < (uint32_t)kOutOld) sm.out_old[pos] = i;
+                        else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
                     }
                 }
             }
@@ -534,61 +669,48 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             // ================= stage C: candidate contacts, one per thread =================
             {
                 const uint32_t nc = sm.n_con < (uint32_t)kConCap ? sm.n_con : (uint32_t)kConCap;
-                for (uint32_t q = tid; q < nc; q += kThreads) process_contact(cx, v, sm, sm.conq[q], t);
+                for (uint32_t q = tid; q < nc; q += kThreads) process_contact(cx, sm, sm.conq[q], t);
             }
             __syncthreads();
             SEIR_STAMP(2);
             // ================= stage H: hits, one per thread =================
             {
                 const uint32_t nh = sm.n_hit < (uint32_t)kHitCap ? sm.n_hit : (uint32_t)kHitCap;
-                for (uint32_t q = tid; q < nh; q += kThreads) {
-                    const uint2 h = sm.hitq[q];
-                    process_hit(cx, v, sm, h.x, h.y, t);
-                }
+                for (uint32_t q = tid; q < nh; q += kThreads) process_hit(cx, sm, sm.hit_c[q], sm.hit_meta[q], sm.hit_age[q], t);
             }
             __syncthreads();
             SEIR_STAMP(3);
-            // ================= stage W: write back, re-append survivors =================
-            if (valid && !finalize) {
-                const uint32_t hn = sm.hit_n[tid];
-                if (hn) {
-                    const uint32_t hits = hn & 0xFFFFu, hits_out = hn >> 16;
-                    r.n_inf_by = inc_sat16(r.n_inf_by, hits);                             // :357,:386
-                    if ((st & 7) == C_E) r.n_inf_asympt = inc_sat16(r.n_inf_asympt, hits);  // :358-359,:389-390
-                    r.n_inf_outside = inc_sat16(r.n_inf_outside, hits_out);               // :388
-                    c_hits += hits;
-                    dirty = true;
-                }
-                const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
-                if (nst != st) {
-                    r.state = nst;
-                    if (nq && !(st & ST_Q) && r.t_q_on == NEVER) r.t_q_on = (uint16_t)t;
-                    if (ncomp == C_R || ncomp == C_D) r.t_end = (uint16_t)t;
-                    dirty = true;
-                }
-                keep = ncomp >= C_E && ncomp <= C_CRIT;
-            }
-            if (valid && dirty) store_rec(v.rec + i, r);
-            {   // survivors re-append themselves: one shared-memory atomic per warp
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-                if (m) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.n_old, (uint32_t)__popc(m));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (keep) {
-                        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                        if (pos < (uint32_t)kOutCap) sm.out_old[pos] = i;
-                        else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
+            // ================= stage W: infector counters (:357-359, :386-390) =================
+            {
+                const uint32_t ns = hi - e0 < (uint32_t)kSlots ? hi - e0 : (uint32_t)kSlots;
+                for (uint32_t sl = tid; sl < ns; sl += kThreads) {
+                    const uint32_t hn = sm.hit_n[sl];
+                    if (hn) {
+                        const uint32_t hits = hn & 0xFFFFu, hits_out = hn >> 16;
+                        // second half of the record: n_inf_by | n_inf_asympt<<16, n_inf_outside | t_end<<16, ...
+                        uint2 *q = reinterpret_cast<uint2 *>(v.rec + sm.slot_agent[sl]) + 2;
+                        uint2 u = __ldcg(q);
+                        uint32_t by = inc_sat16((uint16_t)(u.x & 0xFFFFu), hits), as = u.x >> 16;
+                        if (sm.slot_info[sl] & 128u) as = inc_sat16((uint16_t)as, hits);
+                        u.x = by | (as << 16);
+                        u.y = (u.y & 0xFFFF0000u) | inc_sat16((uint16_t)(u.y & 0xFFFFu), hits_out);
+                        __stcg(q, u);
+                        atomicAdd(&sm.cnt[2], hits);
                     }
+                }
+                if (tid == 0) {
+                    atomicAdd(&sm.cnt[0], ns);
+                    const uint32_t nn = n_new > e0 ? (n_new - e0 < ns ? n_new - e0 : ns) : 0u;  // new infectees in this round
+                    atomicAdd(&sm.cnt[1], nn);
                 }
             }
             __syncthreads();
             // flush the staging buffers when the next round could overflow them
             {
-                const uint32_t so = sm.n_old < (uint32_t)kOutCap ? sm.n_old : (uint32_t)kOutCap;
-                const uint32_t sn = sm.n_new < (uint32_t)kOutCap ? sm.n_new : (uint32_t)kOutCap;
-                const bool fo = so > (uint32_t)(kOutCap - kThreads), fn = sn > (uint32_t)(kOutCap - 2 * kThreads);
-                if (fo || fn) {
+                const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
+                const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
+                const bool fo = so > (uint32_t)(kOutOld - kSlots), fn = sn > (uint32_t)(kOutNew - kHitCap);
+                if ((fo || fn) && e0 + (uint32_t)kSlots < hi) {
                     if (tid == 0) {
                         if (fo) sm.base_old = atomicAdd(v.next_old_cnt, so);
                         if (fn) sm.base_new = atomicAdd(v.next_new_cnt, sn);
@@ -609,25 +731,9 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             stamped = true;
         }
         stamped = false;
-        SEIR_STAMP(5);
-        {   // per-thread counters -> one shared atomic per warp
-            uint32_t a = c_active, b = c_inf, c = c_hits;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-                b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
-                c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-            }
-            if (lane == 0) {
-                if (a) atomicAdd(&sm.cnt[0], a);
-                if (b) atomicAdd(&sm.cnt[1], b);
-                if (c) atomicAdd(&sm.cnt[2], c);
-            }
-        }
-        __syncthreads();
         {
-            const uint32_t so = sm.n_old < (uint32_t)kOutCap ? sm.n_old : (uint32_t)kOutCap;
-            const uint32_t sn = sm.n_new < (uint32_t)kOutCap ? sm.n_new : (uint32_t)kOutCap;
+            const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
+            const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
             if (so | sn) {
                 if (tid == 0) {
                     if (so) sm.base_old = atomicAdd(v.next_old_cnt, so);
@@ -638,6 +744,7 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
             }
         }
+        SEIR_STAMP(5);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
@@ -648,7 +755,11 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 if (day < cx.T) atomicAdd(&tal[(size_t)day * TAL_ROWS * kAges + k], val);
             }
         }
-        if (tid < 3 && sm.cnt[tid]) atomicAdd(&cx.counters[rep * 4 + 1 + tid], (unsigned long long)sm.cnt[tid]);
+        if (tid == 0) {
+            if (sm.cnt[0]) atomicAdd(&cx.counters[rep * 4 + 1], (unsigned long long)sm.cnt[0]);
+            if (sm.cnt[1]) atomicAdd(&cx.counters[rep * 4 + 2], (unsigned long long)sm.cnt[1]);
+            if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
+        }
         __syncthreads();
         SEIR_STAMP(6);
     }
@@ -674,17 +785,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 // packed state byte of an ever-infected agent on day t, from its record
 __device__ __forceinline__ uint8_t state_on_day(const AgentRec &r, int t)
 {
-    if (t < (int)r.t_exposed) return C_S;
-    const bool ended = r.t_end != NEVER && t >= (int)r.t_end;
+    if (t < (int)r.t_exposed()) return C_S;
+    const bool ended = r.t_end() != NEVER && t >= (int)r.t_end();
     int comp;
-    if (ended) comp = r.state & 7;
-    else if ((r.flags & F_CRIT) && t >= t_critical_of(r)) comp = C_CRIT;
-    else if ((r.flags & F_SEV) && t >= t_severe_of(r)) comp = C_SEV;
-    else if ((r.flags & F_MILD) && t >= t_infected_of(r)) comp = C_MILD;
+    if (ended) comp = r.state() & 7;
+    else if ((r.flags() & F_CRIT) && t >= t_critical_of(r)) comp = C_CRIT;
+    else if ((r.flags() & F_SEV) && t >= t_severe_of(r)) comp = C_SEV;
+    else if ((r.flags() & F_MILD) && t >= t_infected_of(r)) comp = C_MILD;
     else comp = C_E;
     uint8_t s = (uint8_t)comp;
-    if (r.t_q_on != NEVER && t >= (int)r.t_q_on && !ended) s |= ST_Q;
-    if (r.t_documented != 0 && t >= (int)r.t_documented) s |= ST_DOC;
+    if (r.t_q_on() != NEVER && t >= (int)r.t_q_on() && !ended) s |= ST_Q;
+    if (r.t_documented() != 0 && t >= (int)r.t_documented()) s |= ST_DOC;
     return s;
 }
 

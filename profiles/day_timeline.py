@@ -27,3 +27,15 @@ st = eng.stage_times_us()
 for t in range(1, len(us) + 1):
     print("pass %2d  %7.2f us   active(t-1)=%-7d stages(setup,A,C,H,W,lists,tallies): %s"
           % (t, us[t - 1], act[t - 1] if t - 1 < len(act) else -1, " ".join("%6.2f" % x for x in st[t, :7])))
+if os.environ.get("FINE"):
+    import ctypes as C
+    out = np.zeros((eng.T + 2) * 16, dtype=np.int64)
+    eng.lib.seir_get_fine_times.argtypes = [C.c_void_p, C.c_void_p]
+    eng.lib.seir_get_fine_times(eng._h, out.ctypes.data)
+    f = out.reshape(-1, 16).astype(float)
+    day = np.zeros(eng.T + 2, dtype=np.int64)
+    eng.lib.seir_get_day_times(eng._h, day.ctypes.data)
+    names = "entry rec/build tallies dayblk progr store hhloads hhdraws comm-end ret".split()
+    for t in range(1, eng.T):
+        rel = [(f[t, k] - day[t]) / 1e3 if f[t, k] > 0 else float("nan") for k in range(10)]
+        print("pass %2d fine: " % t + " ".join("%s=%.2f" % (n, x) for n, x in zip(names, rel)))
