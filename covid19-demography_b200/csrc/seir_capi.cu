@@ -76,30 +76,119 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
 }
 
 // The reference's nine bool[T,n] outputs (:165-173, one row per day) as ONE packed byte per agent-day,
-// written once from the per-agent records: a streaming T*n byte write.  A thread owns 16 agents.
-__global__ void __launch_bounds__(256) seir_materialize_kernel(DevCtx cx)
+// written once from the per-agent records: a streaming T*n byte write.
+// A WARP owns 512 consecutive agents (lane = one 16 B vector per row).  Its ever-infected agents are listed
+// in shared memory and dealt round-robin to the lanes, so the per-row work is balanced whatever the
+// clustering of infections; each agent's timeline is seven day thresholds held in registers, a row byte
+// is a handful of branch-free compares dropped into a 512 B shared tile, and every row leaves the warp as
+// full 16 B vector stores.
+constexpr int kMatWarps = 8, kMatThreads = kMatWarps * 32, kMatPerLane = 4;
+struct MatAgent { uint32_t a, b, c, d; };  // t_exp|t_inf<<16, t_sev|t_crit<<16, t_end|t_q_on<<16, t_doc|final<<16|local<<20
+
+__device__ __forceinline__ MatAgent mat_pack(const AgentRec &r, int local)
 {
-    const int64_t nvec = cx.n_pad / kVec;
-    const int64_t total = nvec * cx.n_rep;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int rep = (int)(g / nvec);
-        const int64_t vi = g % nvec;
+    const uint32_t fl = r.flags();
+    const uint32_t t_exp = r.t_exposed();
+    const uint32_t t_inf = (fl & F_MILD) ? (uint32_t)t_infected_of(r) : 0xFFFFu;
+    const uint32_t t_sev = (fl & F_SEV) ? (uint32_t)t_severe_of(r) : 0xFFFFu;
+    const uint32_t t_cri = (fl & F_CRIT) ? (uint32_t)t_critical_of(r) : 0xFFFFu;
+    const uint32_t t_doc = r.t_documented() ? r.t_documented() : 0xFFFFu;
+    MatAgent m;
+    m.a = t_exp | (t_inf << 16);
+    m.b = t_sev | (t_cri << 16);
+    m.c = (uint32_t)r.t_end() | ((uint32_t)r.t_q_on() << 16);
+    m.d = t_doc | ((uint32_t)(r.state() & 7) << 16) | ((uint32_t)local << 20);
+    return m;
+}
+// packed state byte on day t (same function as state_on_day, on the packed thresholds)
+__device__ __forceinline__ uint32_t mat_byte(const MatAgent &m, uint32_t t)
+{
+    const uint32_t cnt = (t >= (m.a & 0xFFFFu)) + (t >= (m.a >> 16)) + (t >= (m.b & 0xFFFFu)) + (t >= (m.b >> 16));
+    const bool ended = t >= (m.c & 0xFFFFu);
+    const uint32_t q = (t >= (m.c >> 16)) && !ended;
+    const uint32_t doc = t >= (m.d & 0xFFFFu);
+    const uint32_t comp = ended ? ((m.d >> 16) & 7u) : cnt;
+    return comp | (q << 3) | (doc << 4);
+}
+
+__global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __grid_constant__ DevCtx cx)
+{
+    __shared__ __align__(16) uint8_t s_tile[kMatWarps][512];
+    __shared__ uint16_t s_list[kMatWarps][512];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t groups_per_rep = cx.n_pad / 512;
+    const int64_t total = groups_per_rep * cx.n_rep;
+    const int64_t row_stride = cx.n_pad / kVec;
+    uint8_t *tile = s_tile[wib];
+    uint16_t *list = s_list[wib];
+    for (int64_t g = (int64_t)blockIdx.x * kMatWarps + wib; g < total; g += (int64_t)gridDim.x * kMatWarps) {
+        const int rep = (int)(g / groups_per_rep);
+        const int64_t vi = (g % groups_per_rep) * 32 + lane;  // my vector (16 agents) in the row
         uint8_t *hist = cx.hist + (size_t)rep * cx.T * cx.n_pad;
-        const uint32_t ib = __ldcs(cx.inbox + g);
+        const AgentRec *rec = cx.rec + (size_t)rep * cx.n_pad + (g % groups_per_rep) * 512;
         uint4 *row = reinterpret_cast<uint4 *>(hist) + vi;
-        const int64_t row_stride = cx.n_pad / kVec;
-#pragma unroll 4
-        for (int t = 0; t < cx.T; ++t) __stcs(row + (int64_t)t * row_stride, z);  // S everywhere
-        uint32_t m = ib & 0x0F0F0F0Fu;  // "ever infected" bits
+        uint32_t m = __ldcs(cx.inbox + (size_t)rep * row_stride + vi) & 0x0F0F0F0Fu;  // "ever infected" bits
+        // ---- warp-wide list of infected agents (local index 0..511)
+        const int mine = __popc(m);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int n_inf = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        int at = incl - mine;
         while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1;
-            const int k = (bit & 7) * 4 + (bit >> 3);  // inverse of inbox_infected_bit
-            const int64_t i = vi * kVec + k;
-            const AgentRec r = load_rec(cx.rec + (size_t)rep * cx.n_pad + i);
+            list[at++] = (uint16_t)(lane * 16 + (bit & 7) * 4 + (bit >> 3));  // inverse of inbox_infected_bit
+        }
+        __syncwarp();
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (n_inf == 0) {
+            for (int t = 0; t < cx.T; ++t) __stcs(row + (int64_t)t * row_stride, z);
+            continue;
+        }
+        // ---- my share of the agents: entries lane, lane+32, ... (at most kMatPerLane in registers)
+        MatAgent ag[kMatPerLane];
+        int t_first = cx.T;
+#pragma unroll
+        for (int k = 0; k < kMatPerLane; ++k) {
+            const int e = lane + 32 * k;
+            ag[k].a = 0xFFFFFFFFu; ag[k].b = 0xFFFFFFFFu; ag[k].c = 0xFFFFFFFFu; ag[k].d = 0xFFFFu;
+            if (e < n_inf) {
+                const int local = list[e];
+                const AgentRec r = load_rec(rec + local);
+                ag[k] = mat_pack(r, local);
+                t_first = min(t_first, (int)r.t_exposed());
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t_first = min(t_first, __shfl_xor_sync(0xFFFFFFFFu, t_first, o));
+        const int n_slots = min(kMatPerLane, (n_inf + 31) / 32);  // warp-uniform
+        for (int t = 0; t < t_first; ++t) __stcs(row + (int64_t)t * row_stride, z);  // S everywhere
+        for (int t = t_first; t < cx.T; ++t) {
+            reinterpret_cast<uint4 *>(tile)[lane] = z;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kMatPerLane; ++k) {
+                if (k < n_slots) {
+                    const uint32_t byte = mat_byte(ag[k], (uint32_t)t);
+                    if (byte) tile[ag[k].d >> 20] = (uint8_t)byte;
+                }
+            }
+            __syncwarp();
+            __stcs(row + (int64_t)t * row_stride, reinterpret_cast<const uint4 *>(tile)[lane]);
+            __syncwarp();
+        }
+        // ---- more than 32*kMatPerLane infected agents in 512: patch the rest byte-wise
+        for (int e = 32 * kMatPerLane + lane; e < n_inf; e += 32) {
+            const int local = list[e];
+            const AgentRec r = load_rec(rec + local);
+            const int64_t i = (g % groups_per_rep) * 512 + local;
             for (int t = r.t_exposed(); t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t);
         }
+        __syncwarp();
     }
 }
 
@@ -551,7 +640,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(h->ev2, h->stream));
-    seir_materialize_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
+    seir_materialize_kernel<<<h->sms * 8, kMatThreads, 0, h->stream>>>(h->cx);
     ++h->launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev3, h->stream));
