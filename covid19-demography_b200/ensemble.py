@@ -1,0 +1,85 @@
+"""Seed ensembles and parameter sweeps over the GPUs of one box.
+
+The reference runs ensembles as a Python `for` loop over seeds inside one process
+(`run_simulation.py:437-444`, `simulate_agepolicies.py:605-613`, `parameter_sweep.py:546-554`) and
+spreads processes with a SLURM job array (`job.parameter_sweep.sh:15`): runs never talk to each other.
+Here the same work is dealt round-robin to one process per GPU (`partition`), each process packs its
+share into replica batches that share one device-resident population (`run_seeds`), and the small
+per-run results (`[T, 9, 101]` tallies, counters) are gathered on rank 0 (`gather`).  There is no
+data-path collective: `torch.distributed` is only used for the final gather.
+"""
+import numpy as np
+
+from . import tables as _tables
+
+
+def partition(n_items, rank, world):
+    """Indices of the work items rank `rank` of `world` owns: rank, rank + world, ... (round-robin, so
+    every rank gets the same count +-1 whatever the order of the items)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside [0, %d)" % (rank, world))
+    return list(range(rank, n_items, world))
+
+
+def batches(items, batch):
+    """Consecutive batches of at most `batch` items."""
+    if batch < 1:
+        raise ValueError("batch must be >= 1")
+    return [items[k:k + batch] for k in range(0, len(items), batch)]
+
+
+def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fraction, want_vectors=()):
+    """Run `seeds` on `engine` (an engine.Engine with R replica slots) in batches of R.
+
+    Per seed the reference's own prologue picks are used (`tables.prologue`, seir_individual.py:176-187).
+    A short last batch is padded by repeating its last seed (the padding runs are discarded).
+    Returns {"tallies": int64[len(seeds), T, 9, 101], "counters": [dict], "vectors": {name: float64[len(seeds), n]}}.
+    """
+    R = engine.n_replicas
+    n = engine.n
+    tallies = np.zeros((len(seeds), engine.T, 9, _tables.N_AGES), dtype=np.int64)
+    counters = []
+    vectors = {k: np.zeros((len(seeds), n)) for k in want_vectors}
+    done = 0
+    for chunk in batches(list(seeds), R):
+        padded = chunk + [chunk[-1]] * (R - len(chunk))
+        pro = [_tables.prologue(s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in padded]
+        engine.run(padded, [p[0] for p in pro], [p[1] for p in pro])
+        for r in range(len(chunk)):
+            tallies[done + r] = engine.tallies(r)
+            counters.append(engine.counters(r))
+            for k in want_vectors:
+                vectors[k][done + r] = engine.agent_vector(k, replica=r)
+        done += len(chunk)
+    return {"tallies": tallies, "counters": counters, "vectors": vectors}
+
+
+def gather(local_indices, local_array, n_items, dist=None):
+    """Assemble the per-item results of all ranks in item order on every rank.
+
+    local_array[k] belongs to item local_indices[k].  With `dist` (an initialised torch.distributed
+    module; gloo or nccl) the ranks exchange (indices, array) pairs; without it the call is the
+    identity for a single process."""
+    local_array = np.asarray(local_array)
+    out = np.zeros((n_items,) + local_array.shape[1:], dtype=local_array.dtype)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        pieces = [(list(local_indices), local_array)]
+    else:
+        pieces = [None] * dist.get_world_size()
+        dist.all_gather_object(pieces, (list(local_indices), local_array))
+    seen = np.zeros(n_items, dtype=bool)
+    for idx, arr in pieces:
+        for k, i in enumerate(idx):
+            if seen[i]:
+                raise RuntimeError("work item %d was produced by two ranks" % i)
+            seen[i] = True
+            out[i] = arr[k]
+    if not seen.all():
+        raise RuntimeError("work items %s were produced by no rank" % np.flatnonzero(~seen)[:8].tolist())
+    return out
+
+
+def curves_from_tallies(tallies):
+    """[..., T, 9, 101] -> [..., T, 9]: the per-day column sums the drivers compute from the histories
+    (run_simulation.py:448-456)."""
+    return np.asarray(tallies).sum(axis=-1)

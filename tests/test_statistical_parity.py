@@ -1,0 +1,90 @@
+"""Statistical parity (tier T4; BASELINE.json north_star): with native keyed draws
+the ensemble of daily infection / ICU / death curves must agree with the UNMODIFIED reference's ensemble.
+
+The reference ensemble (64 seeds, one fixed 20 000-agent Italy population, tracing never on) was frozen
+by oracle/make_golden.py::run_ensemble from the reference's own numba run_model.  Tolerances, stated:
+  * two-sample Kolmogorov-Smirnov on final deaths, peak ICU (Critical), final attack size and peak
+    Mild: p-value > 1e-3 for each (a 64-vs-64 KS test rejects a 15 % shift of the median at that level);
+  * confidence-interval overlap on the daily means of cumulative infections, Critical and deaths at
+    days 10, 20, ..., 59: |mean_a - mean_b| <= 4 combined standard errors + 1 agent.
+The CPU tier checks the oracle's keyed providers (both community modes) this way; the gpu tier
+checks the CUDA path (64 replicas in ONE persistent launch) the same way."""
+import numpy as np
+import pytest
+import scipy.stats as st
+
+import oracle
+import util
+from covid19_demography_b200 import ensemble, tables as tables_mod
+
+N_SEEDS = 64
+KS_P_MIN = 1e-3
+CI_SIGMAS = 4.0
+
+
+def reference_ensemble():
+    c = util.Case("ensemble_italy_n20000")
+    return c, c.fx["curves"].astype(np.int64)  # [64, T, 9]
+
+
+def assert_same_distribution(a, b, n, label):
+    """a, b: [seeds, T, 9] per-day plane sums (order S,E,Mild,Documented,Severe,Critical,R,D,Q)."""
+    stats = {
+        "final deaths": lambda c: c[:, -1, 7],
+        "peak ICU": lambda c: c[:, :, 5].max(axis=1),
+        "final attack size": lambda c: n - c[:, -1, 0],
+        "peak Mild": lambda c: c[:, :, 2].max(axis=1),
+    }
+    for name, f in stats.items():
+        p = st.ks_2samp(f(a), f(b)).pvalue
+        assert p > KS_P_MIN, "%s: KS p=%.2e on %s (means %.1f vs %.1f)" % (label, p, name, f(a).mean(), f(b).mean())
+    T = a.shape[1]
+    for day in list(range(10, T, 10)) + [T - 1]:
+        for name, col in (("infections", lambda c: n - c[:, day, 0]), ("Critical", lambda c: c[:, day, 5]),
+                          ("deaths", lambda c: c[:, day, 7])):
+            xa, xb = col(a).astype(float), col(b).astype(float)
+            se = np.sqrt(xa.var(ddof=1) / len(xa) + xb.var(ddof=1) / len(xb))
+            assert abs(xa.mean() - xb.mean()) <= CI_SIGMAS * se + 1.0, \
+                "%s: day %d %s means %.1f vs %.1f (se %.2f)" % (label, day, name, xa.mean(), xb.mean(), se)
+
+
+def _oracle_ensemble(c, mode, seeds):
+    T = int(c.params["T"])
+    curves = np.zeros((len(seeds), T, 9), dtype=np.int64)
+    for k, s in enumerate(seeds):
+        tup, _, _, _ = c.keyed_oracle(mode, c.params, seed=s)
+        for j in range(9):
+            curves[k, :, j] = np.asarray(tup[j]).sum(axis=1)
+    return curves
+
+
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_keyed_oracle_ensemble_matches_reference_ensemble(mode):
+    c, ref = reference_ensemble()
+    got = _oracle_ensemble(c, mode, list(range(500, 500 + N_SEEDS)))
+    assert_same_distribution(got, ref, c.n, "oracle/" + mode)
+
+
+def test_reference_ensemble_fixture_is_sane():
+    c, ref = reference_ensemble()
+    assert ref.shape == (N_SEEDS, int(c.params["T"]), 9)
+    assert (ref[:, :, [0, 1, 2, 4, 5, 6, 7]].sum(axis=2) == c.n).all()  # compartments partition the agents
+    assert (np.diff(ref[:, :, 0], axis=1) <= 0).all() and (np.diff(ref[:, :, 7], axis=1) >= 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_gpu_ensemble_matches_reference_ensemble(gpu_engine_module, mode):
+    """64 seeds as 64 replicas of one persistent launch on the device."""
+    c, ref = reference_ensemble()
+    eng = c.gpu_engine(gpu_engine_module, c.params, mode, n_replicas=N_SEEDS)
+    seeds = list(range(900, 900 + N_SEEDS))
+    res = ensemble.run_seeds(eng, seeds, c.age_groups, c.fraction_stay_home, c.params["initial_infected_fraction"])
+    got = ensemble.curves_from_tallies(res["tallies"])
+    assert_same_distribution(got, ref, c.n, "gpu/" + mode)
+    # and the device ensemble is the keyed oracle's, bit for bit, on a few of its members
+    for k in (0, 17, 63):
+        tup, _, _, _ = c.keyed_oracle(mode, c.params, seed=seeds[k])
+        want = np.stack([np.asarray(tup[j]).sum(axis=1) for j in range(9)], axis=1)
+        assert np.array_equal(got[k], want)
+    eng.close()
