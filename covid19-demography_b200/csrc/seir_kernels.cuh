@@ -238,8 +238,16 @@ __device__ __noinline__ uint32_t poisson_ni(uint64_t seed, uint32_t agent, uint3
     return sd_poisson(seed, agent, day, site, sub_base, enlam, cap);
 }
 
-// per-CTA shared state of a day pass.  A ROUND takes up to kSlots list entries through four convergent
-// stages separated by __syncthreads(): A agents -> C contacts -> H hits -> W infector counters.
+// per-CTA shared state of a day pass.  A ROUND takes up to kSlots list entries through six convergent
+// stages separated by __syncthreads(), with shared-memory work queues between them:
+//   A  every entry: record build/load, tallies of day t-1, the draw-free transitions (recovery, death,
+//      isolation entry), the documentation draw, the household S-mask, the first community uniform.
+//      Everything rare or heavy is QUEUED, not executed in place: a warp pays for every path any of
+//      its lanes takes, so stage A keeps to the path (almost) every lane takes
+//   E  agents with a progression event due today (E->Mild, Mild->Severe, Severe->Critical), compacted
+//   D  draw items: one Philox block of household draws / one sender's kept-contact count
+//   C  candidate contacts -> H hits -> W infector counters.
+// Sparse lists and short queues are dealt ONE ITEM PER WARP (then 2, 4, ... per warp as they grow).
 // No per-thread state survives a stage: stages talk through the queues below and the records in L2.
 #ifndef SEIR_ENTRIES_PER_THREAD
 #define SEIR_ENTRIES_PER_THREAD 4
@@ -248,8 +256,17 @@ constexpr int kPerThread = SEIR_ENTRIES_PER_THREAD;  // list entries a thread ta
 constexpr int kSlots = kPerThread * kThreads;        // agents per round and CTA
 constexpr int kConCap = kSlots;                      // contact queue entries per round
 constexpr int kHitCap = kSlots / 2;                  // hit queue entries per round
+constexpr int kDrawCap = 2 * kSlots;                 // draw-item queue entries per round
+#ifndef SEIR_QUEUE_EVENTS
+#define SEIR_QUEUE_EVENTS 0   // 1: progression events run compacted in stage E; 0: in place in stage A (measured faster on C2)
+#endif
+#ifndef SEIR_QUEUE_DRAWS
+#define SEIR_QUEUE_DRAWS 1    // 1: household draw blocks / kept-contact counts run in stage D; 0: in place in stage A
+#endif
+constexpr int kWarps = kThreads / 32;
 constexpr int kOutOld = 2 * kSlots;                  // staged survivors
 constexpr int kOutNew = kSlots;                      // staged new infectees
+static_assert(kSlots <= 65536, "slot ids travel in 16 bits");
 struct RepView {
     uint32_t *inbox;
     unsigned long long *winner;
@@ -262,6 +279,11 @@ struct RepView {
     int phase;
 };
 
+// draw-queue items: slot<<16 | kind<<14 | payload
+enum { DQ_HH = 0,      // payload = jb<<2 | two S-mask bits: household members 2jb, 2jb+1 (draw block jb of site HH)
+       DQ_NATIVE = 1,  // the sender's first Knuth uniform did not end the product: finish the kept-contact count
+       DQ_REPLAY = 2 };// the sender's 101 Poisson draws of the replay mode
+
 struct __align__(16) PassSmem {
     RepView v;                     // the replica this CTA serves in the current pass (uniform per CTA)
     uint32_t out_old[kOutOld];
@@ -270,16 +292,18 @@ struct __align__(16) PassSmem {
     uint32_t hit_meta[kHitCap];    // slot<<16 | ord
     uint8_t hit_age[kHitCap];      // age of the infectee, 127 = look it up
     uint32_t conq[kConCap];        // slot<<16 | payload (native: k; replay: age<<8 | j)
+    uint32_t drawq[kDrawCap];
+    uint16_t evq[kSlots];          // slots with a progression event due
     uint32_t slot_agent[kSlots];
     uint32_t hit_n[kSlots];        // hits of the slot's agent this round: total | outside<<16
-    uint8_t slot_info[kSlots];     // age | E<<7
+    uint16_t slot_info[kSlots];    // age | E<<7 | household position<<8
     uint32_t tally[TAL_ROWS * kAges];
     // small per-age tables staged once per kernel (the grid barrier's acquire loads keep flushing L1)
     double iso_asym[kAges], iso_mean[kAges];
     double nat_enlam[2 * kAges * 2];
     int32_t grp_off[kAges + 1];
     uint32_t cnt[4];
-    uint32_t n_old, n_new, n_hit, n_con, base_old, base_new;
+    uint32_t n_old, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_new;
 };
 
 __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
@@ -296,6 +320,22 @@ __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
 __device__ __forceinline__ bool at_home(const RepView &v, int64_t c)
 {
     return v.home_on && ((__ldg(v.home + (c >> 5)) >> (c & 31)) & 1u);
+}
+
+// threads per item when n items are dealt to a CTA: one item per warp while they fit, then 2, 4, ... per warp
+__device__ __forceinline__ uint32_t spread_of(uint32_t n, uint32_t threads)
+{
+    uint32_t s = 32;
+    while (s > 1 && n * s > threads) s >>= 1;
+    return s;
+}
+// f(q) for q in [0, n), item q on thread (q mod (kThreads/S)) * S
+template <class F> __device__ __forceinline__ void for_items(uint32_t n, F f)
+{
+    const uint32_t S = spread_of(n, kThreads), per = kThreads / S;
+    const bool mine = (threadIdx.x & (S - 1u)) == 0u;
+    for (uint32_t q = threadIdx.x / S; q < n; q += per)
+        if (mine) f(q);
 }
 
 // ---- stage H: one successful transmission slot's agent -> c on day t (:347-359 / :376-390) ----------
@@ -324,7 +364,6 @@ __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_
 __device__ __forceinline__ void push_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
                                          int age_c, int t)
 {
-    const RepView &v = sm.v;
     const uint32_t pos = atomicAdd(&sm.n_hit, 1u);
     if (pos < (uint32_t)kHitCap) {
         sm.hit_c[pos] = c;
@@ -375,10 +414,59 @@ __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uin
 
 __device__ __forceinline__ void push_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
-    const RepView &v = sm.v;
     const uint32_t pos = atomicAdd(&sm.n_con, 1u);
     if (pos < (uint32_t)kConCap) sm.conq[pos] = item;
     else process_contact(cx, sm, item, t);
+}
+
+// ---- stage D: one draw item ---------------------------------------------------------------------------
+__device__ __noinline__ void process_draw_item(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
+{
+    const RepView &v = sm.v;
+    const uint32_t slot = item >> 16, kind = (item >> 14) & 3u, payload = item & 0x3FFFu;
+    const uint32_t i = sm.slot_agent[slot];
+    const uint32_t info = sm.slot_info[slot];
+    const bool Ep = (info & 128u) != 0u;
+    const int age = (int)(info & 127u);
+    if (kind == DQ_HH) {  // :346 for household members 2jb, 2jb+1
+        const uint32_t jb = payload >> 2, bits = payload & 3u;
+        const int pos = (int)((info >> 8) & 7u);
+        const uint32_t base = i - (uint32_t)pos;
+        double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
+        if (Ep) p_h = SD_MUL(p_h, cx.asym);
+        const sd_block hb = draw_block(v.seed, i, (uint32_t)t, SD_SITE_HH, jb);
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            const int j = 2 * (int)jb + l;
+            if (((bits >> l) & 1u) && sd_lane(hb, l) < p_h)
+                push_hit(cx, sm, base + j + (j >= pos ? 1 : 0), (slot << 16) | SD_ORD_HH(j), 127, t);
+        }
+    } else if (kind == DQ_NATIVE) {  // sd_poisson_day past its first uniform (lane 1 of the day block)
+        const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
+        const sd_block db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
+        const uint32_t kept = poisson_day_more(v.seed, i, (uint32_t)t, sd_lane(db, 1), en, SD_MAX_CONTACTS_NATIVE);
+        for (uint32_t k = 0; k < kept; ++k) push_contact(cx, sm, (slot << 16) | k, t);
+    } else {  // :367-372, one Poisson per non-empty contact age
+        const double *en = cx.enlam + ((size_t)v.phase * kAges + age) * kAges;
+#pragma unroll 1
+        for (int a = 0; a < kAges; ++a) {
+            if (sm.grp_off[a + 1] == sm.grp_off[a]) continue;  // :368-369
+            const uint32_t nc = poisson_ni(v.seed, i, (uint32_t)t, SD_SITE_POIS, (uint32_t)a << 8, __ldg(en + a),
+                                           SD_MAX_CONTACTS_PER_AGE);
+            for (uint32_t j = 0; j < nc; ++j) push_contact(cx, sm, (slot << 16) | ((uint32_t)a << 8) | j, t);
+        }
+    }
+}
+
+__device__ __forceinline__ void push_draw(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
+{
+#if SEIR_QUEUE_DRAWS
+    const uint32_t pos = atomicAdd(&sm.n_draw, 1u);
+    if (pos < (uint32_t)kDrawCap) sm.drawq[pos] = item;
+    else process_draw_item(cx, sm, item, t);
+#else
+    process_draw_item(cx, sm, item, t);
+#endif
 }
 
 __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm, uint32_t i, int t, AgentRec &r)
@@ -405,7 +493,7 @@ __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm,
     atomicAdd(&sm.tally[TAL_NEW_E * kAges + (stt & 127)], 1u);
 }
 
-// rare events of the agent's own progression
+// the progression events of the agent's own day (:256-272, :291-311, :312-321)
 __device__ __forceinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
                                                 AgentRec &r, int comp, int &ncomp, bool &nq, bool &ndoc)
 {
@@ -456,47 +544,29 @@ __device__ __forceinline__ void progression_events(const DevCtx &cx, const PassS
     }
 }
 
-// ---- stage A: one list entry.  The agent's own day (:256-337), then WHICH household members and HOW MANY
-// community contacts it may infect today (queued for stages C / H).  Returns true if it stays on the list.
-__device__ __forceinline__ bool stage_a_entry(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i,
-                                              bool is_new, int t, bool finalize)
+// ---- the agent's own day (:256-337) and the set-up of its transmission (:339-390) ---------------------
+// IN_EV = false: stage A.  An agent with a progression event due is handed to stage E untouched
+//                (returns DAY_DEFER); everything else is finished here.
+// IN_EV = true : stage E, the same statements with the event.
+// Returns DAY_KEEP if the agent stays on the active list.
+enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_DEFER = 2 };
+template <bool IN_EV>
+__device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i, AgentRec &r,
+                                         bool dirty, int t)
 {
     const RepView &v = sm.v;
-    AgentRec r;
-    bool dirty = false;
-    SEIR_FINE(0);
-    if (is_new) {
-        build_new_record(cx, sm, i, t, r);
-        dirty = true;
-    } else {
-        r = load_rec(v.rec + i);
-    }
     const uint16_t stt = r.stat();
-    if (stt == 0xFFFF) return false;  // (never; keeps the load above the stamp)
-    SEIR_FINE(1);
     const int age = stt & 127;
     const uint8_t st = r.state();
     const int comp = st & 7;
     const bool Ep = comp == C_E, Mp = comp == C_MILD, Sevp = comp == C_SEV, Cp = comp == C_CRIT;
     const bool Qp = (st & ST_Q) != 0, Dp = (st & ST_DOC) != 0;
-    sm.slot_agent[slot] = i;
-    sm.slot_info[slot] = (uint8_t)(age | (Ep ? 128 : 0));
-    sm.hit_n[slot] = 0;
-    // state tallies of day t-1
-    atomicAdd(&sm.tally[(comp - C_E) * kAges + age], 1u);
-    if (Qp) atomicAdd(&sm.tally[TAL_QACT * kAges + age], 1u);
-    if (finalize) {  // pass T: nothing moves
-        if (dirty) store_rec(v.rec + i, r);
-        return false;
-    }
     int ncomp = comp;
     bool nq = Qp, ndoc = Dp;
-    // the agent's day block: documentation draw + first uniform of the contact count
-    SEIR_FINE(2);
-    const sd_block db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
-    if (db.w[0] == 0x12345678u && db.w[1] == 0x9abcdef0u) return false;  // (never)
-    SEIR_FINE(3);
     bool transmit = !Qp;
+    bool have_db = false;
+    sd_block db;
+    db.w[0] = db.w[1] = db.w[2] = db.w[3] = 0u;
     const int t_inf = t_infected_of(r);
     if (!Ep && due(t, t_inf, r.tt_recovery())) {  // :276-279
         ncomp = C_R;
@@ -504,13 +574,22 @@ __device__ __forceinline__ bool stage_a_entry(const DevCtx &cx, PassSmem &sm, ui
         transmit = false;
         atomicAdd(&sm.tally[TAL_NEW_R * kAges + age], 1u);
     } else {
-        if (Mp && !Dp && sd_lane(db, 0) < cx.p_doc) {  // :280-289
-            ndoc = true;
-            r.set_t_documented((uint16_t)t);
-        }
         const bool ev = (Ep && due(t, r.t_exposed(), r.tt_activation())) || (Mp && due(t, t_inf, r.tt_severe())) ||
                         (Sevp && due(t, t_severe_of(r), r.tt_critical()));
-        if (ev) {
+        if (!IN_EV && ev) {
+            if (dirty) store_rec(v.rec + i, r);
+            sm.evq[atomicAdd(&sm.n_ev, 1u)] = (uint16_t)slot;  // (at most one entry per slot: cannot overflow)
+            return DAY_DEFER;
+        }
+        if (Mp && !Dp && cx.p_doc > 0.0) {  // :280-289 (lane 0 of the agent's day block)
+            db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
+            have_db = true;
+            if (sd_lane(db, 0) < cx.p_doc) {
+                ndoc = true;
+                r.set_t_documented((uint16_t)t);
+            }
+        }
+        if (IN_EV && ev) {
             progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc);
             dirty = true;
         } else if (Cp && due(t, t_critical_of(r), r.tt_death())) {  // :323-327
@@ -533,9 +612,7 @@ __device__ __forceinline__ bool stage_a_entry(const DevCtx &cx, PassSmem &sm, ui
         if (ncomp == C_R || ncomp == C_D) r.set_t_end((uint16_t)t);
         dirty = true;
     }
-    SEIR_FINE(4);
     if (dirty) store_rec(v.rec + i, r);
-    SEIR_FINE(5);
 
     if (transmit) {
         // ---- household push :339-359; households are contiguous ranges [i-pos, i-pos+size)
@@ -549,54 +626,79 @@ __device__ __forceinline__ bool stage_a_entry(const DevCtx &cx, PassSmem &sm, ui
                 if (w == 0ull || (int)(w >> 48) == t) smask |= 1u << j;  // S[t-1,c] (:346)
             }
         }
-        SEIR_FINE(6);
-        if (smask) {
-            double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
-            if (Ep) p_h = SD_MUL(p_h, cx.asym);
-#pragma unroll 1
-            for (int jb = 0; jb < 4; ++jb) {
-                if (!((smask >> (2 * jb)) & 3u)) continue;
-                const sd_block hb = draw_block(v.seed, i, (uint32_t)t, SD_SITE_HH, (uint32_t)jb);
-#pragma unroll
-                for (int l = 0; l < 2; ++l) {
-                    const int j = 2 * jb + l;
-                    if (((smask >> j) & 1u) && sd_lane(hb, l) < p_h)
-                        push_hit(cx, sm, base + j + (j >= pos ? 1 : 0), (slot << 16) | SD_ORD_HH(j), 127, t);
-                }
-            }
+        // ---- community push :361-390: the first Knuth uniform of the kept-contact count is lane 1 of the day block
+        const bool out = !at_home(v, i);
+        if (out && cx.mode == SEIR_MODE_NATIVE) {
+            if (!have_db) db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
+            const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
+            if (sd_lane(db, 1) > en) push_draw(cx, sm, (slot << 16) | (DQ_NATIVE << 14), t);
+        } else if (out) {
+            push_draw(cx, sm, (slot << 16) | (DQ_REPLAY << 14), t);
         }
-        SEIR_FINE(7);
-        // ---- community push :361-390: decide HOW MANY candidate contacts, queue them
-        if (!at_home(v, i)) {
-            if (cx.mode == SEIR_MODE_NATIVE) {
-                const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
-                const double u1 = sd_lane(db, 1);  // sd_poisson_day: the first Knuth uniform is lane 1 of the day block
-                const uint32_t kept = (u1 <= en) ? 0u : poisson_day_more(v.seed, i, (uint32_t)t, u1, en, SD_MAX_CONTACTS_NATIVE);
-                for (uint32_t k = 0; k < kept; ++k) push_contact(cx, sm, (slot << 16) | k, t);
-            } else {
-                const double *en = cx.enlam + ((size_t)v.phase * kAges + age) * kAges;
-#pragma unroll 1
-                for (int a = 0; a < kAges; ++a) {
-                    if (sm.grp_off[a + 1] == sm.grp_off[a]) continue;  // :368-369
-                    const uint32_t nc = poisson_ni(v.seed, i, (uint32_t)t, SD_SITE_POIS, (uint32_t)a << 8, __ldg(en + a),
-                                                   SD_MAX_CONTACTS_PER_AGE);
-                    for (uint32_t j = 0; j < nc; ++j) push_contact(cx, sm, (slot << 16) | ((uint32_t)a << 8) | j, t);
-                }
-            }
+#pragma unroll
+        for (uint32_t jb = 0; jb < 4; ++jb) {
+            const uint32_t bits = (smask >> (2 * jb)) & 3u;
+            if (bits) push_draw(cx, sm, (slot << 16) | (DQ_HH << 14) | (jb << 2) | bits, t);
         }
     }
-    SEIR_FINE(8);
-    return ncomp >= C_E && ncomp <= C_CRIT;
+    return (ncomp >= C_E && ncomp <= C_CRIT) ? DAY_KEEP : DAY_DROP;
+}
+
+// ---- stage A: one list entry -----------------------------------------------------------------------------
+__device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i,
+                                             bool is_new, int t, bool finalize)
+{
+    const RepView &v = sm.v;
+    AgentRec r;
+    bool dirty = false;
+    if (is_new) {
+        build_new_record(cx, sm, i, t, r);
+        dirty = true;
+    } else {
+        r = load_rec(v.rec + i);
+    }
+    const uint16_t stt = r.stat();
+    const int age = stt & 127;
+    const uint8_t st = r.state();
+    const int comp = st & 7;
+    sm.slot_agent[slot] = i;
+    sm.slot_info[slot] = (uint16_t)(age | (comp == C_E ? 128 : 0) | (((stt >> 9) & 7) << 8));
+    // state tallies of day t-1
+    atomicAdd(&sm.tally[(comp - C_E) * kAges + age], 1u);
+    if (st & ST_Q) atomicAdd(&sm.tally[TAL_QACT * kAges + age], 1u);
+    if (finalize) {  // pass T: nothing moves
+        if (dirty) store_rec(v.rec + i, r);
+        return DAY_DROP;
+    }
+    return agent_day<SEIR_QUEUE_EVENTS == 0>(cx, sm, slot, i, r, dirty, t);
+}
+
+// survivors re-append themselves to tomorrow's list: one shared-memory atomic per warp
+__device__ __forceinline__ void append_survivors(PassSmem &sm, bool keep, uint32_t i)
+{
+    const RepView &v = sm.v;
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (m) {
+        uint32_t base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&sm.n_old, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+        if (keep) {
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (pos < (uint32_t)kOutOld) sm.out_old[pos] = i;
+            else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
 // Pass t over all replicas.  CTA b serves replica (b / blocks_per_rep) [+ k * reps_per_sweep]; the CTAs of a
-// replica split its list into equal contiguous chunks, kPerThread entries per thread and round.
+// replica split its list: a list shorter than the replica's threads is dealt S threads apart (one entry
+// per warp while it fits), a longer one in equal contiguous chunks, kPerThread entries per thread and round.
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
 __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
 {
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
     bool stamped = false;
     const bool finalize = t >= cx.T;
     const int bpr = cx.blocks_per_rep;
@@ -623,94 +725,130 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
         const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t);
         const uint32_t count = n_new + n_old;  // new infectees first: their record build stays convergent
-        // this CTA's contiguous chunk, a multiple of 32 entries
-        const uint32_t chunk = ((count + (uint32_t)bpr - 1) / (uint32_t)bpr + 31u) & ~31u;
-        const uint32_t lo = (uint32_t)my_part * chunk;
-        const uint32_t hi = lo + chunk < count ? lo + chunk : count;
+        // this CTA's share of the list.  Sparse (the list fits the replica's threads in one sub-iteration):
+        // entry q sits on replica-thread q*S, one entry per warp while that fits.  Dense: groups of 32
+        // entries are dealt round-robin to the replica's CTAs (the new infectees, whose record build is the
+        // longest path, lead the list: a contiguous split would give them all to the first CTAs).
+        const uint32_t rep_threads = (uint32_t)bpr * kThreads;
+        const bool sparse = count <= rep_threads;
+        const uint32_t S = sparse ? spread_of(count, rep_threads) : 1u;
+        const uint32_t n_groups = (count + 31u) / 32u;
+        const uint32_t my_groups = (!sparse && n_groups > (uint32_t)my_part) ? (n_groups - (uint32_t)my_part + (uint32_t)bpr - 1u) / (uint32_t)bpr : 0u;
+        const uint32_t rounds = sparse ? (((uint32_t)my_part * kThreads) / S < count ? 1u : 0u)
+                                       : (my_groups + (uint32_t)(kPerThread * kWarps) - 1u) / (uint32_t)(kPerThread * kWarps);
 
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
         if (tid < 4) sm.cnt[tid] = 0;
-        if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; }
+        if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; }
         __syncthreads();
         SEIR_STAMP(0);
 
-        for (uint32_t e0 = lo; e0 < hi; e0 += (uint32_t)kSlots) {
+        for (uint32_t round = 0; round < rounds; ++round) {
             // ================= stage A: up to kPerThread list entries per thread =================
+            uint32_t subs = 0;
 #pragma unroll 1
             for (int sub = 0; sub < kPerThread; ++sub) {
-                const uint32_t eb = e0 + (uint32_t)sub * kThreads;
-                if (eb >= hi) break;
-                const uint32_t e = eb + tid;
-                bool keep = false;
-                uint32_t i = 0;
-                if (e < hi) {
-                    const bool is_new = e < n_new;
-                    i = is_new ? __ldcg(cur_new + e) : __ldcg(cur_old + (e - n_new));
-                    keep = stage_a_entry(cx, sm, (uint32_t)sub * kThreads + tid, i, is_new, t, finalize);
-#ifdef SEIR_FINE_STAMPS
-                    if (blockIdx.x == 0 && tid == 0 && sub == 0) cx.fine_ns[(size_t)t * 16 + 9] = global_timer_ns();
-#endif
+                uint32_t e;
+                bool has;
+                if (sparse) {
+                    if (sub > 0) break;
+                    e = ((uint32_t)my_part * kThreads + (uint32_t)tid) / S;
+                    has = (((uint32_t)tid & (S - 1u)) == 0u) && e < count;
+                } else {
+                    const uint32_t kb = (round * (uint32_t)kPerThread + (uint32_t)sub) * (uint32_t)kWarps;
+                    if (kb >= my_groups) break;
+                    const uint32_t k = kb + ((uint32_t)tid >> 5);
+                    e = (k * (uint32_t)bpr + (uint32_t)my_part) * 32u + ((uint32_t)tid & 31u);
+                    has = k < my_groups && e < count;
                 }
-                // survivors re-append themselves: one shared-memory atomic per warp
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-                if (m) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&sm.n_old, (uint32_t)__popc(m));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (keep) {
-                        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                        if (pos < (uint32_t)kOutOld) sm.out_old[pos] = i;
-                        else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
-                    }
+                ++subs;
+                const uint32_t slot = (uint32_t)sub * kThreads + tid;
+                sm.hit_n[slot] = 0;
+                int keep = DAY_DROP;
+                uint32_t i = 0;
+                const bool is_new = e < n_new;
+                if (has) {
+                    i = is_new ? __ldcg(cur_new + e) : __ldcg(cur_old + (e - n_new));
+                    keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
+                }
+                append_survivors(sm, keep == DAY_KEEP, i);
+                const unsigned hm = __ballot_sync(0xFFFFFFFFu, has), nm = __ballot_sync(0xFFFFFFFFu, has && is_new);
+                if ((tid & 31) == 0 && hm) {
+                    atomicAdd(&sm.cnt[0], (uint32_t)__popc(hm));
+                    if (nm) atomicAdd(&sm.cnt[1], (uint32_t)__popc(nm));
                 }
             }
             __syncthreads();
             SEIR_STAMP(1);
-            // ================= stage C: candidate contacts, one per thread =================
-            {
-                const uint32_t nc = sm.n_con < (uint32_t)kConCap ? sm.n_con : (uint32_t)kConCap;
-                for (uint32_t q = tid; q < nc; q += kThreads) process_contact(cx, sm, sm.conq[q], t);
+            // ================= stage E: progression events, compacted =================
+            if (sm.n_ev) {
+                const uint32_t ne = sm.n_ev;
+                const uint32_t Sq = spread_of(ne, kThreads), per = kThreads / Sq;
+                for (uint32_t q0 = 0; q0 < ne; q0 += per) {
+                    const uint32_t q = q0 + (uint32_t)tid / Sq;
+                    int keep = DAY_DROP;
+                    uint32_t i = 0;
+                    if ((((uint32_t)tid & (Sq - 1u)) == 0u) && q < ne) {
+                        const uint32_t slot = sm.evq[q];
+                        i = sm.slot_agent[slot];
+                        AgentRec r = load_rec(v.rec + i);
+                        keep = agent_day<true>(cx, sm, slot, i, r, false, t);
+                    }
+                    append_survivors(sm, keep == DAY_KEEP, i);
+                }
+                __syncthreads();
             }
-            __syncthreads();
             SEIR_STAMP(2);
-            // ================= stage H: hits, one per thread =================
-            {
-                const uint32_t nh = sm.n_hit < (uint32_t)kHitCap ? sm.n_hit : (uint32_t)kHitCap;
-                for (uint32_t q = tid; q < nh; q += kThreads) process_hit(cx, sm, sm.hit_c[q], sm.hit_meta[q], sm.hit_age[q], t);
+            // ================= stage D: draw items =================
+            if (sm.n_draw) {
+                const uint32_t nd = sm.n_draw < (uint32_t)kDrawCap ? sm.n_draw : (uint32_t)kDrawCap;
+                for_items(nd, [&](uint32_t q) { process_draw_item(cx, sm, sm.drawq[q], t); });
+                __syncthreads();
             }
-            __syncthreads();
             SEIR_STAMP(3);
+            // ================= stage C: candidate contacts =================
+            if (sm.n_con) {
+                const uint32_t nc = sm.n_con < (uint32_t)kConCap ? sm.n_con : (uint32_t)kConCap;
+                for_items(nc, [&](uint32_t q) { process_contact(cx, sm, sm.conq[q], t); });
+                __syncthreads();
+            }
+            SEIR_STAMP(4);
+            // ================= stage H: hits =================
+            const bool any_hit = sm.n_hit != 0u;
+            if (any_hit) {
+                const uint32_t nh = sm.n_hit < (uint32_t)kHitCap ? sm.n_hit : (uint32_t)kHitCap;
+                for_items(nh, [&](uint32_t q) { process_hit(cx, sm, sm.hit_c[q], sm.hit_meta[q], sm.hit_age[q], t); });
+                __syncthreads();
+            }
+            SEIR_STAMP(5);
             // ================= stage W: infector counters (:357-359, :386-390) =================
             {
-                const uint32_t ns = hi - e0 < (uint32_t)kSlots ? hi - e0 : (uint32_t)kSlots;
-                for (uint32_t sl = tid; sl < ns; sl += kThreads) {
-                    const uint32_t hn = sm.hit_n[sl];
-                    if (hn) {
-                        const uint32_t hits = hn & 0xFFFFu, hits_out = hn >> 16;
-                        // second half of the record: n_inf_by | n_inf_asympt<<16, n_inf_outside | t_end<<16, ...
-                        uint2 *q = reinterpret_cast<uint2 *>(v.rec + sm.slot_agent[sl]) + 2;
-                        uint2 u = __ldcg(q);
-                        uint32_t by = inc_sat16((uint16_t)(u.x & 0xFFFFu), hits), as = u.x >> 16;
-                        if (sm.slot_info[sl] & 128u) as = inc_sat16((uint16_t)as, hits);
-                        u.x = by | (as << 16);
-                        u.y = (u.y & 0xFFFF0000u) | inc_sat16((uint16_t)(u.y & 0xFFFFu), hits_out);
-                        __stcg(q, u);
-                        atomicAdd(&sm.cnt[2], hits);
+                const uint32_t ns = subs * kThreads;
+                if (any_hit) {
+                    for (uint32_t sl = tid; sl < ns; sl += kThreads) {
+                        const uint32_t hn = sm.hit_n[sl];
+                        if (hn) {
+                            const uint32_t hits = hn & 0xFFFFu, hits_out = hn >> 16;
+                            // second half of the record: n_inf_by | n_inf_asympt<<16, n_inf_outside | t_end<<16, ...
+                            uint2 *q = reinterpret_cast<uint2 *>(v.rec + sm.slot_agent[sl]) + 2;
+                            uint2 u = __ldcg(q);
+                            uint32_t by = inc_sat16((uint16_t)(u.x & 0xFFFFu), hits), as = u.x >> 16;
+                            if (sm.slot_info[sl] & 128u) as = inc_sat16((uint16_t)as, hits);
+                            u.x = by | (as << 16);
+                            u.y = (u.y & 0xFFFF0000u) | inc_sat16((uint16_t)(u.y & 0xFFFFu), hits_out);
+                            __stcg(q, u);
+                            atomicAdd(&sm.cnt[2], hits);
+                        }
                     }
-                }
-                if (tid == 0) {
-                    atomicAdd(&sm.cnt[0], ns);
-                    const uint32_t nn = n_new > e0 ? (n_new - e0 < ns ? n_new - e0 : ns) : 0u;  // new infectees in this round
-                    atomicAdd(&sm.cnt[1], nn);
                 }
             }
             __syncthreads();
             // flush the staging buffers when the next round could overflow them
-            {
+            if (round + 1u < rounds) {
                 const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
                 const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
                 const bool fo = so > (uint32_t)(kOutOld - kSlots), fn = sn > (uint32_t)(kOutNew - kHitCap);
-                if ((fo || fn) && e0 + (uint32_t)kSlots < hi) {
+                if (fo || fn) {
                     if (tid == 0) {
                         if (fo) sm.base_old = atomicAdd(v.next_old_cnt, so);
                         if (fn) sm.base_new = atomicAdd(v.next_new_cnt, sn);
@@ -724,10 +862,10 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                         if (fn) sm.n_new = 0;
                     }
                 }
-                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; }
+                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; }
                 __syncthreads();
             }
-            SEIR_STAMP(4);
+            SEIR_STAMP(6);
             stamped = true;
         }
         stamped = false;
@@ -744,7 +882,6 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
             }
         }
-        SEIR_STAMP(5);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
@@ -761,7 +898,7 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
         }
         __syncthreads();
-        SEIR_STAMP(6);
+        SEIR_STAMP(7);
     }
 }
 

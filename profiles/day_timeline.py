@@ -25,8 +25,8 @@ act = tal[:, [1, 2, 4, 5], :].sum(axis=(1, 2))
 print("init/loop/materialize ms:", eng.last_run_ms3(), "sum of passes us: %.1f" % us.sum())
 st = eng.stage_times_us()
 for t in range(1, len(us) + 1):
-    print("pass %2d  %7.2f us   active(t-1)=%-7d stages(setup,A,C,H,W,lists,tallies): %s"
-          % (t, us[t - 1], act[t - 1] if t - 1 < len(act) else -1, " ".join("%6.2f" % x for x in st[t, :7])))
+    print("pass %2d  %7.2f us   active(t-1)=%-7d stages(setup,A,E,D,C,H,W,end): %s"
+          % (t, us[t - 1], act[t - 1] if t - 1 < len(act) else -1, " ".join("%6.2f" % x for x in st[t, :8])))
 if os.environ.get("FINE"):
     import ctypes as C
     out = np.zeros((eng.T + 2) * 16, dtype=np.int64)
