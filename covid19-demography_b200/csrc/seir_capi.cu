@@ -20,10 +20,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     // the host resets the barrier counter to 0 before each launch
     stage_tables(cx, sm);
+    unsigned int epoch = 0;  // grid barriers passed so far
     for (int t = 1; t <= cx.T; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
         day_pass(cx, sm, t);
-        if (t < cx.T) grid_barrier(cx.barrier, (unsigned int)t * gridDim.x);
+        if (t < cx.T) {
+            grid_barrier(cx.barrier, ++epoch * gridDim.x);
+            if (cx.trace_from >= 1 && t >= cx.trace_from) {  // :241-242 tracing is on: resolve the day's traces
+                bool any = false;  // (grid-uniform: the counts are final after the barrier)
+                for (int r = 0; r < cx.n_rep; ++r) any = any || __ldcg(cx.root_cnt + (size_t)r * (cx.T + 2) + t) != 0u;
+                if (any) {
+                    trace_pass(cx, *reinterpret_cast<TraceSmem *>(sm.out_old), t);
+                    grid_barrier(cx.barrier, ++epoch * gridDim.x);
+                }
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[cx.T + 1] = global_timer_ns();
 }
@@ -34,6 +45,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
     stage_tables(cx, sm);
     day_pass(cx, sm, t);
+}
+
+// contact tracing of day t as its own launch (per-day launch mode)
+__global__ void __launch_bounds__(kThreads, kMinBlocks) seir_trace_kernel(const __grid_constant__ DevCtx cx, int t)
+{
+    trace_pass(cx, *reinterpret_cast<TraceSmem *>(seir_smem_raw), t);
 }
 
 // winner := 0, inbox := 0 (the only per-run state that must be cleared; records are built on infection)
@@ -47,6 +64,14 @@ __global__ void seir_init_state_kernel(DevCtx cx)
         uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + g * kVec);
 #pragma unroll
         for (int k = 0; k < 8; ++k) __stcs(wz + k, z);
+        if (cx.tmark) {  // tracing state: visit marks and log heads
+            uint4 *tz = reinterpret_cast<uint4 *>(cx.tmark + g * kVec);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) __stcs(tz + k, z);
+            uint4 *hz = reinterpret_cast<uint4 *>(cx.log_head + g * kVec);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) __stcs(hz + k, z);
+        }
     }
 }
 
@@ -83,9 +108,9 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
 // is a handful of branch-free compares dropped into a 512 B shared tile, and every row leaves the warp as
 // full 16 B vector stores.
 constexpr int kMatWarps = 8, kMatThreads = kMatWarps * 32, kMatPerLane = 4;
-struct MatAgent { uint32_t a, b, c, d; };  // t_exp|t_inf<<16, t_sev|t_crit<<16, t_end|t_q_on<<16, t_doc|final<<16|local<<20
+struct MatAgent { uint32_t a, b, c, d, e; };  // t_exp|t_inf<<16, t_sev|t_crit<<16, t_end|t_q_on<<16, t_doc|final<<16|local<<20, t_q2
 
-__device__ __forceinline__ MatAgent mat_pack(const AgentRec &r, int local)
+__device__ __forceinline__ MatAgent mat_pack(const AgentRec &r, int local, const uint32_t *trc_of_agent)
 {
     const uint32_t fl = r.flags();
     const uint32_t t_exp = r.t_exposed();
@@ -98,6 +123,7 @@ __device__ __forceinline__ MatAgent mat_pack(const AgentRec &r, int local)
     m.b = t_sev | (t_cri << 16);
     m.c = (uint32_t)r.t_end() | ((uint32_t)r.t_q_on() << 16);
     m.d = t_doc | ((uint32_t)(r.state() & 7) << 16) | ((uint32_t)local << 20);
+    m.e = (fl & F_TRX) ? (__ldcg(trc_of_agent) & 0xFFFFu) : 0xFFFFu;  // first day of a traced Q after the end (:72-73)
     return m;
 }
 // packed state byte on day t (same function as state_on_day, on the packed thresholds)
@@ -105,7 +131,7 @@ __device__ __forceinline__ uint32_t mat_byte(const MatAgent &m, uint32_t t)
 {
     const uint32_t cnt = (t >= (m.a & 0xFFFFu)) + (t >= (m.a >> 16)) + (t >= (m.b & 0xFFFFu)) + (t >= (m.b >> 16));
     const bool ended = t >= (m.c & 0xFFFFu);
-    const uint32_t q = (t >= (m.c >> 16)) && !ended;
+    const uint32_t q = ((t >= (m.c >> 16)) && !ended) || t >= m.e;
     const uint32_t doc = t >= (m.d & 0xFFFFu);
     const uint32_t comp = ended ? ((m.d >> 16) & 7u) : cnt;
     return comp | (q << 3) | (doc << 4);
@@ -155,11 +181,11 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
 #pragma unroll
         for (int k = 0; k < kMatPerLane; ++k) {
             const int e = lane + 32 * k;
-            ag[k].a = 0xFFFFFFFFu; ag[k].b = 0xFFFFFFFFu; ag[k].c = 0xFFFFFFFFu; ag[k].d = 0xFFFFu;
+            ag[k].a = 0xFFFFFFFFu; ag[k].b = 0xFFFFFFFFu; ag[k].c = 0xFFFFFFFFu; ag[k].d = 0xFFFFu; ag[k].e = 0xFFFFu;
             if (e < n_inf) {
                 const int local = list[e];
                 const AgentRec r = load_rec(rec + local);
-                ag[k] = mat_pack(r, local);
+                ag[k] = mat_pack(r, local, cx.trc + (size_t)rep * cx.n_pad + (g % groups_per_rep) * 512 + local);
                 t_first = min(t_first, (int)r.t_exposed());
             }
         }
@@ -186,7 +212,8 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
             const int local = list[e];
             const AgentRec r = load_rec(rec + local);
             const int64_t i = (g % groups_per_rep) * 512 + local;
-            for (int t = r.t_exposed(); t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t);
+            const int t_q2 = (r.flags() & F_TRX) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
+            for (int t = r.t_exposed(); t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t, t_q2);
         }
         __syncwarp();
     }
@@ -220,7 +247,15 @@ __global__ void seir_agent_vector_kernel(DevCtx cx, int rep, int which, double *
             const AgentRec r = rec[i];
             switch (which) {
                 case SEIR_VEC_NUM_INFECTED_BY: v = r.n_inf_by(); break;
-                case SEIR_VEC_TIME_DOCUMENTED: v = r.t_documented(); break;
+                case SEIR_VEC_TIME_DOCUMENTED: {  // :76, :85: every tracer visit rewrites time_documented
+                    uint32_t td = r.t_documented();
+                    if (r.flags() & F_TRX) {
+                        const uint32_t last = cx.trc[(size_t)rep * cx.n_pad + i] >> 16;
+                        if (last > td) td = last;
+                    }
+                    v = td;
+                    break;
+                }
                 case SEIR_VEC_TIME_TO_ACTIVATION: v = dec16(r.tt_activation()); break;
                 case SEIR_VEC_TIME_TO_DEATH: v = dec16(r.tt_death()); break;
                 case SEIR_VEC_TIME_TO_RECOVERY: v = dec16(r.tt_recovery()); break;
@@ -326,6 +361,12 @@ struct seir_handle {
     DevBuf<AgentRec> rec;
     DevBuf<uint64_t> seeds;
     DevBuf<unsigned int> barrier;
+    // contact tracing (allocated when the run can switch tracing on)
+    bool trace_alloc = false;
+    uint32_t log_cap = 0;
+    DevBuf<uint4> log_ent;
+    DevBuf<uint32_t> log_head, log_cnt, rootbits, rootsum, root_cnt, trc, tstack;
+    DevBuf<unsigned long long> tmark;
     double p_hh_scalar = 0.0;
     bool p_hh_uniform = true;
     DevCtx cx{};
@@ -370,15 +411,34 @@ static int check_params(const seir_params *p, int64_t n)
     if (p->T < 2 || p->T > 4000) return fail("seir_params.T must be in [2, 4000]");
     if (p->mode != SEIR_MODE_NATIVE && p->mode != SEIR_MODE_REPLAY) return fail("seir_params.mode is invalid");
     if (p->launch != SEIR_LAUNCH_PERSISTENT && p->launch != SEIR_LAUNCH_PER_DAY) return fail("seir_params.launch is invalid");
-    if (p->tracing_enabled && p->t_tracing_start >= 1 && p->t_tracing_start < p->T)
-        return fail("contact tracing would switch on at t_tracing_start < T: device tracing is not implemented "
-                    "(pass t_tracing_start >= T, or tracing_enabled = 0)");
+    if (p->tracing_enabled && p->t_tracing_start >= 1 && p->t_tracing_start < p->T) {
+        if (!(p->p_trace_household >= 0.0) || !(p->p_trace_outside >= 0.0))
+            return fail("p_trace_household / p_trace_outside must be >= 0");
+        if (n >= (1ll << 31)) return fail("contact tracing supports populations below 2^31 agents");
+    }
     return 0;
 }
+
+static bool tracing_can_start(const seir_params &p) { return p.tracing_enabled && p.t_tracing_start >= 1 && p.t_tracing_start < p.T; }
 
 static int alloc_state(seir_handle *h)
 {
     const size_t R = (size_t)h->n_rep, np = (size_t)h->n_pad, T = (size_t)h->prm.T;
+    if (tracing_can_start(h->prm)) {
+        // every outside infection is logged once per hitter (:387); same-day multiple hits make a few % more
+        // entries than infections
+        h->log_cap = (uint32_t)(np + np / 4 + 1024);
+        CK(h->log_ent.alloc(R * h->log_cap));
+        CK(h->log_head.alloc(R * np));
+        CK(h->log_cnt.alloc(R));
+        CK(h->rootbits.alloc(R * np / 32));
+        CK(h->rootsum.alloc(R * np / 1024));
+        CK(h->root_cnt.alloc(R * (T + 2)));
+        CK(h->tmark.alloc(R * np));
+        CK(h->trc.alloc(R * np));
+        CK(h->tstack.alloc(R * np));
+        h->trace_alloc = true;
+    }
     CK(h->hist.alloc(R * T * np));
     CK(h->tally.alloc(R * T * TAL_ROWS * kAges));
     CK(h->list_cnt.alloc(R * 2 * (T + 2)));
@@ -411,6 +471,13 @@ static void fill_ctx(seir_handle *h)
     c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
     c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
+    const bool tr = tracing_can_start(p) && h->trace_alloc;
+    c.trace_from = tr ? p.t_tracing_start : 0;
+    c.p_trace_hh = p.p_trace_household; c.p_trace_out = p.p_trace_outside;
+    c.log_ent = tr ? h->log_ent.p : nullptr; c.log_head = tr ? h->log_head.p : nullptr; c.log_cnt = tr ? h->log_cnt.p : nullptr;
+    c.log_cap = tr ? h->log_cap : 0u;
+    c.rootbits = tr ? h->rootbits.p : nullptr; c.rootsum = tr ? h->rootsum.p : nullptr; c.root_cnt = tr ? h->root_cnt.p : nullptr;
+    c.tmark = tr ? h->tmark.p : nullptr; c.trc = tr ? h->trc.p : nullptr; c.tstack = tr ? h->tstack.p : nullptr;
     c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
     c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
     c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
@@ -566,7 +633,7 @@ int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables
     if (params) {
         if (check_params(params, h->n)) return 1;
         h->prm = *params;
-        if (params->T > h->T_alloc && alloc_state(h)) return 1;
+        if ((params->T > h->T_alloc || (tracing_can_start(*params) && !h->trace_alloc)) && alloc_state(h)) return 1;
     }
     if (tables && upload_tables(h, tables)) return 1;
     fill_ctx(h);
@@ -619,6 +686,13 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaMemsetAsync(h->counters.p, 0, (size_t)R * 4 * 8, h->stream));
     CK(cudaMemsetAsync(h->barrier.p, 0, 4, h->stream));
     CK(cudaMemsetAsync(h->list_cnt.p, 0, (size_t)R * 2 * (h->prm.T + 2) * 4, h->stream));
+    const bool tracing = h->cx.trace_from >= 1;
+    if (tracing) {
+        CK(cudaMemsetAsync(h->log_cnt.p, 0, (size_t)R * 4, h->stream));
+        CK(cudaMemsetAsync(h->root_cnt.p, 0, (size_t)R * (h->prm.T + 2) * 4, h->stream));
+        CK(cudaMemsetAsync(h->rootbits.p, 0, (size_t)R * h->n_pad / 32 * 4, h->stream));
+        CK(cudaMemsetAsync(h->rootsum.p, 0, (size_t)R * h->n_pad / 1024 * 4, h->stream));
+    }
     seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
     ++h->launches;
     if (!ids.empty()) {
@@ -636,6 +710,10 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         for (int t = 1; t <= h->prm.T; ++t) {
             seir_day_kernel<<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
             ++h->launches;
+            if (tracing && t >= h->cx.trace_from && t < h->prm.T) {
+                seir_trace_kernel<<<R < h->grid ? R : h->grid, 32, sizeof(TraceSmem), h->stream>>>(h->cx, t);
+                ++h->launches;
+            }
         }
         CK(cudaGetLastError());
     }
@@ -648,6 +726,14 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaEventElapsedTime(&h->loop_ms, h->ev1, h->ev2));
     CK(cudaEventElapsedTime(&h->mat_ms, h->ev2, h->ev3));
     CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev3));
+    if (tracing) {
+        std::vector<unsigned long long> c((size_t)R * 4);
+        CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < R; ++r) {
+            if (c[(size_t)r * 4] & 1ull) return fail("contact tracing: the outside-infection log overflowed (more hits than 1.25 n)");
+            if (c[(size_t)r * 4] & 2ull) return fail("contact tracing: the tracer's stack overflowed");
+        }
+    }
     return 0;
 }
 
@@ -678,7 +764,7 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
     std::vector<uint32_t> raw(per);
     CK(cudaMemcpy(raw.data(), h->tally.p + (size_t)replica * per, per * 4, cudaMemcpyDeviceToHost));
     // planes in the order of seir_individual.py:392: S,E,Mild,Documented,Severe,Critical,R,D,Q
-    std::vector<int64_t> cumE(kAges, 0), cumR(kAges, 0), cumD(kAges, 0), cumDoc(kAges, 0);
+    std::vector<int64_t> cumE(kAges, 0), cumR(kAges, 0), cumD(kAges, 0), cumDoc(kAges, 0), cumQ2(kAges, 0);
     for (int t = 0; t < T; ++t) {
         const uint32_t *d = raw.data() + (size_t)t * TAL_ROWS * kAges;
         int64_t *o = out + (size_t)t * SEIR_N_TALLY * kAges;
@@ -687,6 +773,7 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
             cumR[a] += d[TAL_NEW_R * kAges + a];
             cumD[a] += d[TAL_NEW_D * kAges + a];
             cumDoc[a] += d[TAL_NEW_DOC * kAges + a];
+            cumQ2[a] += d[TAL_NEW_Q2 * kAges + a];
             o[0 * kAges + a] = h->group_sizes[a] - cumE[a];
             o[1 * kAges + a] = d[TAL_E * kAges + a];
             o[2 * kAges + a] = d[TAL_MILD * kAges + a];
@@ -695,7 +782,7 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
             o[5 * kAges + a] = d[TAL_CRIT * kAges + a];
             o[6 * kAges + a] = cumR[a];
             o[7 * kAges + a] = cumD[a];
-            o[8 * kAges + a] = d[TAL_QACT * kAges + a];
+            o[8 * kAges + a] = d[TAL_QACT * kAges + a] + cumQ2[a];
         }
     }
     return 0;
@@ -801,6 +888,8 @@ void seir_destroy(seir_handle *h)
     h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
     h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release();
     h->list_old.release(); h->list_new.release(); h->list_cnt.release(); h->day_ns.release();
+    h->log_ent.release(); h->log_head.release(); h->log_cnt.release(); h->rootbits.release(); h->rootsum.release();
+    h->root_cnt.release(); h->tmark.release(); h->trc.release(); h->tstack.release();
     h->alias_idx.release(); h->stage_ns.release(); h->fine_ns.release();
     if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -46,13 +46,20 @@ constexpr int kPad = 4096;               // row stride is a multiple of this man
 constexpr int kOutCap = 3 * kThreads;    // per-CTA staging of list appends
 
 // device tally rows (per day, per age)
-enum { TAL_E = 0, TAL_MILD, TAL_SEV, TAL_CRIT, TAL_QACT, TAL_NEW_E, TAL_NEW_R, TAL_NEW_D, TAL_NEW_DOC, TAL_ROWS };
+enum { TAL_E = 0, TAL_MILD, TAL_SEV, TAL_CRIT, TAL_QACT, TAL_NEW_E, TAL_NEW_R, TAL_NEW_D, TAL_NEW_DOC,
+       TAL_NEW_Q2,  // recovered / dead agents quarantined by a tracer (:72-76 traces every non-S contact)
+       TAL_ROWS };
 constexpr int kTalLagRows = TAL_NEW_E + 1;  // rows [0, kTalLagRows) describe day t-1, the rest day t
 
 // compartments (bits 0-2 of the state byte)
 enum { C_S = 0, C_E = 1, C_MILD = 2, C_SEV = 3, C_CRIT = 4, C_R = 5, C_D = 6 };
 constexpr uint8_t ST_Q = 0x08, ST_DOC = 0x10;
 constexpr uint8_t F_MILD = 1, F_SEV = 2, F_CRIT = 4;  // stages the agent has reached
+constexpr uint8_t F_TRX = 8;                          // trc[agent] is valid (the agent was reached by a tracer)
+// winner word: bit 63 = "reached by a tracer on its infection day" (the agent has no record yet that day)
+constexpr unsigned long long W_TRACED = 1ull << 63;
+__host__ __device__ __forceinline__ int wday(unsigned long long w) { return (int)((w >> 48) & 0x7FFFu); }
+constexpr int kLogWidth = 100;  // width of the reference's infected_by log (:197)
 constexpr uint16_t NEVER = 0xFFFFu;
 
 // 32 B per-agent record.  Derived days: t_infected = t_exposed + tt_activation (F_MILD),
@@ -143,6 +150,19 @@ struct DevCtx {
     unsigned long long *day_ns;    // [T+2] %globaltimer at the start of pass t (CTA 0), [T+1] = end of the loop
     unsigned long long *fine_ns;   // [T+2][16] debug stamps inside stage A (only with -DSEIR_FINE_STAMPS)
     unsigned long long *stage_ns;  // [T+2][8] CTA 0, first round of pass t: stamps after init / A / C / H / W / flush / end
+    // contact tracing (:60-88); all null / 0 when tracing can never switch on
+    int trace_from;                // first day with contact_tracing == True (:241-242), 0 = never
+    double p_trace_hh, p_trace_out;
+    uint4 *log_ent;                // [rep][log_cap] outside-infection log: infectee, next entry + 1, day<<16 | ordinal, -
+    uint32_t *log_head;            // [rep][n_pad]   most recent entry + 1 of the infector (0 = none)
+    uint32_t *log_cnt;             // [rep]
+    uint32_t log_cap;
+    uint32_t *rootbits;            // [rep][n_pad/32]   agents documented today by their own progression (tracing roots)
+    uint32_t *rootsum;             // [rep][n_pad/1024] bit w set = rootbits word w non-zero
+    uint32_t *root_cnt;            // [rep][T+2] roots of day t
+    unsigned long long *tmark;     // [rep][n_pad] day<<32 | root + 1 of the last tracer visit
+    uint32_t *trc;                 // [rep][n_pad] first post-end traced-Q day | last traced day<<16 (valid with F_TRX)
+    uint32_t *tstack;              // [rep][n_pad] DFS stack of the tracing warp
     // scalars
     int t_lockdown, t_stayhome;
     double p_doc, p_contact, asym;
@@ -277,6 +297,8 @@ struct RepView {
     uint64_t seed;
     bool home_on;
     int phase;
+    int rep;
+    bool tracing;                           // contact_tracing is True today (:241-242)
 };
 
 // draw-queue items: slot<<16 | kind<<14 | payload
@@ -350,7 +372,7 @@ __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_
     const unsigned long long old = atomicMax(v.winner + c, key);
     const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
     uint32_t bits = 0;
-    if ((int)(old >> 48) != t) {  // first hit of c today: announce it, queue it for tomorrow
+    if (wday(old) != t) {  // first hit of c today: announce it, queue it for tomorrow
         bits = inbox_infected_bit((int)(c & 15));
         const uint32_t pos = atomicAdd(&sm.n_new, 1u);
         if (pos < (uint32_t)kOutNew) sm.out_new[pos] = c;
@@ -359,6 +381,15 @@ __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_
     if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
     if (bits) atomicOr(v.inbox + (c >> 4), bits);
     atomicAdd(&sm.hit_n[slot], ord >= 16u ? 0x10001u : 1u);  // ord >= 16: community (:386-388)
+    if (cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387); k follows from (day, ordinal) when the log is read
+        const uint32_t e = atomicAdd(cx.log_cnt + v.rep, 1u);
+        if (e < cx.log_cap) {
+            const uint32_t prev = atomicExch(cx.log_head + (size_t)v.rep * cx.n_pad + i, e + 1u);
+            __stcg(cx.log_ent + (size_t)v.rep * cx.log_cap + e, make_uint4(c, prev, ((uint32_t)t << 16) | ord, 0u));
+        } else {
+            atomicOr(&cx.counters[v.rep * 4 + 0], 1ull);  // log overflow: seir_run reports it
+        }
+    }
 }
 
 __device__ __forceinline__ void push_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
@@ -408,7 +439,7 @@ __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uin
     if (glen == 0) return;
     const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
     const unsigned long long w = __ldcg(v.winner + c);
-    if ((w == 0ull || (int)(w >> 48) == t) && !at_home(v, c))  // :375
+    if ((w == 0ull || wday(w) == t) && !at_home(v, c))  // :375
         push_hit(cx, sm, c, (slot << 16) | ord, a, t);
 }
 
@@ -490,12 +521,16 @@ __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm,
     r.set_stat(stt);
     r.set_state(C_E);
     if (ib & inbox_q_bit((int)(i & 15))) { r.set_state(r.state() | ST_Q); r.set_t_q_on((uint16_t)tx); }
+    if (w & W_TRACED) {  // a tracer reached the agent on the day it was infected (:83-87): Documented, Q (inbox bit), traced
+        r.set_state(r.state() | ST_DOC);
+        r.set_t_documented((uint16_t)tx);
+    }
     atomicAdd(&sm.tally[TAL_NEW_E * kAges + (stt & 127)], 1u);
 }
 
 // the progression events of the agent's own day (:256-272, :291-311, :312-321)
 __device__ __forceinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
-                                                AgentRec &r, int comp, int &ncomp, bool &nq, bool &ndoc)
+                                                AgentRec &r, int comp, int &ncomp, bool &nq, bool &ndoc, bool &root)
 {
     const uint16_t stt = r.stat();
     const int age = stt & 127;
@@ -517,8 +552,9 @@ __device__ __forceinline__ void progression_events(const DevCtx &cx, const PassS
     } else if (comp == C_MILD) {  // :291-311 Mild -> Severe
         ncomp = C_SEV;
         r.set_flags(r.flags() | F_SEV);
-        if (!ndoc) {
+        if (!ndoc) {  // :295-303 severe cases are always documented (and start a trace)
             ndoc = true;
+            root = true;
             r.set_t_documented((uint16_t)t);
         }
         nq = true;
@@ -564,6 +600,7 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
     int ncomp = comp;
     bool nq = Qp, ndoc = Dp;
     bool transmit = !Qp;
+    bool root = false;  // newly documented today by its own progression: the root of a trace (:284-289, :298-303)
     bool have_db = false;
     sd_block db;
     db.w[0] = db.w[1] = db.w[2] = db.w[3] = 0u;
@@ -586,11 +623,13 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
             have_db = true;
             if (sd_lane(db, 0) < cx.p_doc) {
                 ndoc = true;
+                root = true;
+                if (v.tracing) nq = true;  // :287-288
                 r.set_t_documented((uint16_t)t);
             }
         }
         if (IN_EV && ev) {
-            progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc);
+            progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc, root);
             dirty = true;
         } else if (Cp && due(t, t_critical_of(r), r.tt_death())) {  // :323-327
             ncomp = C_D;
@@ -598,6 +637,11 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
             atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], 1u);
         }
         if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], 1u);
+        if (root && v.tracing) {
+            atomicOr(cx.rootbits + (size_t)v.rep * (cx.n_pad / 32) + (i >> 5), 1u << (i & 31));
+            atomicOr(cx.rootsum + (size_t)v.rep * (cx.n_pad / 1024) + (i >> 10), 1u << ((i >> 5) & 31));
+            atomicAdd(cx.root_cnt + (size_t)v.rep * (cx.T + 2) + t, 1u);
+        }
     }
     // :328-337 isolation entry (time_to_isolate may just have been redrawn at :270)
     if (transmit) {
@@ -623,7 +667,7 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
         for (int j = 0; j < 7; ++j) {  // independent loads: one round trip for the household
             if (j < size - 1) {
                 const unsigned long long w = __ldcg(v.winner + base + j + (j >= pos ? 1 : 0));
-                if (w == 0ull || (int)(w >> 48) == t) smask |= 1u << j;  // S[t-1,c] (:346)
+                if (w == 0ull || wday(w) == t) smask |= 1u << j;  // S[t-1,c] (:346)
             }
         }
         // ---- community push :361-390: the first Knuth uniform of the kept-contact count is lane 1 of the day block
@@ -721,6 +765,8 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             sm.v.seed = cx.seeds[rep];
             sm.v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;          // :243-244
             sm.v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
+            sm.v.rep = rep;
+            sm.v.tracing = cx.trace_from >= 1 && t >= cx.trace_from;          // :241-242
         }
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
         const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t);
@@ -902,6 +948,212 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Contact tracing of day t (do_contact_tracing, seir_individual.py:60-88), after the day's transmission is
+// complete.  The reference resolves the day's traces INSIDE its sequential agent loop, so what a trace
+// sees depends on the agent order: (a) the tracer of root r sees the day-t entries of infected_by[c]
+// only for c < r (c's iteration has run), (b) a contact that recovers or dies today keeps the tracer's
+// Q[t,c] = True only if the tracer's root comes after it (r > c), (c) a household edge is followed only
+// by the first tracer that reaches the member (`traced`).  To keep all of that exact, ONE warp per replica
+// walks the day's roots in ascending agent order (two-level bitmap) and runs each root's search with an
+// explicit stack; its 32 lanes evaluate the edges of the node being expanded (household members and log
+// entries) in parallel.  Every draw is keyed on (tracer, day, site, edge slot), so re-expansions by later
+// roots -- which the reference performs, its outside edges have no `traced` guard -- repeat the same draws.
+struct TraceView {
+    int rep, t;
+    uint32_t root;
+    uint64_t seed;
+    unsigned long long *winner;
+    uint32_t *inbox;
+    AgentRec *rec;
+    uint32_t *trc;
+    unsigned long long *tmark;
+    uint32_t *tally_day;  // tally rows of day t
+};
+
+__device__ __forceinline__ unsigned long long tkey(int t, uint32_t root) { return ((unsigned long long)t << 32) | ((unsigned long long)root + 1ull); }
+
+// Q[t,x] = Documented[t,x] = traced[x] = True, time_documented[x] = t  (:73-76, :84-87), by ONE lane
+__device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, uint32_t x)
+{
+    const int t = tv.t;
+    const int age = __ldg(cx.stat + x) & 127;
+    const unsigned long long w = __ldcg(tv.winner + x);
+    if (wday(w) == t) {  // infected today: no record before tomorrow's pass; the marks travel in winner / inbox
+        const unsigned long long old = atomicOr(tv.winner + x, W_TRACED);
+        atomicOr(tv.inbox + (x >> 4), inbox_q_bit((int)(x & 15)));
+        if (!(old & W_TRACED)) atomicAdd(tv.tally_day + TAL_NEW_DOC * kAges + age, 1u);
+        return;
+    }
+    AgentRec r = load_rec(tv.rec + x);
+    uint32_t st = r.state();
+    const uint32_t fl = r.flags();
+    const int comp = (int)(st & 7u);
+    uint32_t tw = (fl & F_TRX) ? __ldcg(tv.trc + x) : (uint32_t)NEVER;  // t_q2 | t_doc_last << 16
+    if (!(st & ST_DOC)) {
+        st |= ST_DOC;
+        r.set_t_documented((uint16_t)t);
+        atomicAdd(tv.tally_day + TAL_NEW_DOC * kAges + age, 1u);
+    }
+    if (comp == C_R || comp == C_D) {
+        // the agent's own iteration cleared Q[t,x] if it ended today (:278, :326); the tracer's write stays
+        // only if the tracer's root is iterated later (root > x)
+        const bool sticks = (int)r.t_end() != t || tv.root > x;
+        if (sticks && (tw & 0xFFFFu) == (uint32_t)NEVER) {
+            tw = (tw & 0xFFFF0000u) | (uint32_t)t;
+            st |= ST_Q;
+            atomicAdd(tv.tally_day + TAL_NEW_Q2 * kAges + age, 1u);
+        }
+    } else if (!(st & ST_Q)) {
+        st |= ST_Q;
+        if (r.t_q_on() == NEVER) r.set_t_q_on((uint16_t)t);
+    }
+    tw = (tw & 0xFFFFu) | ((uint32_t)t << 16);
+    r.set_state(st);
+    r.set_flags(fl | F_TRX);
+    store_rec(tv.rec + x, r);
+    __stcg(tv.trc + x, tw);
+}
+
+constexpr int kTraceLogCap = 512;  // log entries of one agent staged in shared memory (the reference keeps 100)
+struct TraceSmem {
+    uint32_t ent_x[kTraceLogCap];
+    uint32_t ent_key[kTraceLogCap];  // day<<16 | ordinal: the order of infected_by[c, :]
+};
+
+// one root: warp-cooperative search.  Returns false on stack overflow.
+__device__ __forceinline__ bool trace_root(const DevCtx &cx, const TraceView &tv, TraceSmem &ts, uint32_t *stack, uint32_t cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = tv.t;
+    const uint32_t root = tv.root;
+    const unsigned long long key = tkey(t, root);
+    const uint32_t *log_head = cx.log_head + (size_t)tv.rep * cx.n_pad;
+    const uint4 *log_ent = cx.log_ent + (size_t)tv.rep * cx.log_cap;
+    if (lane == 0) {
+        __stcg(tv.tmark + root, key);
+        __stcg(stack, root);
+    }
+    __syncwarp();
+    uint32_t sp = 1;
+    bool ok_all = true;
+    while (sp > 0) {
+        const uint32_t c = __ldcg(stack + (sp - 1));
+        --sp;
+        const uint16_t stt = __ldg(cx.stat + c);
+        const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
+        const uint32_t base = c - (uint32_t)pos;
+        // ---- infected_by[c, :]: walk the list (lane 0), newest entry first
+        uint32_t L = 0;
+        if (lane == 0) {
+            uint32_t e = __ldcg(log_head + c);
+            while (e != 0u && L < (uint32_t)kTraceLogCap) {
+                const uint4 en = __ldcg(log_ent + (e - 1u));
+                ts.ent_x[L] = en.x;
+                ts.ent_key[L] = en.z;
+                ++L;
+                e = en.y;
+            }
+        }
+        L = __shfl_sync(0xFFFFFFFFu, L, 0);
+        __syncwarp();
+        const uint32_t n_edges = (uint32_t)(size - 1) + L;
+        for (uint32_t e0 = 0; e0 < n_edges; e0 += 32u) {
+            const uint32_t e = e0 + (uint32_t)lane;
+            bool ok = false;
+            uint32_t target = 0;
+            if (e < (uint32_t)(size - 1)) {  // household edge j (:68-77)
+                const int j = (int)e;
+                target = base + (uint32_t)j + (j >= pos ? 1u : 0u);
+                const unsigned long long w = __ldcg(tv.winner + target);
+                if (w != 0ull && wday(w) != t) {  // not S[t-1, contact]
+                    // traced[contact]: documented before today, or by its own iteration today if that came first
+                    // (contact <= root), or reached by a tracer today
+                    const AgentRec m = load_rec(tv.rec + target);
+                    bool traced = (m.state() & ST_DOC) != 0;
+                    if (traced && (int)m.t_documented() == t && target > root &&
+                        (int)(__ldcg(tv.tmark + target) >> 32) != t)
+                        traced = false;
+                    if (!traced) ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_HH, (uint32_t)j), 0) < cx.p_trace_hh;
+                }
+            } else if (e < n_edges) {  // outside edge (:79-88); slot = rank of the entry in (day, ordinal) order
+                const uint32_t k = e - (uint32_t)(size - 1);
+                const uint32_t kk = ts.ent_key[k];
+                uint32_t rank = 0;
+                for (uint32_t q = 0; q < L; ++q) rank += ts.ent_key[q] < kk ? 1u : 0u;
+                target = ts.ent_x[k];
+                // today's entries exist only if c's iteration has run before the root's (c < root)
+                if (rank < (uint32_t)kLogWidth && ((int)(kk >> 16) < t || c < root))
+                    ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_OUT, rank), 0) < cx.p_trace_out;
+            }
+            if (ok) {
+                const unsigned long long old = atomicExch(tv.tmark + target, key);
+                if (old == key) ok = false;  // already expanded under this root
+                else trace_mark(cx, tv, target);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok) {
+                const uint32_t at = sp + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (at < cap) __stcg(stack + at, target);
+            }
+            sp += (uint32_t)__popc(m);
+            if (sp > cap) { ok_all = false; sp = cap; }
+            __syncwarp();
+        }
+    }
+    return ok_all;
+}
+
+// all roots of day t of the replicas this CTA serves (warp 0 only; no block-wide synchronisation inside)
+__device__ void trace_pass(const DevCtx &cx, TraceSmem &ts, int t)
+{
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    for (int rep = blockIdx.x; rep < cx.n_rep; rep += gridDim.x) {
+        if (__ldcg(cx.root_cnt + (size_t)rep * (cx.T + 2) + t) == 0u) continue;
+        TraceView tv;
+        tv.rep = rep; tv.t = t; tv.root = 0;
+        tv.seed = cx.seeds[rep];
+        tv.winner = cx.winner + (size_t)rep * cx.n_pad;
+        tv.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+        tv.rec = cx.rec + (size_t)rep * cx.n_pad;
+        tv.trc = cx.trc + (size_t)rep * cx.n_pad;
+        tv.tmark = cx.tmark + (size_t)rep * cx.n_pad;
+        tv.tally_day = cx.tally + ((size_t)rep * cx.T + t) * TAL_ROWS * kAges;
+        uint32_t *bits = cx.rootbits + (size_t)rep * (cx.n_pad / 32);
+        uint32_t *sums = cx.rootsum + (size_t)rep * (cx.n_pad / 1024);
+        uint32_t *stack = cx.tstack + (size_t)rep * cx.n_pad;
+        const uint32_t n_sum = (uint32_t)(cx.n_pad / 1024);
+        bool ok = true;
+        for (uint32_t s0 = 0; s0 < n_sum; s0 += 32u) {  // roots in ascending agent order
+            const uint32_t si = s0 + (uint32_t)lane;
+            const uint32_t sw = si < n_sum ? __ldcg(sums + si) : 0u;
+            unsigned any = __ballot_sync(0xFFFFFFFFu, sw != 0u);
+            while (any) {
+                const int src = __ffs(any) - 1;
+                any &= any - 1u;
+                uint32_t sword = __shfl_sync(0xFFFFFFFFu, sw, src);
+                const uint32_t sidx = s0 + (uint32_t)src;
+                while (sword) {
+                    const int wb = __ffs(sword) - 1;
+                    sword &= sword - 1u;
+                    const uint32_t widx = sidx * 32u + (uint32_t)wb;
+                    uint32_t word = __ldcg(bits + widx);
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1u;
+                        tv.root = widx * 32u + (uint32_t)b;
+                        ok = trace_root(cx, tv, ts, stack, (uint32_t)cx.n_pad) && ok;
+                    }
+                    if (lane == 0) __stcg(bits + widx, 0u);
+                }
+                if (lane == 0) __stcg(sums + sidx, 0u);
+            }
+        }
+        if (!ok && lane == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull);  // stack overflow: seir_run reports it
+    }
+}
+
 // grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency)
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
 {
@@ -920,7 +1172,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 
 // ---------------------------------------------------------------------------------------
 // packed state byte of an ever-infected agent on day t, from its record
-__device__ __forceinline__ uint8_t state_on_day(const AgentRec &r, int t)
+__device__ __forceinline__ uint8_t state_on_day(const AgentRec &r, int t, int t_q2 = 0xFFFF)
 {
     if (t < (int)r.t_exposed()) return C_S;
     const bool ended = r.t_end() != NEVER && t >= (int)r.t_end();
@@ -931,7 +1183,7 @@ __device__ __forceinline__ uint8_t state_on_day(const AgentRec &r, int t)
     else if ((r.flags() & F_MILD) && t >= t_infected_of(r)) comp = C_MILD;
     else comp = C_E;
     uint8_t s = (uint8_t)comp;
-    if (r.t_q_on() != NEVER && t >= (int)r.t_q_on() && !ended) s |= ST_Q;
+    if ((r.t_q_on() != NEVER && t >= (int)r.t_q_on() && !ended) || t >= t_q2) s |= ST_Q;
     if (r.t_documented() != 0 && t >= (int)r.t_documented()) s |= ST_DOC;
     return s;
 }

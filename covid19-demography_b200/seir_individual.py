@@ -12,9 +12,10 @@ Differences a caller can see (DESIGN.md has the full list):
   * draws inside the day loop are keyed Philox draws (include/seir_draws.h), not the reference's
     single Mersenne-Twister stream, so trajectories agree with the reference in distribution,
     not per seed; Home_real and initial_infected ARE the reference's for the same seed;
-  * contact tracing on the device is not implemented yet: a run in which the reference, as
-    compiled, would switch tracing on (1 <= t_tracing_start < T) raises
-    unless `SEIR_B200_TRACING=off` (or tracing="off") is given, which runs the paper's
+  * contact tracing (`do_contact_tracing`, :60-88) runs on the device with the reference's sequential
+    semantics.  As compiled by numba 0.65 the reference switches tracing on at t_tracing_start
+    whatever params['contact_tracing'] says; that is the default here too
+    (tracing="as_reference").  `SEIR_B200_TRACING=off` (or tracing="off") runs the paper's
     no-tracing semantics.
 """
 import os

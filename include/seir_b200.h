@@ -37,9 +37,9 @@ typedef struct {
     int32_t t_lockdown;        /* params['t_lockdown']                          :149 */
     int32_t t_stayhome_start;  /* params['t_stayhome_start']                    :158 */
     int32_t t_tracing_start;   /* params['t_tracing_start']                     :157 */
-    int32_t tracing_enabled;   /* value of `tracing_enabled` at :241 (the reference as compiled: 1).
-                                  Tracing on device is not implemented yet: seir_run refuses runs in
-                                  which tracing would switch on (tracing_enabled && 1 <= t_tracing_start < T) */
+    int32_t tracing_enabled;   /* value of `tracing_enabled` at :241 (the reference as compiled: 1; 0 = the paper's
+                                  no-tracing semantics).  When tracing_enabled && 1 <= t_tracing_start < T,
+                                  do_contact_tracing (:60-88) runs on the device from day t_tracing_start */
     int32_t mode;              /* SEIR_MODE_*                                         */
     int32_t launch;            /* SEIR_LAUNCH_*                                       */
     int32_t reserved0;
@@ -54,7 +54,7 @@ typedef struct {
     double mean_time_to_death;            /* :137 */
     double time_to_activation_mean;       /* :135 */
     double time_to_activation_std;        /* :136 */
-    double p_trace_household;             /* :156 (unused until tracing lands) */
+    double p_trace_household;             /* :156 */
     double p_trace_outside;               /* :155 */
 } seir_params;
 

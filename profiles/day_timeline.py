@@ -10,6 +10,8 @@ from covid19_demography_b200 import engine, population, tables
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 p, tabs = bench.workload_params(n, 60)
+if os.environ.get("TRACING"):  # the reference as compiled: tracing switches on at day 37 (run_simulation.py:115-116)
+    p["t_tracing_start"] = float(os.environ["TRACING"])
 hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
 tb = tables.build_tables(tabs["contact_matrix"], np.array([len(g) for g in groups]), tables.params_to_dict(p),
                          tabs["mean_time_to_isolate_factor"], tabs["p_mild_severe"], tabs["p_severe_critical"],

@@ -101,11 +101,48 @@ def test_draw_contract_on_device(gpu_engine_module):
     assert np.isfinite(e).all() and e.mean() == pytest.approx(4.6, rel=0.02)
 
 
-def test_tracing_is_refused_loudly(gpu_engine_module):
-    c = util.Case("italy_default")
-    with pytest.raises((RuntimeError, ValueError), match="tracing"):
-        c.gpu_engine(gpu_engine_module, c.params, "native")  # t_tracing_start = 37 < T, tracing as compiled
-    eng = c.gpu_engine(gpu_engine_module, c.params, "native", tracing_enabled=0)  # the paper's semantics
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", ["native", "replay"])
+def test_gpu_equals_keyed_oracle_with_tracing_as_compiled(gpu_engine_module, name, mode):
+    """The fixtures' own parameters: as compiled, the reference switches contact tracing on at t_tracing_start
+    (day 37 of 60 for the Italy defaults, day 10 in italy_tracing).  do_contact_tracing
+    (seir_individual.py:60-88) on the device == the oracle's sequential recursion, bit for bit."""
+    c = util.Case(name)
+    params = dict(c.params)
+    T = int(params["T"])
+    tup, ex, home, init = c.keyed_oracle(mode, params)
+    tracing_ran = 1 <= params["t_tracing_start"] < T
+    util.check_invariants(tup, c.n, T, tracing_off=not tracing_ran)
+    eng = c.gpu_engine(gpu_engine_module, params, mode)
+    eng.run([c.seed], [home], [init])
+    _compare(eng, tup, ex, c, T)
+    eng.close()
+
+
+@pytest.mark.parametrize("launch", ["persistent", "per_day"])
+def test_tracing_with_replicas_and_launch_modes(gpu_engine_module, launch):
+    c = util.Case("italy_tracing")
+    params = dict(c.params)
+    seeds = [21, 22, 23]
+    runs = [c.keyed_oracle("native", params, seed=s) for s in seeds]
+    assert any(np.asarray(r[0][8])[-1][np.asarray(r[0][6])[-1] | np.asarray(r[0][7])[-1]].any() for r in runs), \
+        "the tracing fixture should quarantine some recovered/dead agents (SURVEY.md section 4)"
+    eng = c.gpu_engine(gpu_engine_module, params, "native", launch=launch, n_replicas=len(seeds))
+    eng.run(seeds, [r[2] for r in runs], [r[3] for r in runs])
+    for k, (tup, ex, _, _) in enumerate(runs):
+        _compare(eng, tup, ex, c, int(params["T"]), replica=k)
+    eng.close()
+
+
+def test_tracing_off_is_the_papers_semantics(gpu_engine_module):
+    """tracing_enabled = 0: `tracing_enabled` False at :241, whatever t_tracing_start says."""
+    c = util.Case("italy_tracing")
+    params = dict(c.params)
+    tup, ex, home, init = c.keyed_oracle("native", params, tracing_enabled=0)
+    util.check_invariants(tup, c.n, int(params["T"]), tracing_off=True)
+    eng = c.gpu_engine(gpu_engine_module, params, "native", tracing_enabled=0)
+    eng.run([c.seed], [home], [init])
+    _compare(eng, tup, ex, c, int(params["T"]))
     eng.close()
 
 
