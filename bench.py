@@ -113,6 +113,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(path))
+        return float(d[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -292,6 +302,7 @@ def run_gpu_arm(args):
     d2h = R * (T * 9 * 101 * 4)
 
     agent_days_step = float(n) * (T - 1) * R
+    loop_ms_local = loop_ms  # the roofline line describes rank 0's own kernel
     if dist is not None:
         import torch
         tt = torch.tensor([dev_ms, e2e_s, loop_ms], dtype=torch.float64, device="cuda:%d" % local)
@@ -303,7 +314,7 @@ def run_gpu_arm(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         balg, a_sum, i_sum = algorithmic_bytes(last_tal, n)
-        kern_s = loop_ms / args.steps / 1e3
+        kern_s = loop_ms_local / args.steps / 1e3
         achieved = balg * R / kern_s / 1e9
         line = {
             "metric": METRIC, "value": world * agent_days_step * args.steps / (dev_ms / 1e3), "unit": UNIT,
@@ -324,10 +335,13 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic, "kernel": "seir_persistent_kernel" if args.launch == "persistent" else "seir_day_kernel x T",
+                         "traffic": args.traffic if args.traffic is not None else measured_traffic("seir_persistent_kernel"),
+                         "kernel": "seir_persistent_kernel" if args.launch == "persistent" else "seir_day_kernel x T",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": balg * R,
                          "active_agent_days": a_sum, "infections": i_sum},
         }
+        if world == 1 and not args.no_tracing_leg:
+            line["config"]["as_reference_tracing"] = tracing_leg(engine, population, tables, args, n, T, local)
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample, T)
@@ -335,6 +349,29 @@ def run_gpu_arm(args):
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def tracing_leg(engine, population, tables, args, n, T, device):
+    """The same workload with the reference's own t_tracing_start = 37 (run_simulation.py:115-116): as
+    compiled the reference traces contacts from that day.  One warm-up + one timed run."""
+    p, tabs = workload_params(n, T)
+    p["t_tracing_start"] = 37.0
+    hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
+    tb = tables.build_tables(tabs["contact_matrix"], np.array([len(g) for g in groups]), tables.params_to_dict(p),
+                             tabs["mean_time_to_isolate_factor"], tabs["p_mild_severe"], tabs["p_severe_critical"],
+                             tabs["p_critical_death"], with_replay=(args.mode == "replay"))
+    eng = engine.Engine(p, hh, age, groups, diab, hyp, np.full(n, tabs["p_infect_household"]), tb, n_replicas=1,
+                        device=device, mode=args.mode, launch=args.launch)
+    rng = np.random.default_rng(7)
+    ms = []
+    for k in range(2):
+        init = [rng.choice(n, size=int(p["initial_infected_fraction"] * n), replace=False).astype(np.int64)]
+        eng.run([900 + k], None, init)
+        ms.append(eng.last_run_ms()[1])
+    tal = eng.tallies(0)
+    eng.close()
+    return {"t_tracing_start": 37, "ms_per_run": ms[-1], "agent_days_per_sec": float(n) * (T - 1) / (ms[-1] / 1e3),
+            "documented_at_end": int(tal[-1, 3].sum()), "deaths_at_end": int(tal[-1, 7].sum())}
 
 
 def main():
@@ -351,6 +388,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="agents per CPU run (0 = full C2 size if memory allows)")
     ap.add_argument("--cpu-workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tracing-leg", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from ncu (profiles/), if known")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

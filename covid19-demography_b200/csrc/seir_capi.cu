@@ -274,6 +274,26 @@ __global__ void seir_agent_vector_kernel(DevCtx cx, int rep, int which, double *
     }
 }
 
+// Exposure-day cohorts (the drivers' per-run statistics: run_simulation.py:448-453, parameter_sweep.py:572-600):
+// for every day d and age a, out[d][0][a] = agents exposed on day d, [1] = sum of their num_infected_by,
+// [2] = of them dead at the end (D[-1]), [3] = of them recovered at the end (R[-1]).
+__global__ void seir_cohort_kernel(DevCtx cx, int rep, unsigned long long *out)
+{
+    const uint32_t *inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+    const AgentRec *rec = cx.rec + (size_t)rep * cx.n_pad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cx.n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (!(inbox[i >> 4] & inbox_infected_bit((int)(i & 15)))) continue;
+        const AgentRec r = load_rec(rec + i);
+        const int d = r.t_exposed(), age = r.stat() & 127, comp = r.state() & 7;
+        if (d >= cx.T) continue;
+        unsigned long long *o = out + (size_t)d * 4 * kAges + age;
+        atomicAdd(o, 1ull);
+        if (r.n_inf_by()) atomicAdd(o + kAges, (unsigned long long)r.n_inf_by());
+        if (comp == C_D) atomicAdd(o + 2 * kAges, 1ull);
+        if (comp == C_R) atomicAdd(o + 3 * kAges, 1ull);
+    }
+}
+
 __global__ void seir_history_plane_kernel(const uint8_t *rows, int64_t n, int64_t n_pad, int n_rows, int which, uint8_t *out)
 {
     const int64_t total = (int64_t)n_rows * n;
@@ -799,6 +819,23 @@ int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out)
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, h->stage_d.p, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int seir_get_cohorts(seir_handle *h, int replica, int64_t *out)
+{
+    if (!h || !out) return fail("seir_get_cohorts: NULL argument");
+    if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    CK(cudaSetDevice(h->device));
+    const size_t cells = (size_t)h->prm.T * 4 * kAges;
+    DevBuf<unsigned long long> buf;
+    CK(buf.alloc(cells));
+    CK(cudaMemsetAsync(buf.p, 0, cells * 8, h->stream));
+    seir_cohort_kernel<<<h->sms * 4, 256, 0, h->stream>>>(h->cx, replica, buf.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, buf.p, cells * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    buf.release();
     return 0;
 }
 

@@ -1,0 +1,89 @@
+"""The per-run statistics the reference's drivers compute from run_model's outputs, derived from the
+device-side tallies instead of O(T * n) NumPy passes over the nine bool[T, n] histories.
+
+    tallies  int64[T, 9, 101]   per-day per-age compartment counts   (engine.Engine.tallies)
+    cohorts  int64[T, 4, 101]   per exposure day and age: exposed, sum num_infected_by, dead / recovered at the end
+                                                                      (engine.Engine.cohorts)
+
+Reference statements restated here: run_simulation.py:448-460, simulate_agepolicies.py:617-631,
+parameter_sweep.py:556-603.  Divisions by zero give nan exactly where NumPy gives nan/inf warnings
+in the reference (an empty cohort keeps the drivers' initial value, which the caller supplies).
+"""
+import numpy as np
+
+PLANES = ("S", "E", "Mild", "Documented", "Severe", "Critical", "R", "D", "Q")
+AGE_GROUPS_SWEEP = ((0, 14), (15, 24), (25, 39), (40, 69), (70, 100))  # parameter_sweep.py:538
+
+
+def per_time(tallies):
+    """{plane: X.sum(axis=1)} -- S_per_time ... Q_per_time (parameter_sweep.py:556-565)."""
+    t = np.asarray(tallies)
+    return {k: t[:, j, :].sum(axis=1) for j, k in enumerate(PLANES)}
+
+
+def _median_from_histogram(counts):
+    """np.median of the multiset {age a repeated counts[a] times}."""
+    c = np.asarray(counts, dtype=np.int64)
+    m = int(c.sum())
+    if m == 0:
+        return np.nan
+    cum = np.cumsum(c)
+    lo = int(np.searchsorted(cum, (m - 1) // 2 + 1))
+    hi = int(np.searchsorted(cum, m // 2 + 1))
+    return 0.5 * (lo + hi)
+
+
+def cohort_statistics(cohorts, fill=0.0):
+    """run_simulation.py:448-453: per exposure day t (rows with no exposure keep `fill`):
+    r_0_over_time, cfr_over_time, fraction_over_70_time, fraction_below_30_time, median_age_time."""
+    c = np.asarray(cohorts).astype(np.float64)
+    T = c.shape[0]
+    out = {k: np.full(T, fill, dtype=np.float64) for k in
+           ("r_0_over_time", "cfr_over_time", "fraction_over_70_time", "fraction_below_30_time", "median_age_time")}
+    for t in range(T):
+        m = c[t, 0].sum()
+        if m > 0:
+            out["r_0_over_time"][t] = c[t, 1].sum() / m
+            d, r = c[t, 2].sum(), c[t, 3].sum()
+            out["cfr_over_time"][t] = d / (d + r) if (d + r) > 0 else np.nan
+            out["fraction_over_70_time"][t] = c[t, 0, 70:].sum() / m
+            out["fraction_below_30_time"][t] = c[t, 0, :30].sum() / m
+            out["median_age_time"][t] = _median_from_histogram(cohorts[t][0])
+    return out
+
+
+def r0_total(cohorts, first=1, last=20):
+    """parameter_sweep.py:567: mean num_infected_by of the agents with 0 < time_exposed <= 20."""
+    c = np.asarray(cohorts)
+    m = c[first:last + 1, 0].sum()
+    return c[first:last + 1, 1].sum() / m if m > 0 else np.nan
+
+
+def totals(tallies, n):
+    """run_simulation.py:454-459: total_infections_time = n - S - E, total_documented_time, total_deaths_time,
+    dead_by_age (D[-1] by age)."""
+    t = np.asarray(tallies)
+    S, E = t[:, 0].sum(axis=1), t[:, 1].sum(axis=1)
+    return {"total_infections_time": n - S - E, "total_documented_time": t[:, 3].sum(axis=1),
+            "total_deaths_time": t[:, 7].sum(axis=1), "dead_by_age": t[-1, 7].copy()}
+
+
+def by_age_group(tallies, cohorts, groups=AGE_GROUPS_SWEEP):
+    """parameter_sweep.py:582-600: per age group and day -- infected (group size - S[t]), group size,
+    CFR of the day's exposure cohort, dead (D[t])."""
+    t = np.asarray(tallies)
+    c = np.asarray(cohorts).astype(np.float64)
+    T = t.shape[0]
+    G = len(groups)
+    size_by_age = t[0, [0, 1, 2, 4, 5, 6, 7]].sum(axis=0)  # the compartments partition the agents
+    out = {"infected_by_age_by_time": np.zeros((G, T)), "total_age_by_time": np.zeros((G, T)),
+           "CFR_by_age_by_time": np.full((G, T), np.nan), "dead_by_age_by_time": np.zeros((G, T))}
+    for g, (lo, hi) in enumerate(groups):
+        sl = slice(lo, hi + 1)
+        out["total_age_by_time"][g, :] = size_by_age[sl].sum()
+        out["infected_by_age_by_time"][g, :] = size_by_age[sl].sum() - t[:, 0, sl].sum(axis=1)
+        out["dead_by_age_by_time"][g, :] = t[:, 7, sl].sum(axis=1)
+        d, r = c[:, 2, sl].sum(axis=1), c[:, 3, sl].sum(axis=1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out["CFR_by_age_by_time"][g, :] = d / (d + r)
+    return out

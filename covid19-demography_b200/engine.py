@@ -28,7 +28,7 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_get_agent_vector", "seir_get_history", "seir_get_counters", "seir_destroy",
            "seir_last_error", "seir_device_count", "seir_build_info", "seir_probe_draws",
            "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
-           "seir_get_stage_times")
+           "seir_get_stage_times", "seir_get_cohorts")
 
 
 class SeirParams(C.Structure):
@@ -81,6 +81,7 @@ def load_library():
     lib.seir_get_agent_vector.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.seir_get_history.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.seir_get_counters.argtypes = [H, C.c_int, C.c_void_p]
+    lib.seir_get_cohorts.argtypes = [H, C.c_int, C.c_void_p]
     lib.seir_get_day_times.argtypes = [H, C.c_void_p]
     lib.seir_get_stage_times.argtypes = [H, C.c_void_p]
     lib.seir_destroy.argtypes = [H]
@@ -243,6 +244,13 @@ class Engine:
         """int64[T, 9, 101]: per-day counts by age, planes S,E,Mild,Documented,Severe,Critical,R,D,Q."""
         out = np.empty((self.T, 9, _tables.N_AGES), dtype=np.int64)
         _check(self.lib.seir_get_tallies(self._h, replica, _ptr(out)))
+        return out
+
+    def cohorts(self, replica=0):
+        """int64[T, 4, 101]: per exposure day and age -- agents exposed, sum of num_infected_by, dead at
+        the end, recovered at the end (see driver_tallies.py)."""
+        out = np.empty((self.T, 4, _tables.N_AGES), dtype=np.int64)
+        _check(self.lib.seir_get_cohorts(self._h, replica, _ptr(out)))
         return out
 
     def agent_vector(self, which, replica=0):

@@ -144,6 +144,12 @@ int seir_last_run_ms3(seir_handle *h, float *init_ms, float *day_loop_ms, float 
  * (what the drivers compute with X.sum(axis=1) and the per-age-group masks). */
 int seir_get_tallies(seir_handle *h, int replica, int64_t *out);
 
+/* Exposure-day cohorts, out[T][4][101] int64: for agents exposed on day d of age a, [0] their number,
+ * [1] the sum of their num_infected_by, [2] how many are dead at the end (D[-1]), [3] recovered (R[-1]).
+ * Everything run_simulation.py:448-453 / parameter_sweep.py:572-600 derive per exposure day (R0, CFR,
+ * age fractions, median age, CFR by age group) follows from these counts. */
+int seir_get_cohorts(seir_handle *h, int replica, int64_t *out);
+
 /* One per-agent vector, out[n] doubles. */
 int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out);
 
