@@ -325,7 +325,7 @@ struct __align__(16) PassSmem {
     double nat_enlam[2 * kAges * 2];
     int32_t grp_off[kAges + 1];
     uint32_t cnt[4];
-    uint32_t n_old, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_new;
+    uint32_t n_old, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_new, next_group;
 };
 
 __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
@@ -771,45 +771,38 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
         const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t);
         const uint32_t count = n_new + n_old;  // new infectees first: their record build stays convergent
-        // this CTA's share of the list.  Sparse (the list fits the replica's threads in one sub-iteration):
-        // entry q sits on replica-thread q*S, one entry per warp while that fits.  Dense: groups of 32
-        // entries are dealt round-robin to the replica's CTAs (the new infectees, whose record build is the
-        // longest path, lead the list: a contiguous split would give them all to the first CTAs).
-        const uint32_t rep_threads = (uint32_t)bpr * kThreads;
-        const bool sparse = count <= rep_threads;
-        const uint32_t S = sparse ? spread_of(count, rep_threads) : 1u;
-        const uint32_t n_groups = (count + 31u) / 32u;
-        const uint32_t my_groups = (!sparse && n_groups > (uint32_t)my_part) ? (n_groups - (uint32_t)my_part + (uint32_t)bpr - 1u) / (uint32_t)bpr : 0u;
-        const uint32_t rounds = sparse ? (((uint32_t)my_part * kThreads) / S < count ? 1u : 0u)
-                                       : (my_groups + (uint32_t)(kPerThread * kWarps) - 1u) / (uint32_t)(kPerThread * kWarps);
+        // this CTA's share of the list: groups of G = 32/S entries (one entry per group while the list is
+        // shorter than the replica's warps: a warp pays for every divergent path of its lanes), dealt round-robin
+        // to the replica's CTAs (the new infectees, whose record build is the longest path, lead the list: a
+        // contiguous split would give them all to the first CTAs) and grabbed dynamically by the CTA's warps.
+        const uint32_t G = 32u / spread_of(count, (uint32_t)bpr * kThreads);
+        const uint32_t n_groups = (count + G - 1u) / G;
+        const uint32_t my_groups = n_groups > (uint32_t)my_part ? (n_groups - (uint32_t)my_part + (uint32_t)bpr - 1u) / (uint32_t)bpr : 0u;
+        constexpr uint32_t kGroupsPerRound = (uint32_t)(kSlots / 32);
+        const uint32_t rounds = (my_groups + kGroupsPerRound - 1u) / kGroupsPerRound;
 
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
         if (tid < 4) sm.cnt[tid] = 0;
-        if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; }
+        if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
         __syncthreads();
         SEIR_STAMP(0);
 
         for (uint32_t round = 0; round < rounds; ++round) {
-            // ================= stage A: up to kPerThread list entries per thread =================
-            uint32_t subs = 0;
-#pragma unroll 1
-            for (int sub = 0; sub < kPerThread; ++sub) {
-                uint32_t e;
-                bool has;
-                if (sparse) {
-                    if (sub > 0) break;
-                    e = ((uint32_t)my_part * kThreads + (uint32_t)tid) / S;
-                    has = (((uint32_t)tid & (S - 1u)) == 0u) && e < count;
-                } else {
-                    const uint32_t kb = (round * (uint32_t)kPerThread + (uint32_t)sub) * (uint32_t)kWarps;
-                    if (kb >= my_groups) break;
-                    const uint32_t k = kb + ((uint32_t)tid >> 5);
-                    e = (k * (uint32_t)bpr + (uint32_t)my_part) * 32u + ((uint32_t)tid & 31u);
-                    has = k < my_groups && e < count;
-                }
-                ++subs;
-                const uint32_t slot = (uint32_t)sub * kThreads + tid;
-                sm.hit_n[slot] = 0;
+            // ================= stage A: the round's groups, grabbed by the warps =================
+            const uint32_t g_lo = round * kGroupsPerRound;
+            const uint32_t g_hi = g_lo + kGroupsPerRound < my_groups ? g_lo + kGroupsPerRound : my_groups;
+            const uint32_t subs = (g_hi - g_lo + (uint32_t)kWarps - 1u) / (uint32_t)kWarps;  // slots in use: subs * kThreads (upper bound)
+            for (uint32_t sl = tid; sl < (g_hi - g_lo) * 32u; sl += kThreads) sm.hit_n[sl] = 0;
+            __syncthreads();  // (a full draw queue makes stage A process hits in place)
+            for (;;) {
+                uint32_t k = 0;
+                if ((tid & 31) == 0) k = g_lo + atomicAdd(&sm.next_group, 1u);
+                k = __shfl_sync(0xFFFFFFFFu, k, 0);
+                if (k >= g_hi) break;
+                const uint32_t lane = (uint32_t)tid & 31u;
+                const uint32_t e = (k * (uint32_t)bpr + (uint32_t)my_part) * G + lane;
+                const bool has = lane < G && e < count;
+                const uint32_t slot = (k - g_lo) * 32u + lane;
                 int keep = DAY_DROP;
                 uint32_t i = 0;
                 const bool is_new = e < n_new;
@@ -819,7 +812,7 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 }
                 append_survivors(sm, keep == DAY_KEEP, i);
                 const unsigned hm = __ballot_sync(0xFFFFFFFFu, has), nm = __ballot_sync(0xFFFFFFFFu, has && is_new);
-                if ((tid & 31) == 0 && hm) {
+                if (lane == 0 && hm) {
                     atomicAdd(&sm.cnt[0], (uint32_t)__popc(hm));
                     if (nm) atomicAdd(&sm.cnt[1], (uint32_t)__popc(nm));
                 }
@@ -869,7 +862,8 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             SEIR_STAMP(5);
             // ================= stage W: infector counters (:357-359, :386-390) =================
             {
-                const uint32_t ns = subs * kThreads;
+                const uint32_t ns = (g_hi - g_lo) * 32u;
+                (void)subs;
                 if (any_hit) {
                     for (uint32_t sl = tid; sl < ns; sl += kThreads) {
                         const uint32_t hn = sm.hit_n[sl];
@@ -908,7 +902,7 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                         if (fn) sm.n_new = 0;
                     }
                 }
-                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; }
+                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
                 __syncthreads();
             }
             SEIR_STAMP(6);
@@ -1105,7 +1099,7 @@ __device__ __forceinline__ bool trace_root(const DevCtx &cx, const TraceView &tv
 }
 
 // all roots of day t of the replicas this CTA serves (warp 0 only; no block-wide synchronisation inside)
-__device__ void trace_pass(const DevCtx &cx, TraceSmem &ts, int t)
+__device__ __noinline__ void trace_pass(const DevCtx &cx, TraceSmem &ts, int t)
 {
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
