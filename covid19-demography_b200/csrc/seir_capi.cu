@@ -21,10 +21,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     // the host resets the barrier counter to 0 before each launch
     stage_tables(cx, sm);
     unsigned int epoch = 0;  // grid barriers passed so far
+    if (cx.n_shards > 1) {  // no GPU touches a peer's arrays before every peer has finished (re-)initialising them
+        ++epoch;
+        grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
+    }
     for (int t = 1; t <= cx.T; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
         day_pass(cx, sm, t);
         if (t < cx.T) {
+            if (cx.n_shards > 1) {
+                ++epoch;
+                grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
+                continue;  // (tracing is not available in sharded runs)
+            }
             grid_barrier(cx.barrier, ++epoch * gridDim.x);
             if (cx.trace_from >= 1 && t >= cx.trace_from) {  // :241-242 tracing is on: resolve the day's traces
                 bool any = false;  // (grid-uniform: the counts are final after the barrier)
@@ -80,9 +89,9 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
 {
     const int rep = blockIdx.y;
     const int64_t lo = init_off[rep], hi = init_off[rep + 1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) cx.list_cnt[(size_t)rep * 2 * (cx.T + 2) + 1] = (uint32_t)(hi - lo);
     for (int64_t k = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = init_ids[k];
+        if (cx.n_shards > 1 && (a < cx.shard_lo[cx.my_shard] || a >= cx.shard_lo[cx.my_shard + 1])) continue;  // another GPU's agent
         const uint64_t seed = cx.seeds[rep];
         AgentRec r;
         r.clear();
@@ -95,7 +104,7 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
         store_rec(cx.rec + (size_t)rep * cx.n_pad + a, r);
         cx.winner[(size_t)rep * cx.n_pad + a] = 1ull;  // day 0, never susceptible again
         atomicOr(cx.inbox + (size_t)rep * (cx.n_pad / 16) + (a >> 4), inbox_infected_bit((int)(a & 15)));
-        cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + (k - lo)] = (uint32_t)a;
+        cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + atomicAdd(cx.list_cnt + (size_t)rep * 2 * (cx.T + 2) + 1, 1u)] = (uint32_t)a;
         atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat() & 127), 1u);
     }
 }
@@ -381,6 +390,14 @@ struct seir_handle {
     DevBuf<AgentRec> rec;
     DevBuf<uint64_t> seeds;
     DevBuf<unsigned int> barrier;
+    // sharded run: one population across the GPUs of a box
+    int n_shards = 0, my_shard = 0;
+    int64_t shard_lo[kMaxShards + 1] = {0};
+    void *peer_ptr[kMaxShards][5] = {{nullptr}};   // opened IPC mappings: winner, inbox, list_new, list_cnt, flags
+    DevBuf<unsigned int> flags;
+    unsigned int run_count = 0;
+    std::vector<uint8_t> age8;         // ages, for the per-shard group sizes
+    std::vector<int64_t> shard_group_sizes;
     // contact tracing (allocated when the run can switch tracing on)
     bool trace_alloc = false;
     uint32_t log_cap = 0;
@@ -491,6 +508,17 @@ static void fill_ctx(seir_handle *h)
     c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
     c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
+    c.n_shards = h->n_shards; c.my_shard = h->my_shard;
+    for (int g = 0; g <= kMaxShards; ++g) c.shard_lo[g] = (uint32_t)h->shard_lo[g < h->n_shards ? g : (h->n_shards > 0 ? h->n_shards : 0)];
+    for (int g = 0; g < kMaxShards; ++g) {
+        const bool mine = g == h->my_shard || h->n_shards <= 1 || g >= h->n_shards;
+        c.peer_winner[g] = mine ? h->winner.p : (unsigned long long *)h->peer_ptr[g][0];
+        c.peer_inbox[g] = mine ? h->inbox.p : (uint32_t *)h->peer_ptr[g][1];
+        c.peer_list_new[g] = mine ? h->list_new.p : (uint32_t *)h->peer_ptr[g][2];
+        c.peer_list_cnt[g] = mine ? h->list_cnt.p : (uint32_t *)h->peer_ptr[g][3];
+        c.peer_flags[g] = mine ? h->flags.p : (unsigned int *)h->peer_ptr[g][4];
+    }
+    c.epoch_base = h->run_count * (unsigned int)(p.T + 2);
     const bool tr = tracing_can_start(p) && h->trace_alloc;
     c.trace_from = tr ? p.t_tracing_start : 0;
     c.p_trace_hh = p.p_trace_household; c.p_trace_out = p.p_trace_outside;
@@ -574,6 +602,8 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
             i += sz;
         }
         if (!ok) { fail("seir_population.households: " + why + " (sample_households.py:344-349 emits contiguous households)"); break; }
+        h->age8.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i) h->age8[(size_t)i] = (uint8_t)pop->age[i];
         std::vector<int32_t> goff(kAges + 1), gmem((size_t)n);
         h->group_sizes.resize(kAges);
         bool gok = pop->group_offsets[0] == 0 && pop->group_offsets[kAges] == n;
@@ -622,6 +652,8 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(h->counters.alloc(R * 4));
         CKB(h->barrier.alloc(1));
         CKB(h->init_off.alloc(R + 1));
+        CKB(h->flags.alloc(kMaxShards + 2));
+        CKB(cudaMemset(h->flags.p, 0, (kMaxShards + 2) * 4));
 #undef CKB
         if (alloc_state(h)) break;
         if (upload_tables(h, tables)) break;
@@ -646,6 +678,53 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
     return 0;
 }
 
+int seir_shard_export(seir_handle *h, uint8_t *handles_out)
+{
+    if (!h || !handles_out) return fail("seir_shard_export: NULL argument");
+    CK(cudaSetDevice(h->device));
+    void *ptrs[5] = {h->winner.p, h->inbox.p, h->list_new.p, h->list_cnt.p, h->flags.p};
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
+    for (int k = 0; k < 5; ++k) {
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, ptrs[k]));
+        memcpy(handles_out + 64 * k, &mh, 64);
+    }
+    return 0;
+}
+
+int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_handles, const int64_t *bounds)
+{
+    if (!h || !all_handles || !bounds) return fail("seir_shard_attach: NULL argument");
+    if (world < 2 || world > kMaxShards || rank < 0 || rank >= world) return fail("seir_shard_attach: need 2 <= world <= 8 and 0 <= rank < world");
+    if (h->n_rep != 1) return fail("a sharded run takes one replica");
+    if (h->n_shards > 1) return fail("seir_shard_attach: already attached");
+    if (bounds[0] != 0 || bounds[world] != h->n) return fail("shard bounds must run from 0 to n");
+    CK(cudaSetDevice(h->device));
+    for (int g = 0; g < world; ++g) {
+        if (bounds[g + 1] <= bounds[g]) return fail("shard bounds must be increasing");
+        // a cut must fall on a household boundary: household transmission never leaves the shard
+        if (g > 0) {
+            std::vector<uint16_t> st(1);
+            CK(cudaMemcpy(st.data(), h->stat.p + bounds[g], 2, cudaMemcpyDeviceToHost));
+            if ((st[0] >> 9) & 7) return fail("a shard bound cuts a household (bounds must be household starts)");
+        }
+    }
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) continue;
+        for (int k = 0; k < 5; ++k) {
+            cudaIpcMemHandle_t mh;
+            memcpy(&mh, all_handles + ((size_t)g * 5 + k) * 64, 64);
+            CK(cudaIpcOpenMemHandle(&h->peer_ptr[g][k], mh, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    h->n_shards = world; h->my_shard = rank;
+    for (int g = 0; g <= world; ++g) h->shard_lo[g] = bounds[g];
+    h->shard_group_sizes.assign(kAges, 0);
+    for (int64_t i = bounds[rank]; i < bounds[rank + 1]; ++i) h->shard_group_sizes[h->age8[(size_t)i]] += 1;
+    fill_ctx(h);
+    return 0;
+}
+
 int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables *tables)
 {
     if (!h) return fail("handle is NULL");
@@ -665,6 +744,12 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     if (!h || !reps) return fail("seir_run: NULL argument");
     CK(cudaSetDevice(h->device));
     if (h->prm.mode == SEIR_MODE_REPLAY && !h->replay_tables) return fail("replay mode needs enlam_pre/enlam_post tables");
+    if (h->n_shards > 1) {
+        if (h->n_rep != 1) return fail("a sharded run takes one replica");
+        if (h->prm.launch != SEIR_LAUNCH_PERSISTENT) return fail("a sharded run needs the persistent launch (the GPUs meet at a device-side barrier every day)");
+        if (tracing_can_start(h->prm)) return fail("contact tracing is not available in sharded runs (pass t_tracing_start >= T or tracing_enabled = 0)");
+        ++h->run_count;  // every rank runs the same sequence of seir_run calls: the barrier epochs stay in step
+    }
     const int R = h->n_rep;
     const int64_t n = h->n;
     // ---- per-run host inputs -> device
@@ -746,6 +831,11 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaEventElapsedTime(&h->loop_ms, h->ev1, h->ev2));
     CK(cudaEventElapsedTime(&h->mat_ms, h->ev2, h->ev3));
     CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev3));
+    if (h->n_shards > 1) {
+        unsigned int fl[kMaxShards + 2];
+        CK(cudaMemcpy(fl, h->flags.p, sizeof fl, cudaMemcpyDeviceToHost));
+        if (fl[kMaxShards + 1]) return fail("sharded run: a peer GPU did not reach the day barrier within 4 s");
+    }
     if (tracing) {
         std::vector<unsigned long long> c((size_t)R * 4);
         CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));
@@ -794,7 +884,7 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
             cumD[a] += d[TAL_NEW_D * kAges + a];
             cumDoc[a] += d[TAL_NEW_DOC * kAges + a];
             cumQ2[a] += d[TAL_NEW_Q2 * kAges + a];
-            o[0 * kAges + a] = h->group_sizes[a] - cumE[a];
+            o[0 * kAges + a] = (h->n_shards > 1 ? h->shard_group_sizes[a] : h->group_sizes[a]) - cumE[a];
             o[1 * kAges + a] = d[TAL_E * kAges + a];
             o[2 * kAges + a] = d[TAL_MILD * kAges + a];
             o[3 * kAges + a] = cumDoc[a];
@@ -924,6 +1014,10 @@ void seir_destroy(seir_handle *h)
     h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release();
     h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
     h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release();
+    for (int g = 0; g < kMaxShards; ++g)
+        for (int k = 0; k < 5; ++k)
+            if (h->peer_ptr[g][k]) cudaIpcCloseMemHandle(h->peer_ptr[g][k]);
+    h->flags.release();
     h->list_old.release(); h->list_new.release(); h->list_cnt.release(); h->day_ns.release();
     h->log_ent.release(); h->log_head.release(); h->log_cnt.release(); h->rootbits.release(); h->rootsum.release();
     h->root_cnt.release(); h->tmark.release(); h->trc.release(); h->tstack.release();

@@ -60,6 +60,7 @@ constexpr uint8_t F_TRX = 8;                          // trc[agent] is valid (th
 constexpr unsigned long long W_TRACED = 1ull << 63;
 __host__ __device__ __forceinline__ int wday(unsigned long long w) { return (int)((w >> 48) & 0x7FFFu); }
 constexpr int kLogWidth = 100;  // width of the reference's infected_by log (:197)
+constexpr int kMaxShards = 8;   // GPUs of one box
 constexpr uint16_t NEVER = 0xFFFFu;
 
 // 32 B per-agent record.  Derived days: t_infected = t_exposed + tt_activation (F_MILD),
@@ -163,6 +164,15 @@ struct DevCtx {
     unsigned long long *tmark;     // [rep][n_pad] day<<32 | root + 1 of the last tracer visit
     uint32_t *trc;                 // [rep][n_pad] first post-end traced-Q day | last traced day<<16 (valid with F_TRX)
     uint32_t *tstack;              // [rep][n_pad] DFS stack of the tracing warp
+    // one population across the GPUs of a box (household-aligned shards, peer memory over NVLink)
+    int n_shards, my_shard;        // n_shards <= 1: not sharded
+    uint32_t shard_lo[kMaxShards + 1];             // shard g owns agents [shard_lo[g], shard_lo[g+1])
+    unsigned long long *peer_winner[kMaxShards];   // every GPU keeps full-size arrays in GLOBAL agent indexing;
+    uint32_t *peer_inbox[kMaxShards];              // an agent's winner / inbox / list entries live on its owner
+    uint32_t *peer_list_new[kMaxShards];
+    uint32_t *peer_list_cnt[kMaxShards];
+    unsigned int *peer_flags[kMaxShards];          // [kMaxShards + 2] per GPU: day epochs of the peers, release word, error word
+    unsigned int epoch_base;                       // run number * (T + 2): epochs never repeat, flags need no reset
     // scalars
     int t_lockdown, t_stayhome;
     double p_doc, p_contact, asym;
@@ -360,6 +370,14 @@ template <class F> __device__ __forceinline__ void for_items(uint32_t n, F f)
         if (mine) f(q);
 }
 
+// owner of agent c in a sharded run
+__device__ __forceinline__ int owner_of(const DevCtx &cx, uint32_t c)
+{
+    int g = 0;
+    while (g + 1 < cx.n_shards && c >= cx.shard_lo[g + 1]) ++g;
+    return g;
+}
+
 // ---- stage H: one successful transmission slot's agent -> c on day t (:347-359 / :376-390) ----------
 __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
                                             int age_c, int t)
@@ -369,17 +387,29 @@ __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_
     const uint32_t i = sm.slot_agent[slot];
     const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
     if (age_c == 127) age_c = __ldg(cx.stat + c) & 127;  // (independent of the atomic below: one round trip)
-    const unsigned long long old = atomicMax(v.winner + c, key);
+    const int g = cx.n_shards > 1 ? owner_of(cx, c) : 0;
+    const bool remote = cx.n_shards > 1 && g != cx.my_shard;
+    // (sharded: every atomic on an infectee is system-scope -- it is performed at the owner's L2 over NVLink)
+    const unsigned long long old = cx.n_shards > 1 ? atomicMax_system(cx.peer_winner[g] + c, key) : atomicMax(v.winner + c, key);
     const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
     uint32_t bits = 0;
     if (wday(old) != t) {  // first hit of c today: announce it, queue it for tomorrow
         bits = inbox_infected_bit((int)(c & 15));
-        const uint32_t pos = atomicAdd(&sm.n_new, 1u);
-        if (pos < (uint32_t)kOutNew) sm.out_new[pos] = c;
-        else v.next_new[atomicAdd(v.next_new_cnt, 1u)] = c;
+        if (remote) {  // append to the OWNER's list of tomorrow, in its memory
+            const size_t lrow = (size_t)((t + 1) & 1) * cx.n_pad;
+            const uint32_t pos = atomicAdd_system(cx.peer_list_cnt[g] + (cx.T + 2) + (t + 1), 1u);
+            __stcg(cx.peer_list_new[g] + lrow + pos, c);
+        } else {
+            const uint32_t pos = atomicAdd(&sm.n_new, 1u);
+            if (pos < (uint32_t)kOutNew) sm.out_new[pos] = c;
+            else v.next_new[atomicAdd_system(v.next_new_cnt, 1u)] = c;
+        }
     }
     if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
-    if (bits) atomicOr(v.inbox + (c >> 4), bits);
+    if (bits) {
+        if (cx.n_shards > 1) atomicOr_system(cx.peer_inbox[g] + (c >> 4), bits);
+        else atomicOr(v.inbox + (c >> 4), bits);
+    }
     atomicAdd(&sm.hit_n[slot], ord >= 16u ? 0x10001u : 1u);  // ord >= 16: community (:386-388)
     if (cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387); k follows from (day, ordinal) when the log is read
         const uint32_t e = atomicAdd(cx.log_cnt + v.rep, 1u);
@@ -438,7 +468,7 @@ __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uin
     const int g0 = sm.grp_off[a], glen = sm.grp_off[a + 1] - g0;
     if (glen == 0) return;
     const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
-    const unsigned long long w = __ldcg(v.winner + c);
+    const unsigned long long w = __ldcg((cx.n_shards > 1 ? cx.peer_winner[owner_of(cx, c)] : v.winner) + c);
     if ((w == 0ull || wday(w) == t) && !at_home(v, c))  // :375
         push_hit(cx, sm, c, (slot << 16) | ord, a, t);
 }
@@ -891,7 +921,7 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 if (fo || fn) {
                     if (tid == 0) {
                         if (fo) sm.base_old = atomicAdd(v.next_old_cnt, so);
-                        if (fn) sm.base_new = atomicAdd(v.next_new_cnt, sn);
+                        if (fn) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
                     }
                     __syncthreads();
                     if (fo) for (uint32_t k = tid; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
@@ -915,7 +945,7 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             if (so | sn) {
                 if (tid == 0) {
                     if (so) sm.base_old = atomicAdd(v.next_old_cnt, so);
-                    if (sn) sm.base_new = atomicAdd(v.next_new_cnt, sn);
+                    if (sn) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
                 }
                 __syncthreads();
                 for (uint32_t k = tid; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
@@ -1160,6 +1190,52 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
         } while (seen < target);
         __threadfence();
+    }
+    __syncthreads();
+}
+
+// Barrier over all CTAs of all GPUs of a sharded run.  Local arrival as above (each CTA fences at system
+// scope first: its remote atomics / stores into the peers' memory must be visible before the peers go on);
+// CTA 0 then publishes the epoch in every peer's flag array over NVLink, waits for all peers' epochs in
+// its own, and releases the local CTAs.  A peer that never arrives (its launch failed) ends the wait
+// after kPeerTimeoutNs and raises the error word instead of hanging the box.
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;
+__device__ __forceinline__ void grid_barrier_multi(const DevCtx &cx, unsigned int *counter, unsigned int target, unsigned int epoch)
+{
+    unsigned int *flags = cx.peer_flags[cx.my_shard];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        if (blockIdx.x == 0) {
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            } while (seen < target);
+            __threadfence_system();
+            for (int g = 0; g < cx.n_shards; ++g)
+                if (g != cx.my_shard)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(cx.peer_flags[g] + cx.my_shard), "r"(epoch) : "memory");
+            const unsigned long long t0 = global_timer_ns();
+            for (int g = 0; g < cx.n_shards; ++g) {
+                if (g == cx.my_shard) continue;
+                if (*(volatile unsigned int *)(flags + kMaxShards + 1)) break;  // a peer is gone: do not wait again
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + g) : "memory");
+                    if (seen < epoch && global_timer_ns() - t0 > kPeerTimeoutNs) {
+                        atomicExch(flags + kMaxShards + 1, 1u);  // error word
+                        break;
+                    }
+                } while (seen < epoch);
+            }
+            __threadfence_system();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + kMaxShards), "r"(epoch) : "memory");
+        } else {
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + kMaxShards) : "memory");
+            } while (seen < epoch);
+        }
+        __threadfence_system();
     }
     __syncthreads();
 }

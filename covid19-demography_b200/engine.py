@@ -28,7 +28,7 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_get_agent_vector", "seir_get_history", "seir_get_counters", "seir_destroy",
            "seir_last_error", "seir_device_count", "seir_build_info", "seir_probe_draws",
            "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
-           "seir_get_stage_times", "seir_get_cohorts")
+           "seir_get_stage_times", "seir_get_cohorts", "seir_shard_export", "seir_shard_attach")
 
 
 class SeirParams(C.Structure):
@@ -82,6 +82,8 @@ def load_library():
     lib.seir_get_history.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.seir_get_counters.argtypes = [H, C.c_int, C.c_void_p]
     lib.seir_get_cohorts.argtypes = [H, C.c_int, C.c_void_p]
+    lib.seir_shard_export.argtypes = [H, C.c_void_p]
+    lib.seir_shard_attach.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.seir_get_day_times.argtypes = [H, C.c_void_p]
     lib.seir_get_stage_times.argtypes = [H, C.c_void_p]
     lib.seir_destroy.argtypes = [H]
@@ -184,6 +186,21 @@ class Engine:
             setattr(tb, k, _ptr(v))
         self._tables_keep = keep
         return tb
+
+    def shard_export(self):
+        """320 bytes: the CUDA IPC handles of this rank's arrays (include/seir_b200.h, seir_shard_export)."""
+        out = np.zeros(5 * 64, dtype=np.uint8)
+        _check(self.lib.seir_shard_export(self._h, _ptr(out)))
+        return out
+
+    def shard_attach(self, rank, world, all_handles, bounds):
+        """all_handles uint8[world, 320] (rank-major), bounds int64[world + 1] (household starts)."""
+        hd = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world, 5 * 64)
+        bd = np.ascontiguousarray(bounds, dtype=np.int64)
+        if bd.shape != (world + 1,):
+            raise ValueError("bounds must have world + 1 entries")
+        _check(self.lib.seir_shard_attach(self._h, int(rank), int(world), _ptr(hd), _ptr(bd)))
+        self.shard = (int(rank), int(world), bd.copy())
 
     def set_params(self, params=None, tables=None, mode=None, launch=None, tracing_enabled=None):
         if mode is not None:

@@ -127,6 +127,18 @@ typedef struct seir_handle seir_handle;
 int seir_create(const seir_params *params, const seir_population *pop, const seir_tables *tables,
                 int n_replicas, int device, seir_handle **out);
 
+/* One population across the GPUs of a box (shards of whole households; every rank creates
+ * its handle on its own device with the FULL population and n_replicas = 1).
+ * seir_shard_export: 5 x 64 bytes of CUDA IPC handles of this rank's winner / inbox / list / flag arrays.
+ * seir_shard_attach: all ranks' handles (world x 5 x 64 bytes, rank-major) and the shard bounds
+ *   (bounds[world + 1], bounds[g] a household start): rank `rank` owns agents [bounds[rank], bounds[rank+1]).
+ * Afterwards seir_run steps only the owned agents; a community contact whose target lives on another GPU is
+ * resolved in that GPU's memory over NVLink (system-scope atomics), and the GPUs meet at a device-side
+ * barrier once per day.  All ranks must call seir_run together, with the same seed and initial cases.
+ * Outputs (tallies, vectors, history) cover the owned agents; tallies of the ranks add up. */
+int seir_shard_export(seir_handle *h, uint8_t *handles_out);
+int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_handles, const int64_t *bounds);
+
 /* Replace the scalar parameters / tables (same population) before the next seir_run. */
 int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables *tables);
 
