@@ -351,6 +351,106 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def c3_params(n, n_initial=5):
+    """C3 parameters: the China block of run_simulation.py (:35-39, :62, :72, :94) as frozen in the golden fixture:
+    T = 127, lockdown on day 69 (/50), China contact matrix; tracing never switches on."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_china_default.npz"))
+    p = dict(zip(fx["param_keys"].tolist(), [float(v) for v in fx["param_vals"]]))
+    p["n"] = float(n)
+    p["initial_infected_fraction"] = n_initial / n
+    p["t_tracing_start"] = 1.0e6
+    tabs = {k: fx[k] for k in ("contact_matrix", "p_mild_severe", "p_severe_critical", "p_critical_death",
+                               "mean_time_to_isolate_factor", "lockdown_factor_age")}
+    tabs["p_infect_household"] = float(fx["p_infect_household_scalar"])
+    return p, tabs
+
+
+def run_sharded_arm(args):
+    """--sharded: ONE population (default C3: 59 M agents, T = 127) split by whole households over the N GPUs
+    (strong scaling).  Cross-shard contacts are resolved in peer memory over NVLink inside the persistent
+    kernel; the ranks meet at a device-side barrier once per day.  N = 1 runs the same workload unsharded."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from covid19_demography_b200 import engine, population, sharding, tables
+    n = args.n if args.n != 10_000_000 else 59_000_000
+    p, tabs = c3_params(n, args.n_initial)
+    T = int(p["T"])
+    hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1, country="China")
+    tb = tables.build_tables(tabs["contact_matrix"], np.array([len(g) for g in groups]), tables.params_to_dict(p),
+                             tabs["mean_time_to_isolate_factor"], tabs["p_mild_severe"], tabs["p_severe_critical"],
+                             tabs["p_critical_death"], with_replay=False)
+    eng = engine.Engine(p, hh, age, groups, diab, hyp, np.full(n, tabs["p_infect_household"]), tb, n_replicas=1,
+                        device=local, mode="native", launch="persistent")
+    bounds = None
+    if world > 1:
+        class _D:  # sharding.attach only needs rank / size / object gather / barrier
+            get_rank, get_world_size = staticmethod(dist.get_rank), staticmethod(dist.get_world_size)
+            all_gather_object, barrier = staticmethod(dist.all_gather_object), staticmethod(dist.barrier)
+        bounds = sharding.attach(eng, hh, _D)
+    del hh
+    rng = np.random.default_rng(3)  # the same initial cases and seeds on every rank
+    runs = [([50 + k], None, [rng.choice(n, size=args.n_initial, replace=False).astype(np.int64)])
+            for k in range(args.warmup + args.steps)]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        eng.run(*runs[k])
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync_all()
+    dev_ms = loop_ms = 0.0
+    launches = 0
+    e0 = time.perf_counter()
+    infected = 0
+    for k in range(args.warmup, args.warmup + args.steps):
+        eng.run(*runs[k])
+        a, b = eng.last_run_ms()
+        loop_ms += a
+        dev_ms += b
+        launches += eng.counters()["launches"]
+        tal = eng.tallies(0)  # d2h of the step's result
+        infected = int(tal[0, 0].sum() - tal[-1, 0].sum())
+    sync_all()
+    e2e_s = time.perf_counter() - e0
+    clocks = sampler.finish()
+    if world > 1:
+        tt = torch.tensor([dev_ms, e2e_s, loop_ms], dtype=torch.float64, device="cuda:%d" % local)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s, loop_ms = [float(x) for x in tt.tolist()]
+        ll = torch.tensor([launches, infected], dtype=torch.int64, device="cuda:%d" % local)
+        dist.all_reduce(ll)
+        launches, infected = int(ll[0].item()), int(ll[1].item())
+    if rank == 0:
+        agent_days = float(n) * (T - 1) * args.steps
+        line = {"metric": METRIC, "value": agent_days / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+                "config": {"workload": "C3 Hubei-like %d agents, T=%d, lockdown day 69 (/50), %d initial cases, ONE population "
+                                       "sharded by whole households over %d GPU(s), tracing never switches on" % (n, T, args.n_initial, world),
+                           "mode": "native", "launch": "persistent", "exchange": "peer-memory atomics over NVLink + device-side day barrier"
+                           if world > 1 else "none (single GPU)", "shard_bounds": None if bounds is None else [int(b) for b in bounds],
+                           "day_loop_ms_per_step": loop_ms / args.steps, "infections_last_step": infected,
+                           "l2": "per-run working set %.1f GB > 126 MB L2; state re-initialised every step" % ((T * n + 46 * n) / 1e9)},
+                "clocks": clocks,
+                "e2e": {"value": agent_days / e2e_s, "unit": UNIT, "h2d_bytes_per_step": world * (8 * args.n_initial + 8),
+                        "d2h_bytes_per_step": world * T * 9 * 101 * 8, "ms_per_step": e2e_s / args.steps * 1e3},
+                "gpu_launches": launches}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def tracing_leg(engine, population, tables, args, n, T, device):
     """The same workload with the reference's own t_tracing_start = 37 (run_simulation.py:115-116): as
     compiled the reference traces contacts from that day.  One warm-up + one timed run."""
@@ -389,12 +489,16 @@ def main():
     ap.add_argument("--cpu-workers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tracing-leg", action="store_true")
+    ap.add_argument("--sharded", action="store_true", help="one C3 population sharded over the GPUs (strong scaling)")
+    ap.add_argument("--n-initial", type=int, default=5, help="initial cases of the --sharded workload")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from ncu (profiles/), if known")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 3) if os.environ.get("SEIR_BENCH_STRICT_WARMUP", "1") == "1" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.sharded:
+        run_sharded_arm(args)
     else:
         run_gpu_arm(args)
 
