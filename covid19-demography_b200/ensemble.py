@@ -28,18 +28,21 @@ def batches(items, batch):
     return [items[k:k + batch] for k in range(0, len(items), batch)]
 
 
-def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fraction, want_vectors=()):
+def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fraction, want_vectors=(),
+              want_cohorts=False):
     """Run `seeds` on `engine` (an engine.Engine with R replica slots) in batches of R.
 
     Per seed the reference's own prologue picks are used (`tables.prologue`, seir_individual.py:176-187).
     A short last batch is padded by repeating its last seed (the padding runs are discarded).
-    Returns {"tallies": int64[len(seeds), T, 9, 101], "counters": [dict], "vectors": {name: float64[len(seeds), n]}}.
+    Returns {"tallies": int64[len(seeds), T, 9, 101], "counters": [dict], "vectors": {name: float64[len(seeds), n]},
+    "cohorts": int64[len(seeds), T, 4, 101] (with want_cohorts)}.
     """
     R = engine.n_replicas
     n = engine.n
     tallies = np.zeros((len(seeds), engine.T, 9, _tables.N_AGES), dtype=np.int64)
     counters = []
     vectors = {k: np.zeros((len(seeds), n)) for k in want_vectors}
+    cohorts = np.zeros((len(seeds), engine.T, 4, _tables.N_AGES), dtype=np.int64) if want_cohorts else None
     done = 0
     for chunk in batches(list(seeds), R):
         padded = chunk + [chunk[-1]] * (R - len(chunk))
@@ -48,10 +51,12 @@ def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fr
         for r in range(len(chunk)):
             tallies[done + r] = engine.tallies(r)
             counters.append(engine.counters(r))
+            if want_cohorts:
+                cohorts[done + r] = engine.cohorts(r)
             for k in want_vectors:
                 vectors[k][done + r] = engine.agent_vector(k, replica=r)
         done += len(chunk)
-    return {"tallies": tallies, "counters": counters, "vectors": vectors}
+    return {"tallies": tallies, "counters": counters, "vectors": vectors, "cohorts": cohorts}
 
 
 def gather(local_indices, local_array, n_items, dist=None):

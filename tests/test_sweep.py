@@ -1,0 +1,100 @@
+"""Parameter sweeps in process: the reference's SLURM-array index arithmetic
+(parameter_sweep.py:107-126, :546-548), the dealing of jobs to ranks, and -- on the GPU -- a two-combination
+sweep on one resident population against the oracle."""
+import numpy as np
+import pytest
+
+import util
+from covid19_demography_b200 import sweep, tables as tables_mod
+
+
+def test_index_arithmetic_matches_the_reference():
+    # parameter_sweep.py: INDEX -> (combo, trial, seed); seed = INDEX * N_SIMS_PER_JOB + offset, +1 before each run
+    items = sweep.work_items(n_combos=3, n_sims_per_combo=8, n_sims_per_job=4, seed_offset=100)
+    assert len(items) == 6
+    for idx, it in enumerate(items):
+        jobs_per_combo = 8 // 4
+        assert it["combo"] == idx // jobs_per_combo and it["trial"] == idx % jobs_per_combo
+        seed = idx * 4 + 100
+        want = []
+        for _ in range(4):
+            seed += 1
+            want.append(seed)
+        assert it["seeds"] == want
+    all_seeds = sum((it["seeds"] for it in items), [])
+    assert len(set(all_seeds)) == len(all_seeds)
+    with pytest.raises(ValueError):
+        sweep.work_items(2, 5, 2)
+
+
+def test_gather_sweep_checks_coverage():
+    a = {0: {"x": 1}, 2: {"x": 3}}
+    with pytest.raises(RuntimeError, match="no rank"):
+        sweep.gather_sweep(a, 3)
+    assert sweep.gather_sweep({0: 1, 1: 2}, 2) == {0: 1, 1: 2}
+
+
+class _FakeEngine:
+    """Records the order of parameter switches and runs; results are a function of (combo marker, seed)."""
+    n_replicas, n, T = 2, 10, 4
+
+    def __init__(self):
+        self.log, self.marker = [], None
+
+    def set_params(self, params=None, tables=None):
+        self.marker = params["p_infect_given_contact"]
+        self.log.append(("set", self.marker))
+
+    def run(self, seeds, home, init):
+        self._seeds = list(seeds)
+        self.log.append(("run", tuple(seeds)))
+
+    def tallies(self, r):
+        return np.full((self.T, 9, 101), int(self._seeds[r] * 1000 + self.marker * 100), dtype=np.int64)
+
+    def cohorts(self, r):
+        return np.zeros((self.T, 4, 101), dtype=np.int64)
+
+    def counters(self, r):
+        return {}
+
+
+def test_run_sweep_switches_parameters_only_between_combinations():
+    c = util.Case("italy_default")
+    base = tables_mod.params_to_dict(c.params)
+    combos = [{"params": dict(base, p_infect_given_contact=float(k)), "tables": None} for k in (1, 2)]
+    items = sweep.work_items(2, 6, 3)
+    groups = tuple(np.arange(0) for _ in range(101))
+    seen = {}
+    for rank in range(2):
+        eng = _FakeEngine()
+        res = sweep.run_sweep(eng, combos, items, groups, np.zeros(101), rank=rank, world=2)
+        sets = [x for x in eng.log if x[0] == "set"]
+        assert len(sets) == 2, "one parameter switch per combination on each rank"
+        for idx, r in res.items():
+            assert idx not in seen
+            seen[idx] = r
+            marker = combos[items[idx]["combo"]]["params"]["p_infect_given_contact"]
+            assert [int(t[0, 0, 0]) for t in r["tallies"]] == [int(s * 1000 + marker * 100) for s in items[idx]["seeds"]]
+    assert sorted(seen) == list(range(len(items)))
+
+
+@pytest.mark.gpu
+def test_two_combination_sweep_on_one_resident_population(gpu_engine_module):
+    """parameter_sweep.py-like: transmissibility and the start day (hence T and the lockdown day) change between
+    combinations, the population stays on the device; every run == the oracle under the same keyed draws."""
+    c = util.Case("italy_default")
+    base = c.no_tracing_params()
+    combos = []
+    for pigc, T, t_lock in ((0.035, 50.0, 30.0), (0.025, 66.0, 46.0)):
+        p = dict(base, p_infect_given_contact=pigc, T=T, t_lockdown=t_lock, initial_infected_fraction=0.004)
+        combos.append({"params": p, "tables": c.tables(p)})
+    items = sweep.work_items(2, 4, 2, seed_offset=40)
+    eng = c.gpu_engine(gpu_engine_module, combos[0]["params"], "native", n_replicas=2)
+    res = sweep.gather_sweep(sweep.run_sweep(eng, combos, items, c.age_groups, c.fraction_stay_home), len(items))
+    for idx, r in res.items():
+        p = combos[items[idx]["combo"]]["params"]
+        for k, seed in enumerate(r["seeds"]):
+            tup, _, _, _ = c.keyed_oracle("native", p, seed=seed)
+            assert np.array_equal(r["tallies"][k], util.tallies_from_history(tup[:9], c.age, int(p["T"]))), (idx, seed)
+    eng.close()
