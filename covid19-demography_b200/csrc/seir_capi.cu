@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
                 bool any = false;  // (grid-uniform: the counts are final after the barrier)
                 for (int r = 0; r < cx.n_rep; ++r) any = any || __ldcg(cx.root_cnt + (size_t)r * (cx.T + 2) + t) != 0u;
                 if (any) {
-                    trace_pass(cx, *reinterpret_cast<TraceSmem *>(sm.out_old), t);
+                    if (cx.tcomp) trace_parallel(cx, sm, t, epoch);  // components in parallel, ordered inside
+                    else trace_pass(cx, *reinterpret_cast<TraceSmem *>(sm.out_old), t);
                     grid_barrier(cx.barrier, ++epoch * gridDim.x);
                 }
             }
@@ -73,10 +74,7 @@ __global__ void seir_init_state_kernel(DevCtx cx)
         uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + g * kVec);
 #pragma unroll
         for (int k = 0; k < 8; ++k) __stcs(wz + k, z);
-        if (cx.tmark) {  // tracing state: visit marks and log heads
-            uint4 *tz = reinterpret_cast<uint4 *>(cx.tmark + g * kVec);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) __stcs(tz + k, z);
+        if (cx.log_head) {  // tracing state: log heads (the tracer's marks are stamped with the run number)
             uint4 *hz = reinterpret_cast<uint4 *>(cx.log_head + g * kVec);
 #pragma unroll
             for (int k = 0; k < 4; ++k) __stcs(hz + k, z);
@@ -400,9 +398,12 @@ struct seir_handle {
     std::vector<int64_t> shard_group_sizes;
     // contact tracing (allocated when the run can switch tracing on)
     bool trace_alloc = false;
+    unsigned int trace_runs = 0;
     uint32_t log_cap = 0;
     DevBuf<uint4> log_ent;
-    DevBuf<uint32_t> log_head, log_cnt, rootbits, rootsum, root_cnt, trc, tstack;
+    DevBuf<uint32_t> log_head, log_cnt, rootbits, rootsum, root_cnt, trc, tstack, rootsum2, treached, troots, treps, tcsz;
+    DevBuf<unsigned long long> tcomp, tlead, ttotal;
+    DevBuf<TraceCtl> tctl;
     DevBuf<unsigned long long> tmark;
     double p_hh_scalar = 0.0;
     bool p_hh_uniform = true;
@@ -472,8 +473,21 @@ static int alloc_state(seir_handle *h)
         CK(h->rootsum.alloc(R * np / 1024));
         CK(h->root_cnt.alloc(R * (T + 2)));
         CK(h->tmark.alloc(R * np));
+        CK(cudaMemset(h->tmark.p, 0, R * np * 8));
         CK(h->trc.alloc(R * np));
         CK(h->tstack.alloc(R * np));
+        CK(h->rootsum2.alloc(R * ((np + 32767) / 32768)));
+        CK(h->tcomp.alloc(R * np));
+        CK(h->tlead.alloc(R * np));
+        CK(cudaMemset(h->tcomp.p, 0, R * np * 8));
+        CK(cudaMemset(h->tlead.p, 0, R * np * 8));
+        CK(h->treached.alloc(R * np));
+        CK(h->troots.alloc(R * np));
+        CK(h->treps.alloc(R * np));
+        CK(h->tcsz.alloc(R * np));
+        CK(h->tctl.alloc(R));
+        CK(h->ttotal.alloc(1));
+        CK(cudaMemset(h->ttotal.p, 0, 8));
         h->trace_alloc = true;
     }
     CK(h->hist.alloc(R * T * np));
@@ -526,6 +540,12 @@ static void fill_ctx(seir_handle *h)
     c.log_cap = tr ? h->log_cap : 0u;
     c.rootbits = tr ? h->rootbits.p : nullptr; c.rootsum = tr ? h->rootsum.p : nullptr; c.root_cnt = tr ? h->root_cnt.p : nullptr;
     c.tmark = tr ? h->tmark.p : nullptr; c.trc = tr ? h->trc.p : nullptr; c.tstack = tr ? h->tstack.p : nullptr;
+    c.rootsum2 = tr ? h->rootsum2.p : nullptr;
+    const bool par = tr && p.launch == SEIR_LAUNCH_PERSISTENT && h->n_rep <= kMaxRepsPerCta * (h->grid / (h->grid / h->n_rep > 0 ? h->grid / h->n_rep : 1));
+    c.tcomp = par ? h->tcomp.p : nullptr; c.tlead = par ? h->tlead.p : nullptr;
+    c.treached = par ? h->treached.p : nullptr; c.troots = par ? h->troots.p : nullptr;
+    c.treps = par ? h->treps.p : nullptr; c.tcsz = par ? h->tcsz.p : nullptr;
+    c.tctl = par ? h->tctl.p : nullptr; c.ttotal = par ? h->ttotal.p : nullptr;
     c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
     c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
     c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
@@ -797,6 +817,14 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaMemsetAsync(h->root_cnt.p, 0, (size_t)R * (h->prm.T + 2) * 4, h->stream));
         CK(cudaMemsetAsync(h->rootbits.p, 0, (size_t)R * h->n_pad / 32 * 4, h->stream));
         CK(cudaMemsetAsync(h->rootsum.p, 0, (size_t)R * h->n_pad / 1024 * 4, h->stream));
+        CK(cudaMemsetAsync(h->rootsum2.p, 0, (size_t)R * ((h->n_pad + 32767) / 32768) * 4, h->stream));
+        if ((++h->trace_runs & 0xFFFFFu) == 0u) {  // the stamps wrap after 2^20 runs: start over with clean marks
+            CK(cudaMemsetAsync(h->tmark.p, 0, (size_t)R * h->n_pad * 8, h->stream));
+            CK(cudaMemsetAsync(h->tcomp.p, 0, (size_t)R * h->n_pad * 8, h->stream));
+            CK(cudaMemsetAsync(h->tlead.p, 0, (size_t)R * h->n_pad * 8, h->stream));
+            ++h->trace_runs;
+        }
+        h->cx.tday0 = (h->trace_runs & 0xFFFFFu) << 12;
     }
     seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
     ++h->launches;
@@ -1021,6 +1049,8 @@ void seir_destroy(seir_handle *h)
     h->list_old.release(); h->list_new.release(); h->list_cnt.release(); h->day_ns.release();
     h->log_ent.release(); h->log_head.release(); h->log_cnt.release(); h->rootbits.release(); h->rootsum.release();
     h->root_cnt.release(); h->tmark.release(); h->trc.release(); h->tstack.release();
+    h->rootsum2.release(); h->tcomp.release(); h->tlead.release(); h->treached.release(); h->troots.release();
+    h->treps.release(); h->tcsz.release(); h->tctl.release(); h->ttotal.release();
     h->alias_idx.release(); h->stage_ns.release(); h->fine_ns.release();
     if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->ev0) cudaEventDestroy(h->ev0);

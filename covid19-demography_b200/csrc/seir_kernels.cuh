@@ -115,6 +115,7 @@ __host__ __device__ inline uint16_t pack_static(int age, int diab, int hyp, int 
 __host__ __device__ inline uint32_t inbox_infected_bit(int k) { return 1u << (8 * (k & 3) + (k >> 2)); }
 __host__ __device__ inline uint32_t inbox_q_bit(int k) { return 1u << (8 * (k & 3) + 4 + (k >> 2)); }
 
+struct TraceCtl;
 struct DevCtx {
     // population, shared by all replicas
     int64_t n;            // agents
@@ -163,7 +164,13 @@ struct DevCtx {
     uint32_t *root_cnt;            // [rep][T+2] roots of day t
     unsigned long long *tmark;     // [rep][n_pad] day<<32 | root + 1 of the last tracer visit
     uint32_t *trc;                 // [rep][n_pad] first post-end traced-Q day | last traced day<<16 (valid with F_TRX)
-    uint32_t *tstack;              // [rep][n_pad] DFS stack of the tracing warp
+    uint32_t *tstack;              // [rep][n_pad] DFS stacks of the tracing warps
+    uint32_t *rootsum2;            // [rep][ceil(n_pad/32768)] bit s set = rootsum word s non-zero
+    unsigned long long *tcomp, *tlead;  // [rep][n_pad] parallel tracer: union-find parents, component leaders (day-stamped)
+    uint32_t *treached, *troots, *treps, *tcsz;  // [rep][n_pad]
+    struct TraceCtl *tctl;         // [rep]
+    uint32_t tday0;                // run number << 12: the tracer's day stamps (tmark, tcomp, tlead) are tday0 + t and never need clearing
+    unsigned long long *ttotal;    // nodes ever appended to a frontier (grows monotonically: the BFS loop's stop test)
     // one population across the GPUs of a box (household-aligned shards, peer memory over NVLink)
     int n_shards, my_shard;        // n_shards <= 1: not sharded
     uint32_t shard_lo[kMaxShards + 1];             // shard g owns agents [shard_lo[g], shard_lo[g+1])
@@ -670,6 +677,7 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
         if (root && v.tracing) {
             atomicOr(cx.rootbits + (size_t)v.rep * (cx.n_pad / 32) + (i >> 5), 1u << (i & 31));
             atomicOr(cx.rootsum + (size_t)v.rep * (cx.n_pad / 1024) + (i >> 10), 1u << ((i >> 5) & 31));
+            atomicOr(cx.rootsum2 + (size_t)v.rep * ((cx.n_pad + 32767) / 32768) + (i >> 15), 1u << ((i >> 10) & 31));
             atomicAdd(cx.root_cnt + (size_t)v.rep * (cx.T + 2) + t, 1u);
         }
     }
@@ -1039,93 +1047,140 @@ __device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, u
     __stcg(tv.trc + x, tw);
 }
 
-constexpr int kTraceLogCap = 512;  // log entries of one agent staged in shared memory (the reference keeps 100)
+// (log entries of one agent staged in shared memory: 504; the reference keeps 100)
+constexpr int kTraceLogCap = 504;
 struct TraceSmem {
     uint32_t ent_x[kTraceLogCap];
     uint32_t ent_key[kTraceLogCap];  // day<<16 | ordinal: the order of infected_by[c, :]
+    uint32_t n, pad[15];             // length of the warp's search list
 };
 
-// one root: warp-cooperative search.  Returns false on stack overflow.
-__device__ __forceinline__ bool trace_root(const DevCtx &cx, const TraceView &tv, TraceSmem &ts, uint32_t *stack, uint32_t cap)
+// One node of a root's search, by one warp: evaluate the edges of c with the reference's guards, claim and
+// mark the contacts reached, append them to the search list.  Within ONE root the order of the visits does not
+// matter (the visited set is a closure and every mark is idempotent), so the list is used as a queue and
+// several warps may expand different nodes of the same root concurrently.  Returns false on list overflow.
+__device__ __forceinline__ bool trace_expand_exact(const DevCtx &cx, const TraceView &tv, TraceSmem &ts, uint32_t c,
+                                                   uint32_t *list, uint32_t cap, uint32_t *n_ptr)
 {
     const int lane = threadIdx.x & 31;
     const int t = tv.t;
     const uint32_t root = tv.root;
-    const unsigned long long key = tkey(t, root);
+    const int td = (int)cx.tday0 + t;  // the day stamp of this run
+    const unsigned long long key = tkey(td, root);
     const uint32_t *log_head = cx.log_head + (size_t)tv.rep * cx.n_pad;
     const uint4 *log_ent = cx.log_ent + (size_t)tv.rep * cx.log_cap;
-    if (lane == 0) {
-        __stcg(tv.tmark + root, key);
-        __stcg(stack, root);
-    }
-    __syncwarp();
-    uint32_t sp = 1;
     bool ok_all = true;
-    while (sp > 0) {
-        const uint32_t c = __ldcg(stack + (sp - 1));
-        --sp;
-        const uint16_t stt = __ldg(cx.stat + c);
-        const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
-        const uint32_t base = c - (uint32_t)pos;
-        // ---- infected_by[c, :]: walk the list (lane 0), newest entry first
-        uint32_t L = 0;
-        if (lane == 0) {
-            uint32_t e = __ldcg(log_head + c);
-            while (e != 0u && L < (uint32_t)kTraceLogCap) {
-                const uint4 en = __ldcg(log_ent + (e - 1u));
-                ts.ent_x[L] = en.x;
-                ts.ent_key[L] = en.z;
-                ++L;
-                e = en.y;
-            }
+    const uint16_t stt = __ldg(cx.stat + c);
+    const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
+    const uint32_t base = c - (uint32_t)pos;
+    // ---- infected_by[c, :]: walk the list (lane 0), newest entry first
+    uint32_t L = 0;
+    if (lane == 0) {
+        uint32_t e = __ldcg(log_head + c);
+        while (e != 0u && L < (uint32_t)kTraceLogCap) {
+            const uint4 en = __ldcg(log_ent + (e - 1u));
+            ts.ent_x[L] = en.x;
+            ts.ent_key[L] = en.z;
+            ++L;
+            e = en.y;
         }
-        L = __shfl_sync(0xFFFFFFFFu, L, 0);
+    }
+    L = __shfl_sync(0xFFFFFFFFu, L, 0);
+    __syncwarp();
+    const uint32_t n_edges = (uint32_t)(size - 1) + L;
+    for (uint32_t e0 = 0; e0 < n_edges; e0 += 32u) {
+        const uint32_t e = e0 + (uint32_t)lane;
+        bool ok = false;
+        uint32_t target = 0;
+        if (e < (uint32_t)(size - 1)) {  // household edge j (:68-77)
+            const int j = (int)e;
+            target = base + (uint32_t)j + (j >= pos ? 1u : 0u);
+            const unsigned long long w = __ldcg(tv.winner + target);
+            if (w != 0ull && wday(w) != t) {  // not S[t-1, contact]
+                // traced[contact]: documented before today, or by its own iteration today if that came first
+                // (contact <= root), or reached by a tracer today
+                const AgentRec m = load_rec(tv.rec + target);
+                bool traced = (m.state() & ST_DOC) != 0;
+                if (traced && (int)m.t_documented() == t && target > root &&
+                    (int)(__ldcg(tv.tmark + target) >> 32) != td)
+                    traced = false;
+                if (!traced) ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_HH, (uint32_t)j), 0) < cx.p_trace_hh;
+            }
+        } else if (e < n_edges) {  // outside edge (:79-88); slot = rank of the entry in (day, ordinal) order
+            const uint32_t k = e - (uint32_t)(size - 1);
+            const uint32_t kk = ts.ent_key[k];
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < L; ++q) rank += ts.ent_key[q] < kk ? 1u : 0u;
+            target = ts.ent_x[k];
+            // today's entries exist only if c's iteration has run before the root's (c < root)
+            if (rank < (uint32_t)kLogWidth && ((int)(kk >> 16) < t || c < root))
+                ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_OUT, rank), 0) < cx.p_trace_out;
+        }
+        if (ok) {
+            const unsigned long long old = atomicExch(tv.tmark + target, key);
+            if (old == key) ok = false;  // already reached under this root
+            else trace_mark(cx, tv, target);
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(n_ptr, (uint32_t)__popc(m));
+            at = __shfl_sync(0xFFFFFFFFu, at, 0);
+            if (ok) {
+                const uint32_t mine = at + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (mine < cap) __stcg(list + mine, target);
+            }
+            if (at + (uint32_t)__popc(m) > cap) ok_all = false;
+        }
         __syncwarp();
-        const uint32_t n_edges = (uint32_t)(size - 1) + L;
-        for (uint32_t e0 = 0; e0 < n_edges; e0 += 32u) {
-            const uint32_t e = e0 + (uint32_t)lane;
-            bool ok = false;
-            uint32_t target = 0;
-            if (e < (uint32_t)(size - 1)) {  // household edge j (:68-77)
-                const int j = (int)e;
-                target = base + (uint32_t)j + (j >= pos ? 1u : 0u);
-                const unsigned long long w = __ldcg(tv.winner + target);
-                if (w != 0ull && wday(w) != t) {  // not S[t-1, contact]
-                    // traced[contact]: documented before today, or by its own iteration today if that came first
-                    // (contact <= root), or reached by a tracer today
-                    const AgentRec m = load_rec(tv.rec + target);
-                    bool traced = (m.state() & ST_DOC) != 0;
-                    if (traced && (int)m.t_documented() == t && target > root &&
-                        (int)(__ldcg(tv.tmark + target) >> 32) != t)
-                        traced = false;
-                    if (!traced) ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_HH, (uint32_t)j), 0) < cx.p_trace_hh;
-                }
-            } else if (e < n_edges) {  // outside edge (:79-88); slot = rank of the entry in (day, ordinal) order
-                const uint32_t k = e - (uint32_t)(size - 1);
-                const uint32_t kk = ts.ent_key[k];
-                uint32_t rank = 0;
-                for (uint32_t q = 0; q < L; ++q) rank += ts.ent_key[q] < kk ? 1u : 0u;
-                target = ts.ent_x[k];
-                // today's entries exist only if c's iteration has run before the root's (c < root)
-                if (rank < (uint32_t)kLogWidth && ((int)(kk >> 16) < t || c < root))
-                    ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_OUT, rank), 0) < cx.p_trace_out;
-            }
-            if (ok) {
-                const unsigned long long old = atomicExch(tv.tmark + target, key);
-                if (old == key) ok = false;  // already expanded under this root
-                else trace_mark(cx, tv, target);
-            }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (ok) {
-                const uint32_t at = sp + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                if (at < cap) __stcg(stack + at, target);
-            }
-            sp += (uint32_t)__popc(m);
-            if (sp > cap) { ok_all = false; sp = cap; }
-            __syncwarp();
-        }
     }
     return ok_all;
+}
+
+// one root, one warp
+__device__ __forceinline__ bool trace_root(const DevCtx &cx, const TraceView &tv, TraceSmem &ts, uint32_t *list, uint32_t cap)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        __stcg(tv.tmark + tv.root, tkey((int)cx.tday0 + tv.t, tv.root));
+        __stcg(list, tv.root);
+        ts.n = 1;
+    }
+    __syncwarp();
+    bool ok_all = true;
+    for (uint32_t lo = 0;; ++lo) {
+        const uint32_t n = min(*(volatile uint32_t *)&ts.n, cap);
+        if (lo >= n) break;
+        ok_all = trace_expand_exact(cx, tv, ts, __ldcg(list + lo), list, cap, &ts.n) && ok_all;
+        __syncwarp();
+    }
+    return ok_all;
+}
+
+// one root, the whole CTA: level-synchronous over the search list (a root whose search covers thousands of agents)
+__device__ __forceinline__ bool trace_root_cta(const DevCtx &cx, const TraceView &tv, TraceSmem &ts, uint32_t *list, uint32_t cap,
+                                               uint32_t *n_shared)
+{
+    const int wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        __stcg(tv.tmark + tv.root, tkey((int)cx.tday0 + tv.t, tv.root));
+        __stcg(list, tv.root);
+        *n_shared = 1;
+    }
+    __syncthreads();
+    bool ok_all = true;
+    uint32_t lo = 0;
+    for (;;) {
+        const uint32_t hi = min(*(volatile uint32_t *)n_shared, cap);
+        __syncthreads();  // (everybody has read the level's end before anybody appends)
+        if (lo >= hi) break;
+        for (uint32_t idx = lo + (uint32_t)wib; idx < hi; idx += (uint32_t)(kThreads / 32))
+            ok_all = trace_expand_exact(cx, tv, ts, __ldcg(list + idx), list, cap, n_shared) && ok_all;
+        lo = hi;
+        __threadfence_block();
+        __syncthreads();
+    }
+    return __syncthreads_and(ok_all ? 1 : 0) != 0;
 }
 
 // all roots of day t of the replicas this CTA serves (warp 0 only; no block-wide synchronisation inside)
@@ -1192,6 +1247,331 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
         __threadfence();
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Parallel tracing for the persistent kernel.  The sequential order of the reference only matters between
+// roots whose searches can touch the same agents.  So: (1) all roots of the day grow a union-find forest
+// over the SUPERSET graph of every edge any search order could follow (household edge: draw succeeds, the
+// member is not S and was not documented before today; outside edge: draw succeeds, today's entries
+// included) with a level-synchronous frontier; (2) every connected component elects its smallest root as
+// leader; (3) one warp per component runs the exact ordered search (trace_root, above) over the
+// component's roots in ascending agent order.  Components share no agent, so they run concurrently and the
+// result is the reference's, bit for bit.  Needs grid barriers between the steps: every thread of the grid
+// calls trace_parallel().
+struct TraceCtl {          // per replica
+    uint32_t n_roots, n_reached, alloc, pad;
+};
+
+__device__ __forceinline__ uint32_t uf_find(unsigned long long *comp, uint32_t x, unsigned long long stamp)
+{
+    for (;;) {
+        const uint32_t p = (uint32_t)__ldcg(comp + x);
+        if (p == x) return x;
+        const uint32_t gp = (uint32_t)__ldcg(comp + p);
+        if (gp != p) atomicCAS(comp + x, stamp | p, stamp | gp);  // path halving
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_union(unsigned long long *comp, uint32_t a, uint32_t b, unsigned long long stamp)
+{
+    for (;;) {
+        a = uf_find(comp, a, stamp);
+        b = uf_find(comp, b, stamp);
+        if (a == b) return;
+        if (a < b) { const uint32_t s = a; a = b; b = s; }
+        if (atomicCAS(comp + a, stamp | a, stamp | b) == (stamp | a)) return;  // the larger id hangs under the smaller
+    }
+}
+
+struct TracePar {          // per-replica arrays of the parallel tracer
+    unsigned long long *comp, *lead;   // [n_pad] day<<32 | union-find parent ; day<<32 | smallest root slot of the component
+    uint32_t *reached, *roots, *reps, *csz;  // [n_pad] each: frontier / reached nodes, the day's roots (ascending), their representatives, component sizes
+    TraceCtl *ctl;
+};
+
+// one node of the frontier: evaluate its superset edges with the warp, claim / unite the targets
+__device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const TraceView &tv, const TracePar &tp, TraceSmem &ts,
+                                                      uint32_t c, unsigned long long *total_appended)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = tv.t;
+    const unsigned long long td = (unsigned long long)cx.tday0 + (unsigned long long)t;
+    const unsigned long long stamp = td << 32;
+    const uint32_t *log_head = cx.log_head + (size_t)tv.rep * cx.n_pad;
+    const uint4 *log_ent = cx.log_ent + (size_t)tv.rep * cx.log_cap;
+    const uint16_t stt = __ldg(cx.stat + c);
+    const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
+    const uint32_t base = c - (uint32_t)pos;
+    uint32_t L = 0;
+    if (lane == 0) {
+        uint32_t e = __ldcg(log_head + c);
+        while (e != 0u && L < (uint32_t)kTraceLogCap) {
+            const uint4 en = __ldcg(log_ent + (e - 1u));
+            ts.ent_x[L] = en.x;
+            ts.ent_key[L] = en.z;
+            ++L;
+            e = en.y;
+        }
+    }
+    L = __shfl_sync(0xFFFFFFFFu, L, 0);
+    __syncwarp();
+    const uint32_t n_edges = (uint32_t)(size - 1) + L;
+    for (uint32_t e0 = 0; e0 < n_edges; e0 += 32u) {
+        const uint32_t e = e0 + (uint32_t)lane;
+        bool ok = false;
+        uint32_t target = 0;
+        if (e < (uint32_t)(size - 1)) {
+            const int j = (int)e;
+            target = base + (uint32_t)j + (j >= pos ? 1u : 0u);
+            const unsigned long long w = __ldcg(tv.winner + target);
+            if (w != 0ull && wday(w) != t) {
+                const AgentRec m = load_rec(tv.rec + target);
+                const bool before_today = (m.state() & ST_DOC) != 0 && (int)m.t_documented() != t;
+                if (!before_today) ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_HH, (uint32_t)j), 0) < cx.p_trace_hh;
+            }
+        } else if (e < n_edges) {
+            const uint32_t k = e - (uint32_t)(size - 1);
+            const uint32_t kk = ts.ent_key[k];
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < L; ++q) rank += ts.ent_key[q] < kk ? 1u : 0u;
+            target = ts.ent_x[k];
+            if (rank < (uint32_t)kLogWidth)
+                ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_OUT, rank), 0) < cx.p_trace_out;
+        }
+        bool fresh = false;
+        if (ok) {
+            const unsigned long long old = __ldcg(tp.comp + target);
+            if ((old >> 32) != td && atomicCAS(tp.comp + target, old, stamp | target) == old) {
+                fresh = true;
+                __stcg(tp.lead + target, stamp | 0xFFFFFFFFull);
+            }
+            uf_union(tp.comp, c, target, stamp);
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, fresh);
+        if (m) {
+            uint32_t at = 0;
+            if (lane == 0) {
+                at = atomicAdd(&tp.ctl->n_reached, (uint32_t)__popc(m));
+                atomicAdd(total_appended, (unsigned long long)__popc(m));
+            }
+            at = __shfl_sync(0xFFFFFFFFu, at, 0);
+            if (fresh) __stcg(tp.reached + at + (uint32_t)__popc(m & ((1u << lane) - 1u)), target);
+        }
+        __syncwarp();
+    }
+}
+
+// the day's roots of one replica in ascending agent order (three-level bitmap), by ONE warp; resets the bitmaps
+__device__ __forceinline__ uint32_t trace_collect_roots(const DevCtx &cx, int rep, const TracePar &tp, unsigned long long stamp)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t *bits = cx.rootbits + (size_t)rep * (cx.n_pad / 32);
+    uint32_t *sums = cx.rootsum + (size_t)rep * (cx.n_pad / 1024);
+    const uint32_t n_sum2 = (uint32_t)((cx.n_pad + 32767) / 32768);
+    uint32_t *sums2 = cx.rootsum2 + (size_t)rep * n_sum2;
+    uint32_t R = 0;
+    for (uint32_t s0 = 0; s0 < n_sum2; s0 += 32u) {
+        const uint32_t w2 = s0 + (uint32_t)lane < n_sum2 ? __ldcg(sums2 + s0 + lane) : 0u;
+        unsigned any2 = __ballot_sync(0xFFFFFFFFu, w2 != 0u);
+        while (any2) {
+            const int src2 = __ffs(any2) - 1;
+            any2 &= any2 - 1u;
+            const uint32_t word2 = __shfl_sync(0xFFFFFFFFu, w2, src2);
+            const uint32_t s2idx = s0 + (uint32_t)src2;
+            const uint32_t sidx = s2idx * 32u + (uint32_t)lane;
+            const bool have1 = (word2 >> lane) & 1u;
+            const uint32_t sw = have1 ? __ldcg(sums + sidx) : 0u;
+            unsigned any1 = __ballot_sync(0xFFFFFFFFu, sw != 0u);
+            while (any1) {
+                const int src1 = __ffs(any1) - 1;
+                any1 &= any1 - 1u;
+                const uint32_t word1 = __shfl_sync(0xFFFFFFFFu, sw, src1);
+                const uint32_t widx = (s2idx * 32u + (uint32_t)src1) * 32u + (uint32_t)lane;
+                const bool have0 = (word1 >> lane) & 1u;
+                uint32_t bw = have0 ? __ldcg(bits + widx) : 0u;
+                const uint32_t cnt = (uint32_t)__popc(bw);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                uint32_t at = R + incl - cnt;
+                while (bw) {
+                    const int b = __ffs(bw) - 1;
+                    bw &= bw - 1u;
+                    const uint32_t root = widx * 32u + (uint32_t)b;
+                    __stcg(tp.roots + at, root);
+                    __stcg(tp.reached + at, root);
+                    __stcg(tp.csz + at, 0u);
+                    __stcg(tp.comp + root, stamp | root);
+                    __stcg(tp.lead + root, stamp | 0xFFFFFFFFull);
+                    ++at;
+                }
+                R += tot;
+                if (have0) __stcg(bits + widx, 0u);
+            }
+            if (have1) __stcg(sums + sidx, 0u);
+        }
+        if (w2) __stcg(sums2 + s0 + lane, 0u);
+    }
+    return R;
+}
+
+constexpr int kMaxRepsPerCta = 16;
+constexpr int kBigComponent = 96;  // agents: larger components are searched by a whole CTA
+__device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int t, unsigned int &epoch)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    TraceSmem &ts = reinterpret_cast<TraceSmem *>(sm.out_old)[wib];  // 16 x 4 KB over the pass queues (idle between passes)
+    static_assert(sizeof(TraceSmem) * (kThreads / 32) <= offsetof(PassSmem, tally) - offsetof(PassSmem, out_old),
+                  "the tracing scratch must fit over the pass queues");
+    const int bpr = cx.blocks_per_rep;
+    const int reps_per_sweep = gridDim.x / bpr;
+    const int my_slot = blockIdx.x / bpr, my_part = blockIdx.x % bpr;
+    const bool serving = my_slot < reps_per_sweep;
+    const uint32_t gw = (uint32_t)my_part * (uint32_t)(kThreads / 32) + (uint32_t)wib, ngw = (uint32_t)bpr * (uint32_t)(kThreads / 32);
+    const unsigned long long stamp = ((unsigned long long)cx.tday0 + (unsigned long long)t) << 32;
+    unsigned long long *total = cx.ttotal;
+
+    auto make = [&](int rep, TraceView &tv, TracePar &tp) {
+        tv.rep = rep; tv.t = t; tv.root = 0;
+        tv.seed = cx.seeds[rep];
+        tv.winner = cx.winner + (size_t)rep * cx.n_pad;
+        tv.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+        tv.rec = cx.rec + (size_t)rep * cx.n_pad;
+        tv.trc = cx.trc + (size_t)rep * cx.n_pad;
+        tv.tmark = cx.tmark + (size_t)rep * cx.n_pad;
+        tv.tally_day = cx.tally + ((size_t)rep * cx.T + t) * TAL_ROWS * kAges;
+        tp.comp = cx.tcomp + (size_t)rep * cx.n_pad;
+        tp.lead = cx.tlead + (size_t)rep * cx.n_pad;
+        tp.reached = cx.treached + (size_t)rep * cx.n_pad;
+        tp.roots = cx.troots + (size_t)rep * cx.n_pad;
+        tp.reps = cx.treps + (size_t)rep * cx.n_pad;
+        tp.csz = cx.tcsz + (size_t)rep * cx.n_pad;
+        tp.ctl = cx.tctl + rep;
+    };
+    TraceView tv;
+    TracePar tp;
+
+    // ---- roots
+    if (serving && my_part == 0 && wib == 0) {
+        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+            make(rep, tv, tp);
+            uint32_t R = 0;
+            if (__ldcg(cx.root_cnt + (size_t)rep * (cx.T + 2) + t) != 0u) R = trace_collect_roots(cx, rep, tp, stamp);
+            if (lane == 0) {
+                tp.ctl->n_roots = R;
+                tp.ctl->n_reached = R;
+                tp.ctl->alloc = 0;
+                if (R) atomicAdd(total, (unsigned long long)R);
+            }
+        }
+    }
+    grid_barrier(cx.barrier, ++epoch * gridDim.x);
+
+    // ---- union-find over the superset graph, level by level
+    uint32_t lo[kMaxRepsPerCta];
+#pragma unroll
+    for (int k = 0; k < kMaxRepsPerCta; ++k) lo[k] = 0;
+    unsigned long long prev_total = __ldcg(total);
+    for (;;) {
+        if (serving) {
+            int k = 0;
+            for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
+                make(rep, tv, tp);
+                const uint32_t hi = __ldcg(&tp.ctl->n_reached);
+                for (uint32_t idx = lo[k] + gw; idx < hi; idx += ngw)
+                    trace_expand_superset(cx, tv, tp, ts, __ldcg(tp.reached + idx), total);
+                lo[k] = hi;
+            }
+        }
+        grid_barrier(cx.barrier, ++epoch * gridDim.x);
+        const unsigned long long now = __ldcg(total);
+        if (now == prev_total) break;
+        prev_total = now;
+    }
+
+    // ---- representatives of the roots, leader (smallest root slot) of every component
+    if (serving) {
+        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+            make(rep, tv, tp);
+            const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            for (uint32_t k = gw * 32u + (uint32_t)lane; k < R; k += ngw * 32u) {
+                const uint32_t rp = uf_find(tp.comp, __ldcg(tp.roots + k), stamp);
+                __stcg(tp.reps + k, rp);
+                atomicMin(tp.lead + rp, stamp | k);
+            }
+        }
+    }
+    grid_barrier(cx.barrier, ++epoch * gridDim.x);
+    // ---- component sizes (the capacity of the leader's search stack)
+    if (serving) {
+        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+            make(rep, tv, tp);
+            const uint32_t NR = __ldcg(&tp.ctl->n_reached);
+            for (uint32_t idx = gw * 32u + (uint32_t)lane; idx < NR; idx += ngw * 32u) {
+                const uint32_t L = (uint32_t)__ldcg(tp.lead + uf_find(tp.comp, __ldcg(tp.reached + idx), stamp));
+                atomicAdd(tp.csz + L, 1u);
+            }
+        }
+    }
+    grid_barrier(cx.barrier, ++epoch * gridDim.x);
+    // ---- every component: its roots in ascending order -- by one warp, or by a whole CTA when the component is large
+    if (serving) {
+        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+            make(rep, tv, tp);
+            const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            bool ok = true;
+            for (uint32_t k = gw; k < R; k += ngw) {
+                const uint32_t rp = __ldcg(tp.reps + k);
+                if ((uint32_t)__ldcg(tp.lead + rp) != k) continue;
+                const uint32_t cap = __ldcg(tp.csz + k);
+                if (cap > (uint32_t)kBigComponent) continue;  // left to the CTA pass below
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&tp.ctl->alloc, cap);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                uint32_t *list = cx.tstack + (size_t)rep * cx.n_pad + base;
+                for (uint32_t j0 = k; j0 < R; j0 += 32u) {
+                    const uint32_t j = j0 + (uint32_t)lane;
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, j < R && __ldcg(tp.reps + (j < R ? j : k)) == rp);
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1u;
+                        tv.root = __ldcg(tp.roots + j0 + (uint32_t)b);
+                        ok = trace_root(cx, tv, ts, list, cap) && ok;
+                    }
+                }
+            }
+            if (!ok && lane == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull);
+        }
+    }
+    __syncthreads();
+    if (serving) {
+        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+            make(rep, tv, tp);
+            const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            bool ok = true;
+            for (uint32_t k = (uint32_t)my_part; k < R; k += (uint32_t)bpr) {  // (CTA-uniform)
+                const uint32_t rp = __ldcg(tp.reps + k);
+                if ((uint32_t)__ldcg(tp.lead + rp) != k) continue;
+                const uint32_t cap = __ldcg(tp.csz + k);
+                if (cap <= (uint32_t)kBigComponent) continue;
+                if (tid == 0) sm.base_new = atomicAdd(&tp.ctl->alloc, cap);
+                __syncthreads();
+                uint32_t *list = cx.tstack + (size_t)rep * cx.n_pad + sm.base_new;
+                for (uint32_t j = k; j < R; ++j) {
+                    if (__ldcg(tp.reps + j) != rp) continue;
+                    tv.root = __ldcg(tp.roots + j);
+                    ok = trace_root_cta(cx, tv, ts, list, cap, &sm.base_old) && ok;
+                }
+                __syncthreads();
+            }
+            if (!ok && tid == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull);
+        }
+    }
 }
 
 // Barrier over all CTAs of all GPUs of a sharded run.  Local arrival as above (each CTA fences at system
