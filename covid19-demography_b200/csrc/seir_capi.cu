@@ -15,6 +15,7 @@ using namespace seir;
 // ------------------------------------------------------------------ kernels
 extern __shared__ __align__(16) unsigned char seir_smem_raw[];
 
+template <bool TR>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(const __grid_constant__ DevCtx cx)
 {
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     }
     for (int t = 1; t <= cx.T; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
-        day_pass(cx, sm, t);
+        Pass<TR>::day_pass(cx, sm, t);
         if (t < cx.T) {
             if (cx.n_shards > 1) {
                 ++epoch;
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
                 continue;  // (tracing is not available in sharded runs)
             }
             grid_barrier(cx.barrier, ++epoch * gridDim.x);
-            if (cx.trace_from >= 1 && t >= cx.trace_from) {  // :241-242 tracing is on: resolve the day's traces
+            if (TR && cx.trace_from >= 1 && t >= cx.trace_from) {  // :241-242 tracing is on: resolve the day's traces
                 bool any = false;  // (grid-uniform: the counts are final after the barrier)
                 for (int r = 0; r < cx.n_rep; ++r) any = any || __ldcg(cx.root_cnt + (size_t)r * (cx.T + 2) + t) != 0u;
                 if (any) {
@@ -49,12 +50,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[cx.T + 1] = global_timer_ns();
 }
 
+template <bool TR>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __grid_constant__ DevCtx cx, int t)
 {
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
     stage_tables(cx, sm);
-    day_pass(cx, sm, t);
+    Pass<TR>::day_pass(cx, sm, t);
 }
 
 // contact tracing of day t as its own launch (per-day launch mode)
@@ -679,15 +681,20 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         if (upload_tables(h, tables)) break;
         // persistent grid: every CTA must be co-resident
         int occ = 0;
-        if (cudaFuncSetAttribute(seir_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
-            cudaFuncSetAttribute(seir_day_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess) {
+        if (cudaFuncSetAttribute(seir_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_day_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_day_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess) {
             fail("cannot reserve shared memory for the day-step kernels");
             break;
         }
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel, kThreads, sizeof(PassSmem)) != cudaSuccess || occ < 1) {
+        int occ_t = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel<false>, kThreads, sizeof(PassSmem)) != cudaSuccess || occ < 1 ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, seir_persistent_kernel<true>, kThreads, sizeof(PassSmem)) != cudaSuccess || occ_t < 1) {
             fail("occupancy query failed for seir_persistent_kernel");
             break;
         }
+        if (occ_t < occ) occ = occ_t;  // one grid size for both instantiations
         h->occ = occ;
         h->grid = h->sms * occ;
         fill_ctx(h);
@@ -837,11 +844,13 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaEventRecord(h->ev1, h->stream));
     if (h->prm.launch == SEIR_LAUNCH_PERSISTENT) {
         void *args[] = {&h->cx};
-        CK(cudaLaunchCooperativeKernel((const void *)seir_persistent_kernel, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
+        const void *fn = tracing ? (const void *)seir_persistent_kernel<true> : (const void *)seir_persistent_kernel<false>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
         ++h->launches;
     } else {
         for (int t = 1; t <= h->prm.T; ++t) {
-            seir_day_kernel<<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
+            if (tracing) seir_day_kernel<true><<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
+            else seir_day_kernel<false><<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
             ++h->launches;
             if (tracing && t >= h->cx.trace_from && t < h->prm.T) {
                 seir_trace_kernel<<<R < h->grid ? R : h->grid, 32, sizeof(TraceSmem), h->stream>>>(h->cx, t);

@@ -377,8 +377,11 @@ template <class F> __device__ __forceinline__ void for_items(uint32_t n, F f)
         if (mine) f(q);
 }
 
+// Everything below exists twice: Pass<false> for runs in which contact tracing can never switch on (no
+// outside-infection log, no root bitmap -- and none of their registers), Pass<true> for the others.
+template <bool TR> struct Pass {
 // owner of agent c in a sharded run
-__device__ __forceinline__ int owner_of(const DevCtx &cx, uint32_t c)
+static __device__ __forceinline__ int owner_of(const DevCtx &cx, uint32_t c)
 {
     int g = 0;
     while (g + 1 < cx.n_shards && c >= cx.shard_lo[g + 1]) ++g;
@@ -386,7 +389,7 @@ __device__ __forceinline__ int owner_of(const DevCtx &cx, uint32_t c)
 }
 
 // ---- stage H: one successful transmission slot's agent -> c on day t (:347-359 / :376-390) ----------
-__device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
+static __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
                                             int age_c, int t)
 {
     const RepView &v = sm.v;
@@ -418,7 +421,7 @@ __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_
         else atomicOr(v.inbox + (c >> 4), bits);
     }
     atomicAdd(&sm.hit_n[slot], ord >= 16u ? 0x10001u : 1u);  // ord >= 16: community (:386-388)
-    if (cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387); k follows from (day, ordinal) when the log is read
+    if (TR && cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387); k follows from (day, ordinal) when the log is read
         const uint32_t e = atomicAdd(cx.log_cnt + v.rep, 1u);
         if (e < cx.log_cap) {
             const uint32_t prev = atomicExch(cx.log_head + (size_t)v.rep * cx.n_pad + i, e + 1u);
@@ -429,7 +432,7 @@ __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, uint32_
     }
 }
 
-__device__ __forceinline__ void push_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
+static __device__ __forceinline__ void push_hit(const DevCtx &cx, PassSmem &sm, uint32_t c, uint32_t meta,
                                          int age_c, int t)
 {
     const uint32_t pos = atomicAdd(&sm.n_hit, 1u);
@@ -443,7 +446,7 @@ __device__ __forceinline__ void push_hit(const DevCtx &cx, PassSmem &sm, uint32_
 }
 
 // ---- stage C: one candidate contact of slot's agent (:373-375) ---------------------------------------
-__device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
+static __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
     const RepView &v = sm.v;
     const uint32_t slot = item >> 16, payload = item & 0xFFFFu;
@@ -480,7 +483,7 @@ __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &sm, uin
         push_hit(cx, sm, c, (slot << 16) | ord, a, t);
 }
 
-__device__ __forceinline__ void push_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
+static __device__ __forceinline__ void push_contact(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
     const uint32_t pos = atomicAdd(&sm.n_con, 1u);
     if (pos < (uint32_t)kConCap) sm.conq[pos] = item;
@@ -488,7 +491,7 @@ __device__ __forceinline__ void push_contact(const DevCtx &cx, PassSmem &sm, uin
 }
 
 // ---- stage D: one draw item ---------------------------------------------------------------------------
-__device__ __noinline__ void process_draw_item(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
+static __device__ __noinline__ void process_draw_item(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
     const RepView &v = sm.v;
     const uint32_t slot = item >> 16, kind = (item >> 14) & 3u, payload = item & 0x3FFFu;
@@ -526,7 +529,7 @@ __device__ __noinline__ void process_draw_item(const DevCtx &cx, PassSmem &sm, u
     }
 }
 
-__device__ __forceinline__ void push_draw(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
+static __device__ __forceinline__ void push_draw(const DevCtx &cx, PassSmem &sm, uint32_t item, int t)
 {
 #if SEIR_QUEUE_DRAWS
     const uint32_t pos = atomicAdd(&sm.n_draw, 1u);
@@ -537,7 +540,7 @@ __device__ __forceinline__ void push_draw(const DevCtx &cx, PassSmem &sm, uint32
 #endif
 }
 
-__device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm, uint32_t i, int t, AgentRec &r)
+static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm, uint32_t i, int t, AgentRec &r)
 {
     const RepView &v = sm.v;
     // infected on day t-1 by the winner of that day's hits (:347-356)
@@ -566,7 +569,7 @@ __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm,
 }
 
 // the progression events of the agent's own day (:256-272, :291-311, :312-321)
-__device__ __forceinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
+static __device__ __forceinline__ void progression_events(const DevCtx &cx, const PassSmem &sm, uint64_t seed, uint32_t i, int t,
                                                 AgentRec &r, int comp, int &ncomp, bool &nq, bool &ndoc, bool &root)
 {
     const uint16_t stt = r.stat();
@@ -624,7 +627,7 @@ __device__ __forceinline__ void progression_events(const DevCtx &cx, const PassS
 // Returns DAY_KEEP if the agent stays on the active list.
 enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_DEFER = 2 };
 template <bool IN_EV>
-__device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i, AgentRec &r,
+static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i, AgentRec &r,
                                          bool dirty, int t)
 {
     const RepView &v = sm.v;
@@ -661,7 +664,7 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
             if (sd_lane(db, 0) < cx.p_doc) {
                 ndoc = true;
                 root = true;
-                if (v.tracing) nq = true;  // :287-288
+                if (TR && v.tracing) nq = true;  // :287-288
                 r.set_t_documented((uint16_t)t);
             }
         }
@@ -674,7 +677,7 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
             atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], 1u);
         }
         if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], 1u);
-        if (root && v.tracing) {
+        if (TR && root && v.tracing) {
             atomicOr(cx.rootbits + (size_t)v.rep * (cx.n_pad / 32) + (i >> 5), 1u << (i & 31));
             atomicOr(cx.rootsum + (size_t)v.rep * (cx.n_pad / 1024) + (i >> 10), 1u << ((i >> 5) & 31));
             atomicOr(cx.rootsum2 + (size_t)v.rep * ((cx.n_pad + 32767) / 32768) + (i >> 15), 1u << ((i >> 10) & 31));
@@ -727,7 +730,7 @@ __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_
 }
 
 // ---- stage A: one list entry -----------------------------------------------------------------------------
-__device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i,
+static __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i,
                                              bool is_new, int t, bool finalize)
 {
     const RepView &v = sm.v;
@@ -756,7 +759,7 @@ __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &sm, uin
 }
 
 // survivors re-append themselves to tomorrow's list: one shared-memory atomic per warp
-__device__ __forceinline__ void append_survivors(PassSmem &sm, bool keep, uint32_t i)
+static __device__ __forceinline__ void append_survivors(PassSmem &sm, bool keep, uint32_t i)
 {
     const RepView &v = sm.v;
     const int lane = threadIdx.x & 31;
@@ -778,7 +781,7 @@ __device__ __forceinline__ void append_survivors(PassSmem &sm, bool keep, uint32
 // replica split its list: a list shorter than the replica's threads is dealt S threads apart (one entry
 // per warp while it fits), a longer one in equal contiguous chunks, kPerThread entries per thread and round.
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
-__device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
+static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
@@ -979,6 +982,8 @@ __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
         SEIR_STAMP(7);
     }
 }
+
+};  // struct Pass
 
 // ---------------------------------------------------------------------------------------
 // Contact tracing of day t (do_contact_tracing, seir_individual.py:60-88), after the day's transmission is
