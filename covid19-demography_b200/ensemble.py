@@ -29,10 +29,11 @@ def batches(items, batch):
 
 
 def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fraction, want_vectors=(),
-              want_cohorts=False):
+              want_cohorts=False, fast_prologue=False):
     """Run `seeds` on `engine` (an engine.Engine with R replica slots) in batches of R.
 
     Per seed the reference's own prologue picks are used (`tables.prologue`, seir_individual.py:176-187).
+    `fast_prologue` swaps in `tables.prologue_fast` (same distributions, O(picks) instead of two O(n) permutations).
     A short last batch is padded by repeating its last seed (the padding runs are discarded).
     Returns {"tallies": int64[len(seeds), T, 9, 101], "counters": [dict], "vectors": {name: float64[len(seeds), n]},
     "cohorts": int64[len(seeds), T, 4, 101] (with want_cohorts)}.
@@ -46,7 +47,8 @@ def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fr
     done = 0
     for chunk in batches(list(seeds), R):
         padded = chunk + [chunk[-1]] * (R - len(chunk))
-        pro = [_tables.prologue(s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in padded]
+        pick = _tables.prologue_fast if fast_prologue else _tables.prologue
+        pro = [pick(s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in padded]
         engine.run(padded, [p[0] for p in pro], [p[1] for p in pro])
         for r in range(len(chunk)):
             tallies[done + r] = engine.tallies(r)

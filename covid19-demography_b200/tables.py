@@ -106,6 +106,24 @@ def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_facto
     return out
 
 
+def prologue_fast(seed, age_groups, n, fraction_stay_home, initial_infected_fraction):
+    """The prologue's picks (seir_individual.py:176-187) from the same distributions -- per age a uniform
+    subset of int(fraction * size) agents shelters at home, int(fraction * n) uniform agents are the initial
+    cases -- but from NumPy's PCG64 generator in O(picks) instead of replaying the reference's Mersenne-Twister
+    stream (two full permutations, about 0.3 s per seed at n = 10 M).  For ensembles and sweeps, where the
+    host prologue would otherwise cost thirty times the device run; NOT the reference's picks for that seed."""
+    rng = np.random.default_rng([int(seed) & 0xFFFFFFFF, 0x5E1B200])
+    home = np.zeros(n, dtype=np.bool_)
+    fsh = np.asarray(fraction_stay_home, dtype=np.float64)
+    for a, matches in enumerate(age_groups):
+        k = int(fsh[a] * len(matches))
+        if k > 0:
+            home[np.asarray(matches)[rng.choice(len(matches), size=k, replace=False)]] = True
+    k0 = int(initial_infected_fraction * n)
+    init = rng.choice(n, size=k0, replace=False).astype(np.int64) if k0 > 0 else np.zeros(0, dtype=np.int64)
+    return home, init
+
+
 def prologue(seed, age_groups, n, fraction_stay_home, initial_infected_fraction):
     """Host restatement of the run_model prologue (seir_individual.py:163,176-187).
 

@@ -117,3 +117,15 @@ def test_history_plane_indexing_matches_numpy():
     assert np.array_equal(X[1:4], e.full[1:4]) and len(X) == 7
     with pytest.raises(IndexError):
         X[7]
+
+
+def test_fast_prologue_draws_the_same_counts():
+    c = util.Case("italy_policy")
+    home_ref, init_ref = tables.prologue(5, c.age_groups, c.n, c.fraction_stay_home, 0.004)
+    home, init = tables.prologue_fast(5, c.age_groups, c.n, c.fraction_stay_home, 0.004)
+    assert len(init) == len(init_ref) == int(0.004 * c.n) and len(set(init.tolist())) == len(init)
+    for a, g in enumerate(c.age_groups):
+        assert home[g].sum() == home_ref[g].sum() == int(c.fraction_stay_home[a] * len(g))
+    h2, i2 = tables.prologue_fast(5, c.age_groups, c.n, c.fraction_stay_home, 0.004)
+    assert np.array_equal(home, h2) and np.array_equal(init, i2)
+    assert not np.array_equal(tables.prologue_fast(6, c.age_groups, c.n, c.fraction_stay_home, 0.004)[1], init)
