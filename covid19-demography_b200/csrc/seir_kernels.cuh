@@ -291,9 +291,12 @@ __device__ __noinline__ uint32_t poisson_ni(uint64_t seed, uint32_t agent, uint3
 #endif
 constexpr int kPerThread = SEIR_ENTRIES_PER_THREAD;  // list entries a thread takes through stage A per round
 constexpr int kSlots = kPerThread * kThreads;        // agents per round and CTA
-constexpr int kConCap = kSlots;                      // contact queue entries per round
-constexpr int kHitCap = kSlots / 2;                  // hit queue entries per round
-constexpr int kDrawCap = 2 * kSlots;                 // draw-item queue entries per round
+#ifndef SEIR_QUEUE_DIV
+#define SEIR_QUEUE_DIV 1   // (tests: shrink the queues so that their overflow paths run on small populations)
+#endif
+constexpr int kConCap = kSlots / SEIR_QUEUE_DIV;                      // contact queue entries per round
+constexpr int kHitCap = kSlots / 2 / SEIR_QUEUE_DIV;                  // hit queue entries per round
+constexpr int kDrawCap = 2 * kSlots / SEIR_QUEUE_DIV;                 // draw-item queue entries per round
 #ifndef SEIR_QUEUE_EVENTS
 #define SEIR_QUEUE_EVENTS 0   // 1: progression events run compacted in stage E; 0: in place in stage A (measured faster on C2)
 #endif

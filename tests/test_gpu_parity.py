@@ -146,6 +146,41 @@ def test_tracing_off_is_the_papers_semantics(gpu_engine_module):
     eng.close()
 
 
+def test_per_agent_household_infectiousness(gpu_engine_module):
+    """p_infect_household is a per-agent vector in the reference's signature (:108); the drivers pass a constant
+    one (detected and kept as a scalar), a varying one takes the vector path."""
+    c = util.Case("italy_seeded")
+    rng = np.random.default_rng(11)
+    c.p_infect_household = rng.uniform(0.0, 0.25, size=c.n)
+    params = c.no_tracing_params()
+    for mode in ("native", "replay"):
+        tup, ex, home, init = c.keyed_oracle(mode, params)
+        eng = c.gpu_engine(gpu_engine_module, params, mode)
+        eng.run([c.seed], [home], [init])
+        _compare(eng, tup, ex, c, int(params["T"]))
+        eng.close()
+
+
+def test_degenerate_runs(gpu_engine_module):
+    """No initial case: everybody stays S.  T = 2: one day.  Everybody infected at t = 0."""
+    c = util.Case("italy_default")
+    params = c.no_tracing_params(initial_infected_fraction=0.0)
+    tup, ex, home, init = c.keyed_oracle("native", params)
+    assert len(init) == 0
+    eng = c.gpu_engine(gpu_engine_module, params, "native")
+    eng.run([c.seed], [home], [init])
+    _compare(eng, tup, ex, c, int(params["T"]))
+    assert eng.tallies()[:, 0].sum(axis=1).tolist() == [c.n] * int(params["T"])
+    eng.close()
+    for over in ({"T": 2.0, "initial_infected_fraction": 0.05}, {"T": 12.0, "initial_infected_fraction": 1.0}):
+        params = c.no_tracing_params(**over)
+        tup, ex, home, init = c.keyed_oracle("native", params)
+        eng = c.gpu_engine(gpu_engine_module, params, "native")
+        eng.run([c.seed], [home], [init])
+        _compare(eng, tup, ex, c, int(params["T"]))
+        eng.close()
+
+
 def test_bad_inputs_raise(gpu_engine_module):
     c = util.Case("italy_default")
     params = c.no_tracing_params()
