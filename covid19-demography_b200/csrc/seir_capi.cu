@@ -104,7 +104,7 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
         store_rec(cx.rec + (size_t)rep * cx.n_pad + a, r);
         cx.winner[(size_t)rep * cx.n_pad + a] = 1ull;  // day 0, never susceptible again
         atomicOr(cx.inbox + (size_t)rep * (cx.n_pad / 16) + (a >> 4), inbox_infected_bit((int)(a & 15)));
-        cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + atomicAdd(cx.list_cnt + (size_t)rep * 2 * (cx.T + 2) + 1, 1u)] = (uint32_t)a;
+        cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + atomicAdd(cx.list_cnt + (size_t)rep * 3 * (cx.T + 2) + 1, 1u)] = (uint32_t)a;
         atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat() & 127), 1u);
     }
 }
@@ -494,7 +494,7 @@ static int alloc_state(seir_handle *h)
     }
     CK(h->hist.alloc(R * T * np));
     CK(h->tally.alloc(R * T * TAL_ROWS * kAges));
-    CK(h->list_cnt.alloc(R * 2 * (T + 2)));
+    CK(h->list_cnt.alloc(R * 3 * (T + 2)));
     CK(h->day_ns.alloc(T + 2));
     CK(cudaMemset(h->day_ns.p, 0, (T + 2) * 8));
     CK(h->fine_ns.alloc((T + 2) * 16));
@@ -817,7 +817,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaMemsetAsync(h->tally.p, 0, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, h->stream));
     CK(cudaMemsetAsync(h->counters.p, 0, (size_t)R * 4 * 8, h->stream));
     CK(cudaMemsetAsync(h->barrier.p, 0, 4, h->stream));
-    CK(cudaMemsetAsync(h->list_cnt.p, 0, (size_t)R * 2 * (h->prm.T + 2) * 4, h->stream));
+    CK(cudaMemsetAsync(h->list_cnt.p, 0, (size_t)R * 3 * (h->prm.T + 2) * 4, h->stream));
     const bool tracing = h->cx.trace_from >= 1;
     if (tracing) {
         CK(cudaMemsetAsync(h->log_cnt.p, 0, (size_t)R * 4, h->stream));

@@ -141,9 +141,10 @@ struct DevCtx {
     uint32_t *inbox;               // [rep][n_pad/16]
     unsigned long long *winner;    // [rep][n_pad]
     AgentRec *rec;                 // [rep][n_pad]
-    uint32_t *list_old;            // [rep][2][n_pad]  agents that were active yesterday and still are
+    uint32_t *list_old;            // [rep][2][n_pad]  agents that were active yesterday and still are: the ones that may
+                                   //                  transmit from the front, the quarantined ones from the back
     uint32_t *list_new;            // [rep][2][n_pad]  agents infected yesterday (record not built yet)
-    uint32_t *list_cnt;            // [rep][2][T+2]    entries of the old / new list consumed by pass t
+    uint32_t *list_cnt;            // [rep][3][T+2]    entries of the old (transmitting) / new / old (quarantined) list consumed by pass t
     uint32_t *tally;               // [rep][T][TAL_ROWS][101]
     const uint32_t *home;          // [rep][n_pad/32] bitmap of Home_real
     const uint64_t *seeds;         // [rep]
@@ -313,7 +314,8 @@ struct RepView {
     AgentRec *rec;
     const uint32_t *home;
     uint32_t *next_old, *next_new;          // tomorrow's lists
-    uint32_t *next_old_cnt, *next_new_cnt;
+    uint32_t *next_old_cnt, *next_new_cnt, *next_oldq_cnt;
+    uint32_t n_pad_m1;                      // the quarantined survivors fill tomorrow's old list from index n_pad - 1 downwards
     uint64_t seed;
     bool home_on;
     int phase;
@@ -345,7 +347,7 @@ struct __align__(16) PassSmem {
     double nat_enlam[2 * kAges * 2];
     int32_t grp_off[kAges + 1];
     uint32_t cnt[4];
-    uint32_t n_old, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_new, next_group;
+    uint32_t n_old, n_oldq, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_oldq, base_new, next_group;
 };
 
 __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
@@ -628,7 +630,7 @@ static __device__ __forceinline__ void progression_events(const DevCtx &cx, cons
 //                (returns DAY_DEFER); everything else is finished here.
 // IN_EV = true : stage E, the same statements with the event.
 // Returns DAY_KEEP if the agent stays on the active list.
-enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_DEFER = 2 };
+enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_DEFER = 2, DAY_KEEP_Q = 3 };  // KEEP_Q: stays active and is quarantined
 template <bool IN_EV>
 static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i, AgentRec &r,
                                          bool dirty, int t)
@@ -729,7 +731,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
             if (bits) push_draw(cx, sm, (slot << 16) | (DQ_HH << 14) | (jb << 2) | bits, t);
         }
     }
-    return (ncomp >= C_E && ncomp <= C_CRIT) ? DAY_KEEP : DAY_DROP;
+    return (ncomp >= C_E && ncomp <= C_CRIT) ? (nq ? DAY_KEEP_Q : DAY_KEEP) : DAY_DROP;
 }
 
 // ---- stage A: one list entry -----------------------------------------------------------------------------
@@ -761,21 +763,54 @@ static __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &
     return agent_day<SEIR_QUEUE_EVENTS == 0>(cx, sm, slot, i, r, dirty, t);
 }
 
-// survivors re-append themselves to tomorrow's list: one shared-memory atomic per warp
-static __device__ __forceinline__ void append_survivors(PassSmem &sm, bool keep, uint32_t i)
+// survivors re-append themselves to tomorrow's list -- the quarantined ones (no transmission: a short path) apart
+// from the ones that may transmit, so that tomorrow's warps are homogeneous; one shared-memory atomic per warp and class
+static constexpr int kOutHalf = kOutOld / 2;
+static __device__ __forceinline__ void append_survivors(PassSmem &sm, int keep, uint32_t i)
 {
     const RepView &v = sm.v;
     const int lane = threadIdx.x & 31;
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-    if (m) {
+    const unsigned mt = __ballot_sync(0xFFFFFFFFu, keep == DAY_KEEP), mq = __ballot_sync(0xFFFFFFFFu, keep == DAY_KEEP_Q);
+    if (mt) {
         uint32_t base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&sm.n_old, (uint32_t)__popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-        if (keep) {
-            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-            if (pos < (uint32_t)kOutOld) sm.out_old[pos] = i;
+        if (lane == __ffs(mt) - 1) base = atomicAdd(&sm.n_old, (uint32_t)__popc(mt));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mt) - 1);
+        if (keep == DAY_KEEP) {
+            const uint32_t pos = base + __popc(mt & ((1u << lane) - 1u));
+            if (pos < (uint32_t)kOutHalf) sm.out_old[pos] = i;
             else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
         }
+    }
+    if (mq) {
+        uint32_t base = 0;
+        if (lane == __ffs(mq) - 1) base = atomicAdd(&sm.n_oldq, (uint32_t)__popc(mq));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mq) - 1);
+        if (keep == DAY_KEEP_Q) {
+            const uint32_t pos = base + __popc(mq & ((1u << lane) - 1u));
+            if (pos < (uint32_t)kOutHalf) sm.out_old[kOutHalf + pos] = i;
+            else v.next_old[v.n_pad_m1 - atomicAdd(v.next_oldq_cnt, 1u)] = i;
+        }
+    }
+}
+
+// both staging halves to tomorrow's list (the whole CTA; ends with the staging counters reset)
+static __device__ __forceinline__ void flush_survivors(PassSmem &sm)
+{
+    const RepView &v = sm.v;
+    const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
+    const uint32_t sq = sm.n_oldq < (uint32_t)kOutHalf ? sm.n_oldq : (uint32_t)kOutHalf;
+    __syncthreads();
+    if (so | sq) {
+        if (threadIdx.x == 0) {
+            if (so) sm.base_old = atomicAdd(v.next_old_cnt, so);
+            if (sq) sm.base_oldq = atomicAdd(v.next_oldq_cnt, sq);
+            sm.n_old = 0;
+            sm.n_oldq = 0;
+        }
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
+        for (uint32_t k = threadIdx.x; k < sq; k += kThreads) v.next_old[v.n_pad_m1 - (sm.base_oldq + k)] = sm.out_old[kOutHalf + k];
+        __syncthreads();
     }
 }
 
@@ -795,7 +830,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
     // (CTAs beyond the last full group idle through the pass; they must still reach the grid barrier)
     for (int rep = my_slot; rep < cx.n_rep && my_slot < reps_per_sweep; rep += reps_per_sweep) {
         const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
-        uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 2 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2);
+        uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_oldq = cnt_new + (cx.T + 2);
         const RepView &v = sm.v;
         if (tid == 0) {
             sm.v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
@@ -806,6 +841,8 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             sm.v.next_new = cx.list_new + lrow;
             sm.v.next_old_cnt = cnt_old + (t + 1);
             sm.v.next_new_cnt = cnt_new + (t + 1);
+            sm.v.next_oldq_cnt = cnt_oldq + (t + 1);
+            sm.v.n_pad_m1 = (uint32_t)(cx.n_pad - 1);
             sm.v.seed = cx.seeds[rep];
             sm.v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;          // :243-244
             sm.v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
@@ -813,8 +850,11 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             sm.v.tracing = cx.trace_from >= 1 && t >= cx.trace_from;          // :241-242
         }
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
-        const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t);
-        const uint32_t count = n_new + n_old;  // new infectees first: their record build stays convergent
+        const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t), n_oldq = __ldcg(cnt_oldq + t);
+        // three segments, each starting on a multiple of 32: new infectees (their record build is the longest path),
+        // agents that may transmit, quarantined agents -- a warp of a dense day serves one kind
+        const uint32_t o_t = (n_new + 31u) & ~31u, o_q = o_t + ((n_old + 31u) & ~31u);
+        const uint32_t count = o_q + n_oldq;
         // this CTA's share of the list: groups of G = 32/S entries (one entry per group while the list is
         // shorter than the replica's warps: a warp pays for every divergent path of its lanes), dealt round-robin
         // to the replica's CTAs (the new infectees, whose record build is the longest path, lead the list: a
@@ -827,7 +867,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
 
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
         if (tid < 4) sm.cnt[tid] = 0;
-        if (tid == 0) { sm.n_old = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
+        if (tid == 0) { sm.n_old = 0; sm.n_oldq = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
         __syncthreads();
         SEIR_STAMP(0);
 
@@ -845,16 +885,16 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 if (k >= g_hi) break;
                 const uint32_t lane = (uint32_t)tid & 31u;
                 const uint32_t e = (k * (uint32_t)bpr + (uint32_t)my_part) * G + lane;
-                const bool has = lane < G && e < count;
+                const bool is_new = e < n_new, is_t = e >= o_t && e - o_t < n_old, is_q = e >= o_q && e - o_q < n_oldq;
+                const bool has = lane < G && (is_new || is_t || is_q);
                 const uint32_t slot = (k - g_lo) * 32u + lane;
                 int keep = DAY_DROP;
                 uint32_t i = 0;
-                const bool is_new = e < n_new;
                 if (has) {
-                    i = is_new ? __ldcg(cur_new + e) : __ldcg(cur_old + (e - n_new));
+                    i = is_new ? __ldcg(cur_new + e) : is_t ? __ldcg(cur_old + (e - o_t)) : __ldcg(cur_old + (sm.v.n_pad_m1 - (e - o_q)));
                     keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
                 }
-                append_survivors(sm, keep == DAY_KEEP, i);
+                append_survivors(sm, keep, i);
                 const unsigned hm = __ballot_sync(0xFFFFFFFFu, has), nm = __ballot_sync(0xFFFFFFFFu, has && is_new);
                 if (lane == 0 && hm) {
                     atomicAdd(&sm.cnt[0], (uint32_t)__popc(hm));
@@ -877,7 +917,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                         AgentRec r = load_rec(v.rec + i);
                         keep = agent_day<true>(cx, sm, slot, i, r, false, t);
                     }
-                    append_survivors(sm, keep == DAY_KEEP, i);
+                    append_survivors(sm, keep, i);
                 }
                 __syncthreads();
             }
@@ -927,24 +967,16 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 }
             }
             __syncthreads();
-            // flush the staging buffers when the next round could overflow them
+            // more rounds follow: empty the staging buffers
             if (round + 1u < rounds) {
-                const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
+                flush_survivors(sm);
                 const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
-                const bool fo = so > (uint32_t)(kOutOld - kSlots), fn = sn > (uint32_t)(kOutNew - kHitCap);
-                if (fo || fn) {
-                    if (tid == 0) {
-                        if (fo) sm.base_old = atomicAdd(v.next_old_cnt, so);
-                        if (fn) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
-                    }
+                if (sn > (uint32_t)(kOutNew - kHitCap)) {
+                    if (tid == 0) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
                     __syncthreads();
-                    if (fo) for (uint32_t k = tid; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
-                    if (fn) for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
+                    for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
                     __syncthreads();
-                    if (tid == 0) {
-                        if (fo) sm.n_old = 0;
-                        if (fn) sm.n_new = 0;
-                    }
+                    if (tid == 0) sm.n_new = 0;
                 }
                 if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
                 __syncthreads();
@@ -953,16 +985,12 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             stamped = true;
         }
         stamped = false;
+        flush_survivors(sm);
         {
-            const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
             const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
-            if (so | sn) {
-                if (tid == 0) {
-                    if (so) sm.base_old = atomicAdd(v.next_old_cnt, so);
-                    if (sn) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
-                }
+            if (sn) {
+                if (tid == 0) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
                 __syncthreads();
-                for (uint32_t k = tid; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
                 for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
             }
         }
