@@ -188,7 +188,9 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     T = 60
-    n_sample = args.cpu_sample if args.cpu_sample > 0 else 10_000_000  # the full C2 population per run
+    # a bounded sample of the workload per step: every worker runs ONE simulation of 4 M agents (C2 parameters, the same
+    # 5 initial cases); --cpu-sample 10000000 times the full C2 population (about 22 s per step on 16 cores)
+    n_sample = args.cpu_sample if args.cpu_sample > 0 else 4_000_000
     cores = len(os.sched_getaffinity(0))
     workers = max(1, min(cores, int(_mem_available() * 0.6 / _bytes_per_run(n_sample, T)), args.cpu_workers or 32))
     ctx = mp.get_context("fork")
@@ -207,8 +209,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": {"workload": "C2 Lombardy-like 10M agents, T=60, lockdown day 46 (/10), single seed per GPU",
-                       "sample": sample},
+            "config": {"workload": "C2 Lombardy-like 10000000 agents, T=60, lockdown day 46 (/10), 1 seed(s) per GPU, "
+                                   "tracing never switches on", "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -314,6 +316,7 @@ def run_gpu_arm(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         balg, a_sum, i_sum = algorithmic_bytes(last_tal, n)
+        init_ms, _, mat_ms = eng.last_run_ms3()  # (last step)
         kern_s = loop_ms_local / args.steps / 1e3
         achieved = balg * R / kern_s / 1e9
         line = {
@@ -338,7 +341,13 @@ def run_gpu_arm(args):
                          "traffic": args.traffic if args.traffic is not None else measured_traffic("seir_persistent_kernel"),
                          "kernel": "seir_persistent_kernel" if args.launch == "persistent" else "seir_day_kernel x T",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": balg * R,
-                         "active_agent_days": a_sum, "infections": i_sum},
+                         "active_agent_days": a_sum, "infections": i_sum,
+                         "note": "the day loop visits only E/Mild/Severe/Critical agents (L2-resident); the 2n bytes per "
+                                 "agent-day of the algorithmic figure are paid once by seir_materialize_kernel as a streaming "
+                                 "T x n byte write",
+                         "other_kernels": {"seir_materialize_kernel": {"ms": mat_ms, "GBps": R * (T * n + n / 4.0 + 32.0 * i_sum) / (mat_ms / 1e3) / 1e9 if mat_ms > 0 else None,
+                                                                       "frac": R * (T * n + n / 4.0 + 32.0 * i_sum) / (mat_ms / 1e3) / 1e9 / peak if mat_ms > 0 else None},
+                                           "seir_init_state_kernel + seir_init_infected_kernel": {"ms": init_ms}}},
         }
         if world == 1 and not args.no_tracing_leg:
             line["config"]["as_reference_tracing"] = tracing_leg(engine, population, tables, args, n, T, local)
