@@ -99,14 +99,15 @@ def run_case(name):
           "Doc", int(((hp[-1] >> 4) & 1).sum()), "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
-def run_ensemble(n=20000, seeds=64):
+def run_ensemble(n=20000, seeds=64, t_tracing_start=1000.0, name="ref_ensemble_italy_n%d.npz"):
     """Reference ensemble for the statistical-parity tier: one fixed
-    Italy population, `seeds` simulation seeds, tracing never starts; stores the daily curves."""
+    Italy population, `seeds` simulation seeds; stores the daily curves.  With t_tracing_start < T the
+    reference traces contacts from that day (as compiled)."""
     ns = ref_shim.driver_namespace(n, "Italy")
     ref = ref_shim.load()
     params = ns["params"]
     params["initial_infected_fraction"] = 0.001
-    params["t_tracing_start"] = 1000.0
+    params["t_tracing_start"] = float(t_tracing_start)
     params["t_lockdown"] = 40.0
     args = (ns["contact_matrix"], ns["p_mild_severe"], ns["p_severe_critical"], ns["p_critical_death"],
             ns["mean_time_to_isolate_factor"], ns["lockdown_factor_age"], ns["p_infect_household"],
@@ -134,16 +135,18 @@ def run_ensemble(n=20000, seeds=64):
         "lockdown_factor_age": args[5], "p_infect_household_scalar": np.float64(args[6][0]),
         "fraction_stay_home": args[7], "curves": curves, "r0_early": r0, "hits_per_infection": multi,
     }
-    path = os.path.join(GOLDEN, "ref_ensemble_italy_n%d.npz" % n)
+    path = os.path.join(GOLDEN, name % n)
     np.savez_compressed(path, **fx)
-    print("ensemble", curves[:, -1, :].mean(axis=0), "%.0f kB" % (os.path.getsize(path) / 1e3))
+    print("ensemble", name % n, curves[:, -1, :].mean(axis=0), "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or (list(CASES) + ["ensemble"])
+    which = sys.argv[1:] or (list(CASES) + ["ensemble", "ensemble_tracing"])
     for name in which:
         if name == "ensemble":
             run_ensemble()
+        elif name == "ensemble_tracing":  # tracing from day 25 of 60, the drivers' p_trace_household = 1, p_trace_outside = 0.95
+            run_ensemble(t_tracing_start=25.0, name="ref_ensemble_tracing_italy_n%d.npz")
         else:
             run_case(name)
