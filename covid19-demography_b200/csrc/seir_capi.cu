@@ -22,13 +22,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     // the host resets the barrier counter to 0 before each launch
     stage_tables(cx, sm);
     unsigned int epoch = 0;  // grid barriers passed so far
+    const int reps_per_sweep = gridDim.x / cx.blocks_per_rep;  // >= 1
+    const int my_slot = blockIdx.x / cx.blocks_per_rep, my_part = blockIdx.x % cx.blocks_per_rep;
     if (cx.n_shards > 1) {  // no GPU touches a peer's arrays before every peer has finished (re-)initialising them
         ++epoch;
         grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
     }
     for (int t = 1; t <= cx.T; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
-        Pass<TR>::day_pass(cx, sm, t);
+        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep);
         if (t < cx.T) {
             if (cx.n_shards > 1) {
                 ++epoch;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
     stage_tables(cx, sm);
-    Pass<TR>::day_pass(cx, sm, t);
+    Pass<TR>::day_pass(cx, sm, t, blockIdx.x / cx.blocks_per_rep, blockIdx.x % cx.blocks_per_rep, gridDim.x / cx.blocks_per_rep);
 }
 
 // contact tracing of day t as its own launch (per-day launch mode)
@@ -672,7 +674,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(cudaMemset(h->home.p, 0, R * np / 32 * 4));
         CKB(h->seeds.alloc(R));
         CKB(h->counters.alloc(R * 4));
-        CKB(h->barrier.alloc(1));
+        CKB(h->barrier.alloc(kBarStride * (2 + 64)));  // flat word, global word, up to 64 group counters (1024 CTAs)
         CKB(h->init_off.alloc(R + 1));
         CKB(h->flags.alloc(kMaxShards + 2));
         CKB(cudaMemset(h->flags.p, 0, (kMaxShards + 2) * 4));
@@ -816,7 +818,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaEventRecord(h->ev0, h->stream));
     CK(cudaMemsetAsync(h->tally.p, 0, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, h->stream));
     CK(cudaMemsetAsync(h->counters.p, 0, (size_t)R * 4 * 8, h->stream));
-    CK(cudaMemsetAsync(h->barrier.p, 0, 4, h->stream));
+    CK(cudaMemsetAsync(h->barrier.p, 0, kBarStride * (2 + 64) * 4, h->stream));
     CK(cudaMemsetAsync(h->list_cnt.p, 0, (size_t)R * 3 * (h->prm.T + 2) * 4, h->stream));
     const bool tracing = h->cx.trace_from >= 1;
     if (tracing) {

@@ -794,22 +794,22 @@ static __device__ __forceinline__ void append_survivors(PassSmem &sm, int keep, 
 }
 
 // both staging halves to tomorrow's list (the whole CTA; ends with the staging counters reset)
-static __device__ __forceinline__ void flush_survivors(PassSmem &sm)
+static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_new)
 {
     const RepView &v = sm.v;
     const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
     const uint32_t sq = sm.n_oldq < (uint32_t)kOutHalf ? sm.n_oldq : (uint32_t)kOutHalf;
+    const uint32_t sn = flush_new ? (sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew) : 0u;
     __syncthreads();
-    if (so | sq) {
-        if (threadIdx.x == 0) {
-            if (so) sm.base_old = atomicAdd(v.next_old_cnt, so);
-            if (sq) sm.base_oldq = atomicAdd(v.next_oldq_cnt, sq);
-            sm.n_old = 0;
-            sm.n_oldq = 0;
-        }
+    if (so | sq | sn) {
+        // (the three reservations are independent round trips to L2: three warps issue them side by side)
+        if (threadIdx.x == 0 && so) { sm.base_old = atomicAdd(v.next_old_cnt, so); sm.n_old = 0; }
+        if (threadIdx.x == 32 && sq) { sm.base_oldq = atomicAdd(v.next_oldq_cnt, sq); sm.n_oldq = 0; }
+        if (threadIdx.x == 64 && sn) { sm.base_new = atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
         __syncthreads();
         for (uint32_t k = threadIdx.x; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
         for (uint32_t k = threadIdx.x; k < sq; k += kThreads) v.next_old[v.n_pad_m1 - (sm.base_oldq + k)] = sm.out_old[kOutHalf + k];
+        for (uint32_t k = threadIdx.x; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
         __syncthreads();
     }
 }
@@ -819,14 +819,12 @@ static __device__ __forceinline__ void flush_survivors(PassSmem &sm)
 // replica split its list: a list shorter than the replica's threads is dealt S threads apart (one entry
 // per warp while it fits), a longer one in equal contiguous chunks, kPerThread entries per thread and round.
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
-static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
+static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
     const bool finalize = t >= cx.T;
     const int bpr = cx.blocks_per_rep;
-    const int reps_per_sweep = gridDim.x / bpr;  // >= 1
-    const int my_slot = blockIdx.x / bpr, my_part = blockIdx.x % bpr;
     // (CTAs beyond the last full group idle through the pass; they must still reach the grid barrier)
     for (int rep = my_slot; rep < cx.n_rep && my_slot < reps_per_sweep; rep += reps_per_sweep) {
         const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
@@ -859,8 +857,11 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
         // shorter than the replica's warps: a warp pays for every divergent path of its lanes), dealt round-robin
         // to the replica's CTAs (the new infectees, whose record build is the longest path, lead the list: a
         // contiguous split would give them all to the first CTAs) and grabbed dynamically by the CTA's warps.
-        const uint32_t G = 32u / spread_of(count, (uint32_t)bpr * kThreads);
-        const uint32_t n_groups = (count + G - 1u) / G;
+        uint32_t lgG = 0;  // G = 32 / spread_of(count, threads of the replica) as a shift
+        if (count >= (uint32_t)bpr * kThreads) lgG = 5u;
+        else while (lgG < 5u && (count << (5u - lgG)) > (uint32_t)bpr * kThreads) ++lgG;
+        const uint32_t G = 1u << lgG;
+        const uint32_t n_groups = (count + G - 1u) >> lgG;
         const uint32_t my_groups = n_groups > (uint32_t)my_part ? (n_groups - (uint32_t)my_part + (uint32_t)bpr - 1u) / (uint32_t)bpr : 0u;
         constexpr uint32_t kGroupsPerRound = (uint32_t)(kSlots / 32);
         const uint32_t rounds = (my_groups + kGroupsPerRound - 1u) / kGroupsPerRound;
@@ -884,7 +885,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
                 k = __shfl_sync(0xFFFFFFFFu, k, 0);
                 if (k >= g_hi) break;
                 const uint32_t lane = (uint32_t)tid & 31u;
-                const uint32_t e = (k * (uint32_t)bpr + (uint32_t)my_part) * G + lane;
+                const uint32_t e = ((k * (uint32_t)bpr + (uint32_t)my_part) << lgG) + lane;
                 const bool is_new = e < n_new, is_t = e >= o_t && e - o_t < n_old, is_q = e >= o_q && e - o_q < n_oldq;
                 const bool has = lane < G && (is_new || is_t || is_q);
                 const uint32_t slot = (k - g_lo) * 32u + lane;
@@ -969,15 +970,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             __syncthreads();
             // more rounds follow: empty the staging buffers
             if (round + 1u < rounds) {
-                flush_survivors(sm);
-                const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
-                if (sn > (uint32_t)(kOutNew - kHitCap)) {
-                    if (tid == 0) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
-                    __syncthreads();
-                    for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
-                    __syncthreads();
-                    if (tid == 0) sm.n_new = 0;
-                }
+                flush_survivors(sm, sm.n_new > (uint32_t)(kOutNew - kHitCap));
                 if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
                 __syncthreads();
             }
@@ -985,15 +978,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t)
             stamped = true;
         }
         stamped = false;
-        flush_survivors(sm);
-        {
-            const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
-            if (sn) {
-                if (tid == 0) sm.base_new = atomicAdd_system(v.next_new_cnt, sn);
-                __syncthreads();
-                for (uint32_t k = tid; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
-            }
-        }
+        flush_survivors(sm, true);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
@@ -1270,16 +1255,28 @@ __device__ __noinline__ void trace_pass(const DevCtx &cx, TraceSmem &ts, int t)
 }
 
 // grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency)
+// Two levels: the CTAs arrive in groups of kBarGroup on per-group counters (one 128 B line each -- 296 atomics
+// on ONE word serialise at its L2 slice), the last CTA of a group arrives on the global counter, everybody polls
+// the global counter.  `target` = barrier number * gridDim.x as before (kept for the call sites); word 0 of the
+// buffer is the flat counter of the sharded barrier, words 32.. the global / group counters of this one.
+constexpr unsigned int kBarGroup = 16, kBarStride = 32;
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned int epoch = target / gridDim.x;
+        const unsigned int g = blockIdx.x / kBarGroup, n_groups = (gridDim.x + kBarGroup - 1u) / kBarGroup;
+        const unsigned int size = min(kBarGroup, gridDim.x - g * kBarGroup);
+        unsigned int *global = counter + kBarStride, *group = counter + (2u + g) * kBarStride;
         __threadfence();
-        atomicAdd(counter, 1u);
+        if (atomicAdd(group, 1u) + 1u == epoch * size) {  // the last one of the group
+            __threadfence();
+            atomicAdd(global, 1u);
+        }
         unsigned int seen;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-        } while (seen < target);
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(global) : "memory");
+        } while (seen < epoch * n_groups);
         __threadfence();
     }
     __syncthreads();
