@@ -7,4 +7,4 @@ import os as _os
 
 __path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
                           "covid19-demography_b200")]
-__all__ = ["engine", "tables", "history", "seir_individual", "population", "build", "ensemble", "driver_tallies", "sharding", "sweep"]
+__all__ = ["engine", "tables", "history", "seir_individual", "population", "build", "ensemble", "driver_tallies", "sharding", "sweep", "sweep_io"]

@@ -98,3 +98,38 @@ def test_two_combination_sweep_on_one_resident_population(gpu_engine_module):
             tup, _, _, _ = c.keyed_oracle("native", p, seed=seed)
             assert np.array_equal(r["tallies"][k], util.tallies_from_history(tup[:9], c.age, int(p["T"]))), (idx, seed)
     eng.close()
+
+
+def test_job_files_have_the_reference_names_shapes_and_values(tmp_path):
+    """parameter_sweep.py:617-733: 19 tab-separated files per job, read back the way combine_results.py does."""
+    import pandas as pd
+    import test_driver_tallies as tdt
+    from covid19_demography_b200 import sweep_io
+    c = util.Case("italy_seeded")
+    params = c.no_tracing_params()
+    T = int(params["T"])
+    runs = [c.keyed_oracle("native", params, seed=s)[0] for s in (61, 62)]
+    tallies = np.stack([util.tallies_from_history(tup[:9], c.age, T) for tup in runs])
+    cohorts = np.stack([tdt.cohorts_from_outputs(tup, c.age, T) for tup in runs])
+    obs = np.arange(5, dtype=np.float64)
+    arrays = sweep_io.job_arrays(tallies, cohorts, actual_deaths=obs, first_day=40)
+    stem = sweep_io.file_stem("sweepA", 10000000.0, 7, 1, 0.029, 4, 22)
+    assert stem == "sweepA_paramsweep_n10000000.0_i7_N1_p0.029_m4_s22"
+    paths = sweep_io.write_job_files(str(tmp_path / "sweepA"), stem, arrays)
+    assert len(paths) == 19 and set(paths) == set(sweep_io.DATATYPES)
+    want = [tdt.drivers_way(tup, c.age, c.n, T) for tup in runs]
+    back = {k: pd.read_csv(p, sep="\t", header=None).values for k, p in paths.items()}
+    assert back["susceptible"].shape == (2, T) and back["infected_age_time"].shape == (2, 5 * T) and back["r0_tot"].shape == (2, 1)
+    for i, (tup, w) in enumerate(zip(runs, want)):
+        assert np.array_equal(back["deaths"][i], np.asarray(tup[7]).sum(axis=1))
+        assert np.array_equal(back["quarantine"][i], np.asarray(tup[8]).sum(axis=1))
+        assert np.allclose(back["r0_time"][i], w["r_0_over_time"], equal_nan=True)
+        assert np.allclose(back["cfr_time"][i], w["cfr_over_time"], equal_nan=True)
+        assert np.allclose(back["median_age_time"][i], w["median_age_time"], equal_nan=True)
+        assert np.allclose(back["infected_age_time"][i].reshape(5, T), w["infected_by_age_by_time"])
+        assert np.allclose(back["cfr_age_time"][i].reshape(5, T), w["CFR_by_age_by_time"], equal_nan=True)
+        assert np.allclose(back["dead_age_time"][i].reshape(5, T), w["dead_by_age_by_time"])
+        assert back["r0_tot"][i, 0] == pytest.approx(w["r0_total"])
+        d = np.asarray(tup[7]).sum(axis=1)[40:45]
+        assert back["mse"][i, 0] == pytest.approx(np.mean((d - obs) ** 2))
+    assert "NA" in open(paths["cfr_age_time"]).read()  # empty cohorts: 0/0, written as NA like the reference
