@@ -10,6 +10,8 @@ the others in ascending order, -1 padded), which is the only thing the kernels d
 `sample_households` / `sample_joint_comorbidities` are the entry points `run_complete_simulation`
 uses (seir_individual.py:24-37).
 """
+import os
+
 import numpy as np
 
 N_AGES = 101
@@ -86,12 +88,38 @@ def age_groups_csr(age):
     return offsets, order
 
 
+def _reference_module(name):
+    """The reference's own host module `name` (sample_households / sample_comorbidities) when the reference
+    repository is on sys.path -- the drop-in scenario of INTEGRATION.md -- else None.  Those modules use the
+    NumPy aliases `np.int` / `np.bool8`, removed in NumPy 1.24 / 2.0; they are put back before the import."""
+    import importlib
+    if not hasattr(np, "int"):
+        np.int = int
+    if not hasattr(np, "bool8"):
+        np.bool8 = np.bool_
+    try:
+        mod = importlib.import_module(name)
+    except Exception:
+        return None
+    return mod if hasattr(mod, "sample_households_italy") or hasattr(mod, "sample_joint_comorbidities") else None
+
+
 def sample_households(country, n):
     """Entry used by `run_complete_simulation` (seir_individual.py:24-35).
 
-    The reference's census-driven samplers (sample_households.py) are host code outside the hot path
-    (SURVEY.md section 8f rank 3); until their restatement lands this draws the synthetic population
-    above, seeded from NumPy's global stream the way the reference's samplers are (:19)."""
+    Household sampling stays the reference's own Python host code (BASELINE.json north_star): when the
+    reference's `sample_households` module is importable (the drop-in scenario: the reference repository is the
+    CWD / on sys.path, its census files next to it) it is called as the reference calls it (:25, :27).  Otherwise
+    -- tests, benchmarks, the GPU box -- the synthetic population above is drawn, seeded from NumPy's global
+    stream the way the reference's samplers are (:19)."""
+    ref = _reference_module("sample_households")
+    if ref is not None and os.environ.get("SEIR_B200_POPULATION", "reference") == "reference":
+        try:
+            fn = ref.sample_households_china if country == "China" else ref.sample_households_italy
+            households, age = fn(n)
+            return np.asarray(households, dtype=np.int64), np.asarray(age, dtype=np.int64)
+        except (OSError, IOError):  # the census CSV files are not in the CWD
+            pass
     seed = int(np.random.randint(0, 2**31 - 1))
     households, age, _, _, _ = synthetic_population(n, seed=seed, country="China" if country == "China" else "Italy")
     sample_households._last_seed = seed
@@ -99,7 +127,16 @@ def sample_households(country, n):
 
 
 def sample_joint_comorbidities(age, country="Italy"):
-    """(diabetes, hypertension) int64[n] -- sample_comorbidities.py:74-82 interface."""
+    """(diabetes, hypertension) int64[n] -- sample_comorbidities.py:74-82 interface; the reference's own module when
+    it is importable (see sample_households), else the synthetic prevalences below."""
+    ref = _reference_module("sample_comorbidities")
+    if ref is not None and os.environ.get("SEIR_B200_POPULATION", "reference") == "reference":
+        d, h = ref.sample_joint_comorbidities(np.asarray(age), country)
+        return np.asarray(d, dtype=np.int64), np.asarray(h, dtype=np.int64)
+    return _synthetic_comorbidities(age)
+
+
+def _synthetic_comorbidities(age):
     rng = np.random.default_rng(int(np.random.randint(0, 2**31 - 1)))
     a = np.asarray(age, dtype=np.float64)
     n = len(a)

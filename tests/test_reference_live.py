@@ -39,3 +39,25 @@ def test_oracle_equals_live_reference_new_seed():
     out2 = ref.run_model(11, households, age, age_groups, diabetes, hypertension, *args, params)
     for k, a, b in zip(oracle.OUTPUT_NAMES, out, out2):
         assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
+
+
+def test_dropin_population_is_the_references_own_sampler(monkeypatch):
+    """BASELINE.json north_star: household / comorbidity sampling stay the reference's Python host code.  With the
+    reference repository on sys.path and as CWD (the drop-in scenario) `population.sample_households` calls the
+    reference's sampler, so the same NumPy seed gives the same population."""
+    import sys
+    from covid19_demography_b200 import population
+    ref_shim.load()  # puts /root/reference on sys.path, chdir to a scratch dir with the data symlinks, numpy aliases
+    import sample_households as ref_sh
+    import sample_comorbidities as ref_sc
+    np.random.seed(21)
+    hh_ref, age_ref = ref_sh.sample_households_italy(700)
+    d_ref, h_ref = ref_sc.sample_joint_comorbidities(age_ref, "Italy")
+    np.random.seed(21)
+    hh, age = population.sample_households("Italy", 700)
+    d, h = population.sample_joint_comorbidities(age, "Italy")
+    assert np.array_equal(hh, hh_ref) and np.array_equal(age, age_ref)
+    assert np.array_equal(d, d_ref) and np.array_equal(h, h_ref)
+    monkeypatch.setenv("SEIR_B200_POPULATION", "synthetic")
+    hh2, _ = population.sample_households("Italy", 700)
+    assert hh2.shape == (700, 6) and not np.array_equal(hh2, hh_ref)
