@@ -300,7 +300,8 @@ def run_gpu_arm(args):
             eng.tallies(r)
     sync_all()
     e2e_s = time.perf_counter() - e0
-    h2d = R * (n + 8 * n_init + 8)
+    home_used = 1 <= p["t_stayhome_start"] < T  # (C2: stay-home never starts, Home_real is never read nor copied)
+    h2d = R * ((n if home_used else 0) + 8 * n_init + 8)
     d2h = R * (T * 9 * 101 * 4)
 
     agent_days_step = float(n) * (T - 1) * R

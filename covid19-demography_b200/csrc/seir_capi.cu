@@ -801,7 +801,9 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     CK(cudaMemcpyAsync(h->init_off.p, off.data(), (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     if (!ids.empty()) CK(cudaMemcpyAsync(h->init_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
     const int64_t n_words = h->n_pad / 32;
-    for (int r = 0; r < R; ++r) {
+    // Home = Home_real only from t_stayhome_start on (:243-244): a run that never gets there never reads the bitmap
+    const bool home_used = h->prm.t_stayhome_start >= 1 && h->prm.t_stayhome_start < h->prm.T;
+    for (int r = 0; r < R && home_used; ++r) {
         uint32_t *bm = h->home.p + (size_t)r * n_words;
         if (reps[r].home_real) {
             CK(h->stage_u8.alloc((size_t)n));
