@@ -877,6 +877,14 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaMemcpy(fl, h->flags.p, sizeof fl, cudaMemcpyDeviceToHost));
         if (fl[kMaxShards + 1]) return fail("sharded run: a peer GPU did not reach the day barrier within 4 s");
     }
+#ifdef SEIR_CHECKS
+    {
+        std::vector<unsigned long long> c((size_t)R * 4);
+        CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < R; ++r)
+            if (c[(size_t)r * 4] & 4ull) return fail("SEIR_CHECKS: an index left its array (see SEIR_CHECK in seir_kernels.cuh)");
+    }
+#endif
     if (tracing) {
         std::vector<unsigned long long> c((size_t)R * 4);
         CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));

@@ -232,6 +232,15 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 #else
 #define SEIR_FINE(k) do { } while (0)
 #endif
+// Bounds checks of our own (compute-sanitizer is closed on this pool): with -DSEIR_CHECKS every index that reaches a
+// list, a record or a queue is tested, a violation sets bit 2 of the replica's error word (seir_run then fails)
+// and the access is skipped.  Off in the product build.
+#ifdef SEIR_CHECKS
+#define SEIR_CHECK(cond, cx, rep) (!(cond) ? (atomicOr(&(cx).counters[(rep) * 4 + 0], 4ull), false) : true)
+#else
+#define SEIR_CHECK(cond, cx, rep) true
+#endif
+
 // ---- out-of-line draw helpers ----------------------------------------------------------------------------
 // The day step is latency-bound and its code is executed by few warps per pass, so instruction fetch is
 // on the critical path: every heavy piece of the draw contract exists ONCE in the kernel image.
@@ -399,6 +408,7 @@ static __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, 
 {
     const RepView &v = sm.v;
     const uint32_t slot = meta >> 16, ord = meta & 0xFFFFu;
+    if (!SEIR_CHECK(slot < (uint32_t)kSlots && (int64_t)c < cx.n, cx, v.rep)) return;
     const uint32_t i = sm.slot_agent[slot];
     const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
     if (age_c == 127) age_c = __ldg(cx.stat + c) & 127;  // (independent of the atomic below: one round trip)
@@ -413,7 +423,7 @@ static __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, 
         if (remote) {  // append to the OWNER's list of tomorrow, in its memory
             const size_t lrow = (size_t)((t + 1) & 1) * cx.n_pad;
             const uint32_t pos = atomicAdd_system(cx.peer_list_cnt[g] + (cx.T + 2) + (t + 1), 1u);
-            __stcg(cx.peer_list_new[g] + lrow + pos, c);
+            if (SEIR_CHECK((int64_t)pos < cx.n_pad, cx, v.rep)) __stcg(cx.peer_list_new[g] + lrow + pos, c);
         } else {
             const uint32_t pos = atomicAdd(&sm.n_new, 1u);
             if (pos < (uint32_t)kOutNew) sm.out_new[pos] = c;
@@ -483,6 +493,7 @@ static __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &
     const int g0 = sm.grp_off[a], glen = sm.grp_off[a + 1] - g0;
     if (glen == 0) return;
     const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
+    if (!SEIR_CHECK((int64_t)c < cx.n && sd_index(b, (uint64_t)glen) < (uint64_t)glen, cx, v.rep)) return;
     const unsigned long long w = __ldcg((cx.n_shards > 1 ? cx.peer_winner[owner_of(cx, c)] : v.winner) + c);
     if ((w == 0ull || wday(w) == t) && !at_home(v, c))  // :375
         push_hit(cx, sm, c, (slot << 16) | ord, a, t);
@@ -807,6 +818,13 @@ static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_
         if (threadIdx.x == 32 && sq) { sm.base_oldq = atomicAdd(v.next_oldq_cnt, sq); sm.n_oldq = 0; }
         if (threadIdx.x == 64 && sn) { sm.base_new = atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
         __syncthreads();
+#ifdef SEIR_CHECKS
+        if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sq && sm.base_oldq + sq > v.n_pad_m1 + 1u) ||
+                                 (sn && sm.base_new + sn > v.n_pad_m1 + 1u)))
+            atomicOr(&sm.cnt[3], 1u);
+        __syncthreads();
+        if (sm.cnt[3]) return;
+#endif
         for (uint32_t k = threadIdx.x; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
         for (uint32_t k = threadIdx.x; k < sq; k += kThreads) v.next_old[v.n_pad_m1 - (sm.base_oldq + k)] = sm.out_old[kOutHalf + k];
         for (uint32_t k = threadIdx.x; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
@@ -893,7 +911,8 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 uint32_t i = 0;
                 if (has) {
                     i = is_new ? __ldcg(cur_new + e) : is_t ? __ldcg(cur_old + (e - o_t)) : __ldcg(cur_old + (sm.v.n_pad_m1 - (e - o_q)));
-                    keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
+                    if (SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_oldq) <= cx.n, cx, rep))
+                        keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
                 }
                 append_survivors(sm, keep, i);
                 const unsigned hm = __ballot_sync(0xFFFFFFFFu, has), nm = __ballot_sync(0xFFFFFFFFu, has && is_new);
@@ -993,6 +1012,9 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             if (sm.cnt[0]) atomicAdd(&cx.counters[rep * 4 + 1], (unsigned long long)sm.cnt[0]);
             if (sm.cnt[1]) atomicAdd(&cx.counters[rep * 4 + 2], (unsigned long long)sm.cnt[1]);
             if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
+#ifdef SEIR_CHECKS
+            if (sm.cnt[3]) atomicOr(&cx.counters[rep * 4 + 0], 4ull);
+#endif
         }
         __syncthreads();
         SEIR_STAMP(7);
@@ -1030,6 +1052,7 @@ __device__ __forceinline__ unsigned long long tkey(int t, uint32_t root) { retur
 __device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, uint32_t x)
 {
     const int t = tv.t;
+    if (!SEIR_CHECK((int64_t)x < cx.n, cx, tv.rep)) return;
     const int age = __ldg(cx.stat + x) & 127;
     const unsigned long long w = __ldcg(tv.winner + x);
     if (wday(w) == t) {  // infected today: no record before tomorrow's pass; the marks travel in winner / inbox
