@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
                     if (cx.tcomp) trace_parallel(cx, sm, t, epoch);  // components in parallel, ordered inside
                     else trace_pass(cx, *reinterpret_cast<TraceSmem *>(sm.out_old), t);
                     grid_barrier(cx.barrier, ++epoch * gridDim.x);
+                    if (blockIdx.x == 0 && threadIdx.x == 0) cx.stage_ns[(size_t)t * 8 + 6] = global_timer_ns();
                 }
             }
         }
@@ -408,6 +409,7 @@ struct seir_handle {
     DevBuf<uint32_t> log_head, log_cnt, rootbits, rootsum, root_cnt, trc, tstack, rootsum2, treached, troots, treps, tcsz;
     DevBuf<unsigned long long> tcomp, tlead, ttotal;
     DevBuf<TraceCtl> tctl;
+    DevBuf<uint32_t> tcta, tbig;
     DevBuf<unsigned long long> tmark;
     double p_hh_scalar = 0.0;
     bool p_hh_uniform = true;
@@ -490,6 +492,8 @@ static int alloc_state(seir_handle *h)
         CK(h->treps.alloc(R * np));
         CK(h->tcsz.alloc(R * np));
         CK(h->tctl.alloc(R));
+        CK(h->tcta.alloc(R * 2048));  // (grids of up to 2048 CTAs)
+        CK(h->tbig.alloc(R * kBigCap));
         CK(h->ttotal.alloc(1));
         CK(cudaMemset(h->ttotal.p, 0, 8));
         h->trace_alloc = true;
@@ -550,6 +554,7 @@ static void fill_ctx(seir_handle *h)
     c.treached = par ? h->treached.p : nullptr; c.troots = par ? h->troots.p : nullptr;
     c.treps = par ? h->treps.p : nullptr; c.tcsz = par ? h->tcsz.p : nullptr;
     c.tctl = par ? h->tctl.p : nullptr; c.ttotal = par ? h->ttotal.p : nullptr;
+    c.tcta = par ? h->tcta.p : nullptr; c.tbig = par ? h->tbig.p : nullptr;
     c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
     c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
     c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
@@ -1071,7 +1076,7 @@ void seir_destroy(seir_handle *h)
     h->log_ent.release(); h->log_head.release(); h->log_cnt.release(); h->rootbits.release(); h->rootsum.release();
     h->root_cnt.release(); h->tmark.release(); h->trc.release(); h->tstack.release();
     h->rootsum2.release(); h->tcomp.release(); h->tlead.release(); h->treached.release(); h->troots.release();
-    h->treps.release(); h->tcsz.release(); h->tctl.release(); h->ttotal.release();
+    h->treps.release(); h->tcsz.release(); h->tctl.release(); h->ttotal.release(); h->tcta.release(); h->tbig.release();
     h->alias_idx.release(); h->stage_ns.release(); h->fine_ns.release();
     if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->ev0) cudaEventDestroy(h->ev0);

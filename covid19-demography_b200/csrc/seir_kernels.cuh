@@ -170,6 +170,8 @@ struct DevCtx {
     unsigned long long *tcomp, *tlead;  // [rep][n_pad] parallel tracer: union-find parents, component leaders (day-stamped)
     uint32_t *treached, *troots, *treps, *tcsz;  // [rep][n_pad]
     struct TraceCtl *tctl;         // [rep]
+    uint32_t *tcta;                // [rep][grid] roots found by each CTA in its slice of the root bitmap
+    uint32_t *tbig;                // [rep][kBigCap] leaders (root slots) of the components that get a whole CTA
     uint32_t tday0;                // run number << 12: the tracer's day stamps (tmark, tcomp, tlead) are tday0 + t and never need clearing
     unsigned long long *ttotal;    // nodes ever appended to a frontier (grows monotonically: the BFS loop's stop test)
     // one population across the GPUs of a box (household-aligned shards, peer memory over NVLink)
@@ -1316,7 +1318,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 // result is the reference's, bit for bit.  Needs grid barriers between the steps: every thread of the grid
 // calls trace_parallel().
 struct TraceCtl {          // per replica
-    uint32_t n_roots, n_reached, alloc, pad;
+    uint32_t n_roots, n_reached, alloc, n_big;
 };
 
 __device__ __forceinline__ uint32_t uf_find(unsigned long long *comp, uint32_t x, unsigned long long stamp)
@@ -1478,6 +1480,7 @@ __device__ __forceinline__ uint32_t trace_collect_roots(const DevCtx &cx, int re
 
 constexpr int kMaxRepsPerCta = 16;
 constexpr int kBigComponent = 96;  // agents: larger components are searched by a whole CTA
+constexpr int kBigCap = 16384;     // such components per replica and day (more: searched by their leader's warp)
 __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int t, unsigned int &epoch)
 {
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -1512,21 +1515,92 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     TraceView tv;
     TracePar tp;
 
-    // ---- roots
-    if (serving && my_part == 0 && wib == 0) {
-        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+    // ---- roots, in ascending agent order: every warp of the replica's CTAs owns a contiguous slice of the root
+    // bitmap; count, exchange the CTA totals (one grid barrier), then write at the prefix offsets and clear the bits.
+    // (A CTA serves at most kMaxRepsPerCta replicas here; the host falls back to trace_pass beyond that.)
+    uint32_t *warp_cnt = sm.tally;              // [kMaxRepsPerCta][kWarps + 1] scratch, free between passes
+    const uint32_t n_words = (uint32_t)(cx.n_pad / 32);
+    const uint32_t words_per_warp = ((n_words + ngw - 1u) / ngw + 31u) & ~31u;
+    const uint32_t w_lo = min(gw * words_per_warp, n_words), w_hi = min(w_lo + words_per_warp, n_words);
+    if (serving) {
+        int k = 0;
+        for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
+            uint32_t cnt = 0;
+            if (__ldcg(cx.root_cnt + (size_t)rep * (cx.T + 2) + t) != 0u) {
+                const uint32_t *bits = cx.rootbits + (size_t)rep * n_words;
+                for (uint32_t w = w_lo + (uint32_t)lane; w < w_hi; w += 32u) cnt += (uint32_t)__popc(__ldcg(bits + w));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            }
+            if (lane == 0) warp_cnt[k * (kWarps + 1) + wib] = cnt;
+        }
+        __syncthreads();
+        if (tid < k) {  // one thread per replica of this CTA: the CTA's total
+            uint32_t tot = 0;
+            for (int w = 0; w < kWarps; ++w) tot += warp_cnt[tid * (kWarps + 1) + w];
+            warp_cnt[tid * (kWarps + 1) + kWarps] = tot;
+            __stcg(cx.tcta + (size_t)(my_slot + tid * reps_per_sweep) * gridDim.x + my_part, tot);
+        }
+    }
+    grid_barrier(cx.barrier, ++epoch * gridDim.x);
+    if (serving) {
+        int k = 0;
+        for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
             make(rep, tv, tp);
-            uint32_t R = 0;
-            if (__ldcg(cx.root_cnt + (size_t)rep * (cx.T + 2) + t) != 0u) R = trace_collect_roots(cx, rep, tp, stamp);
-            if (lane == 0) {
-                tp.ctl->n_roots = R;
-                tp.ctl->n_reached = R;
+            // offset of this warp: the CTAs before mine, then the warps before mine
+            uint32_t before = 0, all = 0;
+            for (int p0 = 0; p0 < bpr; p0 += 32) {
+                const int pp = p0 + lane;
+                const uint32_t v = pp < bpr ? __ldcg(cx.tcta + (size_t)rep * gridDim.x + pp) : 0u;
+                all += v;
+                if (pp < my_part) before += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+                all += __shfl_xor_sync(0xFFFFFFFFu, all, o);
+            }
+            for (int w = 0; w < wib; ++w) before += warp_cnt[k * (kWarps + 1) + w];
+            if (my_part == 0 && tid == 0) {
+                tp.ctl->n_roots = all;
+                tp.ctl->n_reached = all;
                 tp.ctl->alloc = 0;
-                if (R) atomicAdd(total, (unsigned long long)R);
+                tp.ctl->n_big = 0;
+                if (all) atomicAdd(total, (unsigned long long)all);
+            }
+            if (warp_cnt[k * (kWarps + 1) + wib] == 0u) continue;
+            uint32_t *bits = cx.rootbits + (size_t)rep * n_words;
+            uint32_t at0 = before;
+            for (uint32_t w0 = w_lo; w0 < w_hi; w0 += 32u) {
+                const uint32_t w = w0 + (uint32_t)lane;
+                uint32_t bw = w < w_hi ? __ldcg(bits + w) : 0u;
+                const uint32_t cnt = (uint32_t)__popc(bw);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                uint32_t at = at0 + incl - cnt;
+                at0 += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (bw) __stcg(bits + w, 0u);
+                while (bw) {
+                    const int b = __ffs(bw) - 1;
+                    bw &= bw - 1u;
+                    const uint32_t root = w * 32u + (uint32_t)b;
+                    __stcg(tp.roots + at, root);
+                    __stcg(tp.reached + at, root);
+                    __stcg(tp.csz + at, 0u);
+                    __stcg(tp.comp + root, stamp | root);
+                    __stcg(tp.lead + root, stamp | 0xFFFFFFFFull);
+                    ++at;
+                }
             }
         }
     }
     grid_barrier(cx.barrier, ++epoch * gridDim.x);
+#define SEIR_TSTAMP(k) do { if (blockIdx.x == 0 && tid == 0) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
+    SEIR_TSTAMP(1);
 
     // ---- union-find over the superset graph, level by level
     uint32_t lo[kMaxRepsPerCta];
@@ -1549,6 +1623,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
         if (now == prev_total) break;
         prev_total = now;
     }
+    SEIR_TSTAMP(2);
 
     // ---- representatives of the roots, leader (smallest root slot) of every component
     if (serving) {
@@ -1563,6 +1638,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
         }
     }
     grid_barrier(cx.barrier, ++epoch * gridDim.x);
+    SEIR_TSTAMP(3);
     // ---- component sizes (the capacity of the leader's search stack)
     if (serving) {
         for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
@@ -1575,6 +1651,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
         }
     }
     grid_barrier(cx.barrier, ++epoch * gridDim.x);
+    SEIR_TSTAMP(4);
     // ---- every component: its roots in ascending order -- by one warp, or by a whole CTA when the component is large
     if (serving) {
         for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
@@ -1585,7 +1662,15 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                 const uint32_t rp = __ldcg(tp.reps + k);
                 if ((uint32_t)__ldcg(tp.lead + rp) != k) continue;
                 const uint32_t cap = __ldcg(tp.csz + k);
-                if (cap > (uint32_t)kBigComponent) continue;  // left to the CTA pass below
+                if (cap > (uint32_t)kBigComponent) {  // queued for the CTA pass below
+                    uint32_t pos = 0;
+                    if (lane == 0) pos = atomicAdd(&tp.ctl->n_big, 1u);
+                    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+                    if (pos < (uint32_t)kBigCap) {
+                        if (lane == 0) __stcg(cx.tbig + (size_t)rep * kBigCap + pos, k);
+                        continue;
+                    }
+                }
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(&tp.ctl->alloc, cap);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -1604,23 +1689,45 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
             if (!ok && lane == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull);
         }
     }
-    __syncthreads();
+    grid_barrier(cx.barrier, ++epoch * gridDim.x);
+    SEIR_TSTAMP(5);
     if (serving) {
+        uint32_t *wc = sm.tally;  // [kWarps + 2] scratch
         for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
             make(rep, tv, tp);
             const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            const uint32_t n_big = min(__ldcg(&tp.ctl->n_big), (uint32_t)kBigCap);
             bool ok = true;
-            for (uint32_t k = (uint32_t)my_part; k < R; k += (uint32_t)bpr) {  // (CTA-uniform)
+            for (uint32_t q = (uint32_t)my_part; q < n_big; q += (uint32_t)bpr) {  // (CTA-uniform)
+                const uint32_t k = __ldcg(cx.tbig + (size_t)rep * kBigCap + q);
                 const uint32_t rp = __ldcg(tp.reps + k);
-                if ((uint32_t)__ldcg(tp.lead + rp) != k) continue;
                 const uint32_t cap = __ldcg(tp.csz + k);
-                if (cap <= (uint32_t)kBigComponent) continue;
-                if (tid == 0) sm.base_new = atomicAdd(&tp.ctl->alloc, cap);
+                if (tid == 0) { sm.base_new = atomicAdd(&tp.ctl->alloc, cap); wc[kWarps + 1] = 0; }
                 __syncthreads();
-                uint32_t *list = cx.tstack + (size_t)rep * cx.n_pad + sm.base_new;
-                for (uint32_t j = k; j < R; ++j) {
-                    if (__ldcg(tp.reps + j) != rp) continue;
-                    tv.root = __ldcg(tp.roots + j);
+                const uint32_t base = sm.base_new;
+                uint32_t *list = cx.tstack + (size_t)rep * cx.n_pad + base;
+                uint32_t *croots = tp.reached + base;  // (the frontier array is free by now; a component has at most `cap` roots)
+                // the component's roots, ascending: ordered compaction of the matching root slots
+                for (uint32_t j0 = k; j0 < R; j0 += kThreads) {
+                    const uint32_t j = j0 + (uint32_t)tid;
+                    const bool match = j < R && __ldcg(tp.reps + j) == rp;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, match);
+                    if (lane == 0) wc[wib] = (uint32_t)__popc(m);
+                    __syncthreads();
+                    uint32_t before = wc[kWarps + 1];
+                    for (int w = 0; w < wib; ++w) before += wc[w];
+                    if (match) __stcg(croots + before + (uint32_t)__popc(m & ((1u << lane) - 1u)), __ldcg(tp.roots + j));
+                    __syncthreads();
+                    if (tid == 0) {
+                        uint32_t tot = 0;
+                        for (int w = 0; w < kWarps; ++w) tot += wc[w];
+                        wc[kWarps + 1] += tot;
+                    }
+                    __syncthreads();
+                }
+                const uint32_t n_cr = wc[kWarps + 1];
+                for (uint32_t j = 0; j < n_cr; ++j) {
+                    tv.root = __ldcg(croots + j);
                     ok = trace_root_cta(cx, tv, ts, list, cap, &sm.base_old) && ok;
                 }
                 __syncthreads();
