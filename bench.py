@@ -61,21 +61,24 @@ def algorithmic_bytes(tal, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  nvidia-smi needs ~0.1 s to
+    deliver its first row, longer than a whole timed region here, so the sampler is started before the warm-up
+    steps (every 20 ms) and finish() keeps the rows stamped inside [start, end] of the timed region (and, when the
+    region is shorter than the sampling period, the rows right before and after it)."""
 
     def __init__(self, gpu_index):
         self.rows = []
-        self.stop = False
         self.idx = gpu_index
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -85,32 +88,46 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def finish(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.mark_end()
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [r for (ts, r) in self.rows if t0 <= ts <= self.t1]
+        if len(inside) < 3:  # a region shorter than a few sampling periods: add the neighbours
+            before = [r for (ts, r) in self.rows if ts < t0][-2:]
+            after = [r for (ts, r) in self.rows if ts > self.t1][:2]
+            inside = before + inside + after
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
+            for name, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_all": len(self.rows), "reasons": sorted(reasons)}
 
 
 def measured_traffic(kernel):
@@ -263,12 +280,13 @@ def run_gpu_arm(args):
         import torch
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for w in range(args.warmup):
         eng.run(*inputs(-1 - w))
     # ---- device-timed region
-    sampler = ClockSampler(local)
-    sampler.start()
     sync_all()
+    sampler.mark_start()
     dev_ms = loop_ms = 0.0
     launches = 0
     wall0 = time.perf_counter()
@@ -284,6 +302,7 @@ def run_gpu_arm(args):
         dev_ms += b
         launches += eng.counters()["launches"]
     sync_all()
+    sampler.mark_end()
     wall = time.perf_counter() - wall0
     clocks = sampler.finish()
     last_tal = eng.tallies(0)
@@ -413,11 +432,12 @@ def run_sharded_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        eng.run(*runs[k])
     sampler = ClockSampler(local)
     sampler.start()
+    for k in range(args.warmup):
+        eng.run(*runs[k])
     sync_all()
+    sampler.mark_start()
     dev_ms = loop_ms = 0.0
     launches = 0
     e0 = time.perf_counter()
@@ -431,6 +451,7 @@ def run_sharded_arm(args):
         tal = eng.tallies(0)  # d2h of the step's result
         infected = int(tal[0, 0].sum() - tal[-1, 0].sum())
     sync_all()
+    sampler.mark_end()
     e2e_s = time.perf_counter() - e0
     clocks = sampler.finish()
     if world > 1:
