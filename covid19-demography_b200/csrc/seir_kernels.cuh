@@ -1051,19 +1051,19 @@ struct TraceView {
 __device__ __forceinline__ unsigned long long tkey(int t, uint32_t root) { return ((unsigned long long)t << 32) | ((unsigned long long)root + 1ull); }
 
 // Q[t,x] = Documented[t,x] = traced[x] = True, time_documented[x] = t  (:73-76, :84-87), by ONE lane
-__device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, uint32_t x)
+// (w = winner[x] and, unless x was infected today, r = rec[x] were loaded by the caller while it evaluated the edge:
+// nobody else writes them during this root's search)
+__device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, uint32_t x, unsigned long long w, AgentRec r)
 {
     const int t = tv.t;
     if (!SEIR_CHECK((int64_t)x < cx.n, cx, tv.rep)) return;
-    const int age = __ldg(cx.stat + x) & 127;
-    const unsigned long long w = __ldcg(tv.winner + x);
+    const int age = wday(w) == t ? (__ldg(cx.stat + x) & 127) : (int)(r.stat() & 127);
     if (wday(w) == t) {  // infected today: no record before tomorrow's pass; the marks travel in winner / inbox
         const unsigned long long old = atomicOr(tv.winner + x, W_TRACED);
         atomicOr(tv.inbox + (x >> 4), inbox_q_bit((int)(x & 15)));
         if (!(old & W_TRACED)) atomicAdd(tv.tally_day + TAL_NEW_DOC * kAges + age, 1u);
         return;
     }
-    AgentRec r = load_rec(tv.rec + x);
     uint32_t st = r.state();
     const uint32_t fl = r.flags();
     const int comp = (int)(st & 7u);
@@ -1138,16 +1138,19 @@ __device__ __forceinline__ bool trace_expand_exact(const DevCtx &cx, const Trace
         const uint32_t e = e0 + (uint32_t)lane;
         bool ok = false;
         uint32_t target = 0;
+        unsigned long long w = 0ull;
+        AgentRec mrec;
+        mrec.clear();
         if (e < (uint32_t)(size - 1)) {  // household edge j (:68-77)
             const int j = (int)e;
             target = base + (uint32_t)j + (j >= pos ? 1u : 0u);
-            const unsigned long long w = __ldcg(tv.winner + target);
+            w = __ldcg(tv.winner + target);
             if (w != 0ull && wday(w) != t) {  // not S[t-1, contact]
                 // traced[contact]: documented before today, or by its own iteration today if that came first
                 // (contact <= root), or reached by a tracer today
-                const AgentRec m = load_rec(tv.rec + target);
-                bool traced = (m.state() & ST_DOC) != 0;
-                if (traced && (int)m.t_documented() == t && target > root &&
+                mrec = load_rec(tv.rec + target);
+                bool traced = (mrec.state() & ST_DOC) != 0;
+                if (traced && (int)mrec.t_documented() == t && target > root &&
                     (int)(__ldcg(tv.tmark + target) >> 32) != td)
                     traced = false;
                 if (!traced) ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_HH, (uint32_t)j), 0) < cx.p_trace_hh;
@@ -1159,13 +1162,16 @@ __device__ __forceinline__ bool trace_expand_exact(const DevCtx &cx, const Trace
             for (uint32_t q = 0; q < L; ++q) rank += ts.ent_key[q] < kk ? 1u : 0u;
             target = ts.ent_x[k];
             // today's entries exist only if c's iteration has run before the root's (c < root)
-            if (rank < (uint32_t)kLogWidth && ((int)(kk >> 16) < t || c < root))
+            if (rank < (uint32_t)kLogWidth && ((int)(kk >> 16) < t || c < root)) {
+                w = __ldcg(tv.winner + target);  // (for trace_mark: in flight while the draw is computed)
+                if (wday(w) != t) mrec = load_rec(tv.rec + target);
                 ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_OUT, rank), 0) < cx.p_trace_out;
+            }
         }
         if (ok) {
             const unsigned long long old = atomicExch(tv.tmark + target, key);
             if (old == key) ok = false;  // already reached under this root
-            else trace_mark(cx, tv, target);
+            else trace_mark(cx, tv, target, w, mrec);
         }
         const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
         if (m) {
