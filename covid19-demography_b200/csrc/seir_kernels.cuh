@@ -1020,6 +1020,9 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         }
         __syncthreads();
         SEIR_STAMP(7);
+#ifdef SEIR_CTA_STAMPS  // (debug) when does every CTA finish pass SEIR_CTA_STAMPS?  overwrites the stage stamps of the first passes
+        if (t == SEIR_CTA_STAMPS && tid == 0 && blockIdx.x < (unsigned)((cx.T + 2) * 8)) cx.stage_ns[blockIdx.x] = global_timer_ns();
+#endif
     }
 }
 
@@ -1094,7 +1097,10 @@ __device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, u
 }
 
 // (log entries of one agent staged in shared memory: 504; the reference keeps 100)
-constexpr int kTraceLogCap = 504;
+#ifndef SEIR_TRACE_LOGCAP
+#define SEIR_TRACE_LOGCAP 504
+#endif
+constexpr int kTraceLogCap = SEIR_TRACE_LOGCAP;
 struct TraceSmem {
     uint32_t ent_x[kTraceLogCap];
     uint32_t ent_key[kTraceLogCap];  // day<<16 | ordinal: the order of infected_by[c, :]
