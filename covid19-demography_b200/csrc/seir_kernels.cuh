@@ -659,9 +659,14 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
     bool nq = Qp, ndoc = Dp;
     bool transmit = !Qp;
     bool root = false;  // newly documented today by its own progression: the root of a trace (:284-289, :298-303)
-    bool have_db = false;
+    // the agent's day block (lane 0: documentation draw, lane 1: first uniform of the kept-contact count), drawn ONCE, here,
+    // for every lane of the warp that may need it -- the two users sit in different branches below, and a warp would
+    // otherwise run the Philox rounds once per branch
+    const bool want_doc = Mp && !Dp && cx.p_doc > 0.0;
+    const bool have_db = want_doc || (!Qp && cx.mode == SEIR_MODE_NATIVE);
     sd_block db;
     db.w[0] = db.w[1] = db.w[2] = db.w[3] = 0u;
+    if (have_db) db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
     const int t_inf = t_infected_of(r);
     if (!Ep && due(t, t_inf, r.tt_recovery())) {  // :276-279
         ncomp = C_R;
@@ -676,9 +681,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
             sm.evq[atomicAdd(&sm.n_ev, 1u)] = (uint16_t)slot;  // (at most one entry per slot: cannot overflow)
             return DAY_DEFER;
         }
-        if (Mp && !Dp && cx.p_doc > 0.0) {  // :280-289 (lane 0 of the agent's day block)
-            db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
-            have_db = true;
+        if (want_doc) {  // :280-289 (lane 0 of the agent's day block)
             if (sd_lane(db, 0) < cx.p_doc) {
                 ndoc = true;
                 root = true;
@@ -732,7 +735,6 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
         // ---- community push :361-390: the first Knuth uniform of the kept-contact count is lane 1 of the day block
         const bool out = !at_home(v, i);
         if (out && cx.mode == SEIR_MODE_NATIVE) {
-            if (!have_db) db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
             const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
             if (sd_lane(db, 1) > en) push_draw(cx, sm, (slot << 16) | (DQ_NATIVE << 14), t);
         } else if (out) {
