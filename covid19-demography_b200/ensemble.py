@@ -29,11 +29,14 @@ def batches(items, batch):
 
 
 def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fraction, want_vectors=(),
-              want_cohorts=False, fast_prologue=False):
+              want_cohorts=False, fast_prologue=False, host_threads=0):
     """Run `seeds` on `engine` (an engine.Engine with R replica slots) in batches of R.
 
     Per seed the reference's own prologue picks are used (`tables.prologue`, seir_individual.py:176-187).
     `fast_prologue` swaps in `tables.prologue_fast` (same distributions, O(picks) instead of two O(n) permutations).
+    `host_threads` > 0 draws the prologues of the NEXT batch on that many host threads while the device runs the
+    current one (NumPy's generators and ctypes' foreign calls release the GIL), so a long ensemble is bound by
+    the device, not by the host prologue (0.3 s per seed at n = 10 M for the reference's stream).
     A short last batch is padded by repeating its last seed (the padding runs are discarded).
     Returns {"tallies": int64[len(seeds), T, 9, 101], "counters": [dict], "vectors": {name: float64[len(seeds), n]},
     "cohorts": int64[len(seeds), T, 4, 101] (with want_cohorts)}.
@@ -44,20 +47,43 @@ def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fr
     counters = []
     vectors = {k: np.zeros((len(seeds), n)) for k in want_vectors}
     cohorts = np.zeros((len(seeds), engine.T, 4, _tables.N_AGES), dtype=np.int64) if want_cohorts else None
+    pick = _tables.prologue_fast if fast_prologue else _tables.prologue
+    chunks = batches(list(seeds), R)
+    padded = [c + [c[-1]] * (R - len(c)) for c in chunks]
+
+    def draw(batch):
+        return [pick(s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in batch]
+
+    pool = None
+    if host_threads > 0 and len(chunks) > 0:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=host_threads)
+
+        def draw_async(batch):
+            futs = [pool.submit(pick, s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in batch]
+            return lambda: [f.result() for f in futs]
+        pending = draw_async(padded[0])
     done = 0
-    for chunk in batches(list(seeds), R):
-        padded = chunk + [chunk[-1]] * (R - len(chunk))
-        pick = _tables.prologue_fast if fast_prologue else _tables.prologue
-        pro = [pick(s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in padded]
-        engine.run(padded, [p[0] for p in pro], [p[1] for p in pro])
-        for r in range(len(chunk)):
-            tallies[done + r] = engine.tallies(r)
-            counters.append(engine.counters(r))
-            if want_cohorts:
-                cohorts[done + r] = engine.cohorts(r)
-            for k in want_vectors:
-                vectors[k][done + r] = engine.agent_vector(k, replica=r)
-        done += len(chunk)
+    try:
+        for b, chunk in enumerate(chunks):
+            if pool is not None:
+                pro = pending()
+                if b + 1 < len(chunks):
+                    pending = draw_async(padded[b + 1])  # overlaps with the device run below
+            else:
+                pro = draw(padded[b])
+            engine.run(padded[b], [p[0] for p in pro], [p[1] for p in pro])
+            for r in range(len(chunk)):
+                tallies[done + r] = engine.tallies(r)
+                counters.append(engine.counters(r))
+                if want_cohorts:
+                    cohorts[done + r] = engine.cohorts(r)
+                for k in want_vectors:
+                    vectors[k][done + r] = engine.agent_vector(k, replica=r)
+            done += len(chunk)
+    finally:
+        if pool is not None:
+            pool.shutdown(wait=True)
     return {"tallies": tallies, "counters": counters, "vectors": vectors, "cohorts": cohorts}
 
 

@@ -44,6 +44,14 @@ def run(label, fx, p, n, R, batches, fsh):
           "%.3e agent-days/s, %.0f runs/hour per GPU (device), attack rate of seed 0 %.1f %%, host prologue %.0f ms per seed"
           % (label, n, T, R, ms, ms / R, wall * 1e3, n * (T - 1) * R / (ms / 1e3), 3600e3 * R / ms,
              100.0 * (1 - tal[-1, 0].sum() / n), t_pro * 1e3), flush=True)
+    # end to end through ensemble.run_seeds: prologue picks on host threads overlapped with the device runs
+    for fast in (False, True):
+        t0 = time.perf_counter()
+        res = ensemble.run_seeds(eng, list(range(5000, 5000 + R * batches)), groups, fsh, p["initial_infected_fraction"],
+                                 fast_prologue=fast, host_threads=min(R, len(os.sched_getaffinity(0))))
+        dt = time.perf_counter() - t0
+        print("   end to end, %d runs, %s prologue on host threads: %.2f s -> %.0f runs/hour per GPU"
+              % (R * batches, "fast" if fast else "reference-stream", dt, 3600.0 * R * batches / dt), flush=True)
     eng.close()
 
 

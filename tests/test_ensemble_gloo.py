@@ -87,3 +87,25 @@ def test_two_rank_ensemble_equals_single_process():
         assert np.array_equal(full, want), "rank %d assembled a different ensemble" % rank
         owned += mine
     assert sorted(owned) == list(range(len(SEEDS)))
+
+
+def test_threaded_prologue_gives_the_same_runs():
+    """host_threads > 0 only moves the prologue draws of the next batch onto host threads."""
+    from test_sweep import _FakeEngine
+    c = util.Case("italy_policy")
+    calls = {}
+    for threads in (0, 3):
+        eng = _FakeEngine()
+        eng.n = c.n
+        eng.marker = 1
+        seen = []
+        orig = eng.run
+
+        def run(seeds, home, init, _orig=orig, _seen=seen):
+            _seen.append((tuple(seeds), [h.sum() for h in home], [tuple(i.tolist()) for i in init]))
+            _orig(seeds, home, init)
+        eng.run = run
+        res = ensemble.run_seeds(eng, [5, 6, 7, 8, 9], c.age_groups, c.fraction_stay_home, 0.004, host_threads=threads)
+        calls[threads] = (seen, res["tallies"].copy())
+    assert calls[0][0] == calls[3][0] and np.array_equal(calls[0][1], calls[3][1])
+    assert [s[0] for s in calls[0][0]] == [(5, 6), (7, 8), (9, 9)]
