@@ -896,6 +896,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         for (int r = 0; r < R; ++r) {
             if (c[(size_t)r * 4] & 1ull) return fail("contact tracing: the outside-infection log overflowed (more hits than 1.25 n)");
             if (c[(size_t)r * 4] & 2ull) return fail("contact tracing: the tracer's stack overflowed");
+            if (c[(size_t)r * 4] & 8ull) return fail("contact tracing: an agent infected more than 504 others outside its household (the tracer stages at most that many log entries; the reference keeps 100)");
         }
     }
     return 0;

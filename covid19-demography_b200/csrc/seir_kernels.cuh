@@ -1138,6 +1138,7 @@ __device__ __forceinline__ bool trace_expand_exact(const DevCtx &cx, const Trace
             ++L;
             e = en.y;
         }
+        if (e != 0u) atomicOr(&cx.counters[tv.rep * 4 + 0], 8ull);  // more entries than the staging holds: seir_run reports it
     }
     L = __shfl_sync(0xFFFFFFFFu, L, 0);
     __syncwarp();
@@ -1385,6 +1386,7 @@ __device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const Tr
             ++L;
             e = en.y;
         }
+        if (e != 0u) atomicOr(&cx.counters[tv.rep * 4 + 0], 8ull);  // more entries than the staging holds: seir_run reports it
     }
     L = __shfl_sync(0xFFFFFFFFu, L, 0);
     __syncwarp();
