@@ -52,12 +52,34 @@ def job_arrays(tallies, cohorts, actual_deaths=None, first_day=None):
     return out
 
 
-def write_job_files(directory, stem, arrays):
+AGEPOLICY_DATATYPES = ("r0_tot", "mse", "infected", "susceptible", "exposed", "deaths", "mild", "severe", "critical",
+                       "recovered", "quarantine", "documented")
+"""The twelve per-job files of `simulate_agepolicies.py` (:645-716)."""
+
+
+def agepolicy_file_stem(sim_name, n, combo_index, trial, pigc, mm, sd):
+    """simulate_agepolicies.py:646."""
+    return "%s_agepolicy_n%s_i%s_N%s_p%s_m%s_s%s" % (sim_name, float(n), combo_index, trial, pigc, mm, sd)
+
+
+def agepolicy_job_arrays(tallies, cohorts, n, actual_deaths=None, first_day=None):
+    """{datatype: array} of simulate_agepolicies.py from tallies int64[N, T, 9, 101] and cohorts int64[N, T, 4, 101];
+    `infected` is n - S per day (:617), `documented` the Documented column sums."""
+    base = job_arrays(tallies, cohorts, actual_deaths=actual_deaths, first_day=first_day)
+    out = {k: base[k] for k in ("r0_tot", "mse", "susceptible", "exposed", "deaths", "mild", "severe", "critical",
+                                "recovered", "quarantine")}
+    t = np.asarray(tallies)
+    out["infected"] = (float(n) - t[:, :, 0, :].sum(axis=2)).astype(np.float64)
+    out["documented"] = t[:, :, 3, :].sum(axis=2).astype(np.float64)
+    return out
+
+
+def write_job_files(directory, stem, arrays, datatypes=None):
     """One file per datatype, the reference's to_csv settings (:716-729).  Returns the paths."""
     import pandas as pd
     os.makedirs(directory, exist_ok=True)
     paths = {}
-    for name in DATATYPES:
+    for name in (DATATYPES if datatypes is None else datatypes):
         path = os.path.join(directory, "%s_%s.csv" % (stem, name))
         pd.DataFrame(arrays[name]).to_csv(path, sep="\t", index=False, header=False, na_rep="NA")
         paths[name] = path

@@ -133,3 +133,26 @@ def test_job_files_have_the_reference_names_shapes_and_values(tmp_path):
         d = np.asarray(tup[7]).sum(axis=1)[40:45]
         assert back["mse"][i, 0] == pytest.approx(np.mean((d - obs) ** 2))
     assert "NA" in open(paths["cfr_age_time"]).read()  # empty cohorts: 0/0, written as NA like the reference
+
+
+def test_agepolicy_job_files(tmp_path):
+    """simulate_agepolicies.py:645-716: twelve files per job."""
+    import pandas as pd
+    import test_driver_tallies as tdt
+    from covid19_demography_b200 import sweep_io
+    c = util.Case("italy_policy")
+    params = c.no_tracing_params()
+    T = int(params["T"])
+    tup = c.keyed_oracle("native", params, seed=70)[0]
+    tallies = util.tallies_from_history(tup[:9], c.age, T)[None]
+    cohorts = tdt.cohorts_from_outputs(tup, c.age, T)[None]
+    arrays = sweep_io.agepolicy_job_arrays(tallies, cohorts, c.n)
+    stem = sweep_io.agepolicy_file_stem("pol", c.n, 3, 0, 0.029, 4, 22)
+    assert stem == "pol_agepolicy_n3000.0_i3_N0_p0.029_m4_s22"
+    paths = sweep_io.write_job_files(str(tmp_path), stem, arrays, datatypes=sweep_io.AGEPOLICY_DATATYPES)
+    assert len(paths) == 12
+    S, E, Doc = (np.asarray(tup[k]) for k in (0, 1, 3))
+    back = {k: pd.read_csv(p, sep="\t", header=None).values for k, p in paths.items()}
+    assert np.array_equal(back["infected"][0], c.n - S.sum(axis=1))  # :617
+    assert np.array_equal(back["documented"][0], Doc.sum(axis=1))
+    assert np.array_equal(back["susceptible"][0], S.sum(axis=1))
