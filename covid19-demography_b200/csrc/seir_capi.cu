@@ -494,8 +494,8 @@ static int alloc_state(seir_handle *h)
         CK(h->tctl.alloc(R));
         CK(h->tcta.alloc(R * 2048));  // (grids of up to 2048 CTAs)
         CK(h->tbig.alloc(R * kBigCap));
-        CK(h->ttotal.alloc(1));
-        CK(cudaMemset(h->ttotal.p, 0, 8));
+        CK(h->ttotal.alloc(2));
+        CK(cudaMemset(h->ttotal.p, 0, 16));
         h->trace_alloc = true;
     }
     CK(h->hist.alloc(R * T * np));
@@ -895,7 +895,11 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));
         for (int r = 0; r < R; ++r) {
             if (c[(size_t)r * 4] & 1ull) return fail("contact tracing: the outside-infection log overflowed (more hits than 1.25 n)");
-            if (c[(size_t)r * 4] & 2ull) return fail("contact tracing: the tracer's stack overflowed");
+            if (c[(size_t)r * 4] & 2ull) {
+                char b[160];
+                snprintf(b, sizeof b, "contact tracing: the tracer's search list overflowed (replica %d, flags %llu)", r, c[(size_t)r * 4]);
+                return fail(b);
+            }
             if (c[(size_t)r * 4] & 8ull) return fail("contact tracing: an agent infected more than 504 others outside its household (the tracer stages at most that many log entries; the reference keeps 100)");
         }
     }
@@ -1044,6 +1048,27 @@ int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
     unsigned long long c[4];
     CK(cudaMemcpy(c, h->counters.p + (size_t)replica * 4, sizeof c, cudaMemcpyDeviceToHost));
     out4[0] = h->launches; out4[1] = (int64_t)c[1]; out4[2] = (int64_t)c[2]; out4[3] = (int64_t)c[3];
+    return 0;
+}
+
+/* debug: raw copy of one of the tracer's per-replica arrays (0 ctl, 1 roots, 2 reps, 3 csz, 4 reached, 5 lead, 6 comp) */
+int seir_debug_trace_array(seir_handle *h, int which, int replica, void *out, uint64_t bytes)
+{
+    if (!h || !out || !h->trace_alloc) return fail("seir_debug_trace_array: no tracer state");
+    CK(cudaSetDevice(h->device));
+    const size_t np = (size_t)h->n_pad, r = (size_t)replica;
+    const void *src = nullptr;
+    switch (which) {
+        case 0: src = h->tctl.p + r; break;
+        case 1: src = h->troots.p + r * np; break;
+        case 2: src = h->treps.p + r * np; break;
+        case 3: src = h->tcsz.p + r * np; break;
+        case 4: src = h->treached.p + r * np; break;
+        case 5: src = h->tlead.p + r * np; break;
+        case 6: src = h->tcomp.p + r * np; break;
+        default: return fail("seir_debug_trace_array: unknown array");
+    }
+    CK(cudaMemcpy(out, src, (size_t)bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -1334,6 +1334,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 // calls trace_parallel().
 struct TraceCtl {          // per replica
     uint32_t n_roots, n_reached, alloc, n_big;
+    uint32_t appended[2];  // nodes appended to the frontier by the even / odd levels of the day (cumulative)
 };
 
 __device__ __forceinline__ uint32_t uf_find(unsigned long long *comp, uint32_t x, unsigned long long stamp)
@@ -1365,7 +1366,7 @@ struct TracePar {          // per-replica arrays of the parallel tracer
 
 // one node of the frontier: evaluate its superset edges with the warp, claim / unite the targets
 __device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const TraceView &tv, const TracePar &tp, TraceSmem &ts,
-                                                      uint32_t c, unsigned long long *total_appended)
+                                                      uint32_t c, int parity, unsigned long long *total_appended)
 {
     const int lane = threadIdx.x & 31;
     const int t = tv.t;
@@ -1427,6 +1428,7 @@ __device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const Tr
             uint32_t at = 0;
             if (lane == 0) {
                 at = atomicAdd(&tp.ctl->n_reached, (uint32_t)__popc(m));
+                atomicAdd(&tp.ctl->appended[parity], (uint32_t)__popc(m));
                 atomicAdd(total_appended, (unsigned long long)__popc(m));
             }
             at = __shfl_sync(0xFFFFFFFFu, at, 0);
@@ -1582,7 +1584,8 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                 tp.ctl->n_reached = all;
                 tp.ctl->alloc = 0;
                 tp.ctl->n_big = 0;
-                if (all) atomicAdd(total, (unsigned long long)all);
+                tp.ctl->appended[0] = 0;
+                tp.ctl->appended[1] = 0;
             }
             if (warp_cnt[k * (kWarps + 1) + wib] == 0u) continue;
             uint32_t *bits = cx.rootbits + (size_t)rep * n_words;
@@ -1619,25 +1622,48 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     SEIR_TSTAMP(1);
 
     // ---- union-find over the superset graph, level by level
-    uint32_t lo[kMaxRepsPerCta];
-#pragma unroll
-    for (int k = 0; k < kMaxRepsPerCta; ++k) lo[k] = 0;
-    unsigned long long prev_total = __ldcg(total);
-    for (;;) {
+    // Everything a CTA reads to steer the loop must be STABLE when it reads it, because fast CTAs (and fast warps
+    // of a CTA that serves several replicas) are already appending for the next level:
+    //  * the frontier of level i + 1 of a replica is [hi_i, hi_i + what level i appended); the appends of level i are
+    //    counted in ctl->appended[i & 1], which nobody touches again before level i + 2.  (n_reached itself is the
+    //    allocator: it may run ahead of the entries written behind it, so it is never read inside the loop);
+    //  * the loop ends after a level that appended nothing anywhere, counted the same way in total[i & 1], and every
+    //    CTA takes the same decision (they meet at the grid barrier).
+    uint32_t lo[kMaxRepsPerCta], hi[kMaxRepsPerCta], seen[kMaxRepsPerCta][2];
+    if (serving) {
+        int k = 0;
+        for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
+            lo[k] = 0;
+            hi[k] = __ldcg(&cx.tctl[rep].n_roots);
+            seen[k][0] = seen[k][1] = 0;
+        }
+    }
+    unsigned long long prev_total[2] = {__ldcg(total), __ldcg(total + 1)};
+    for (unsigned int level = 0;; ++level) {
+        const int par = (int)(level & 1u);
+        unsigned long long *counter = total + par;
         if (serving) {
             int k = 0;
             for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
+                if (lo[k] == hi[k]) continue;
                 make(rep, tv, tp);
-                const uint32_t hi = __ldcg(&tp.ctl->n_reached);
-                for (uint32_t idx = lo[k] + gw; idx < hi; idx += ngw)
-                    trace_expand_superset(cx, tv, tp, ts, __ldcg(tp.reached + idx), total);
-                lo[k] = hi;
+                for (uint32_t idx = lo[k] + gw; idx < hi[k]; idx += ngw)
+                    trace_expand_superset(cx, tv, tp, ts, __ldcg(tp.reached + idx), par, counter);
             }
         }
         grid_barrier(cx.barrier, ++epoch * gridDim.x);
-        const unsigned long long now = __ldcg(total);
-        if (now == prev_total) break;
-        prev_total = now;
+        const unsigned long long now = __ldcg(counter);
+        if (now == prev_total[par]) break;
+        prev_total[par] = now;
+        if (serving) {
+            int k = 0;
+            for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
+                const uint32_t a = __ldcg(&cx.tctl[rep].appended[par]);
+                lo[k] = hi[k];
+                hi[k] += a - seen[k][par];
+                seen[k][par] = a;
+            }
+        }
     }
     SEIR_TSTAMP(2);
 
@@ -1698,11 +1724,12 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                         const int b = __ffs(m) - 1;
                         m &= m - 1u;
                         tv.root = __ldcg(tp.roots + j0 + (uint32_t)b);
-                        ok = trace_root(cx, tv, ts, list, cap) && ok;
+                        const bool ok1 = trace_root(cx, tv, ts, list, cap);
+                        ok = ok1 && ok;
                     }
                 }
             }
-            if (!ok && lane == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull);
+            if (!ok && lane == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull | 16ull);
         }
     }
     grid_barrier(cx.barrier, ++epoch * gridDim.x);
@@ -1748,7 +1775,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                 }
                 __syncthreads();
             }
-            if (!ok && tid == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull);
+            if (!ok && tid == 0) atomicOr(&cx.counters[rep * 4 + 0], 2ull | 32ull);
         }
     }
 }

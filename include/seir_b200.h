@@ -180,6 +180,10 @@ int seir_get_day_times(seir_handle *h, int64_t *out);
  * pass set-up done / stage A / C / H / W done / lists flushed / tallies flushed (0 where not reached). */
 int seir_get_stage_times(seir_handle *h, int64_t *out);
 
+/* debug: raw copy of one of the parallel tracer's per-replica arrays of the last tracing day
+ * (0 ctl {n_roots, n_reached, alloc, n_big}, 1 roots, 2 representatives, 3 component sizes, 4 reached, 5 leaders, 6 parents) */
+int seir_debug_trace_array(seir_handle *h, int which, int replica, void *out, uint64_t bytes);
+
 /* Page-lock / unlock a caller-owned host buffer so the per-run copies in seir_run are DMA transfers. */
 int seir_host_register(void *ptr, uint64_t bytes);
 int seir_host_unregister(void *ptr);

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import util
+from covid19_demography_b200 import tables as tables_mod
 
 pytestmark = pytest.mark.gpu
 
@@ -143,6 +144,23 @@ def test_tracing_off_is_the_papers_semantics(gpu_engine_module):
     eng = c.gpu_engine(gpu_engine_module, params, "native", tracing_enabled=0)
     eng.run([c.seed], [home], [init])
     _compare(eng, tup, ex, c, int(params["T"]))
+    eng.close()
+
+
+@pytest.mark.parametrize("tracing", [False, True])
+def test_more_replicas_than_ctas(gpu_engine_module, tracing):
+    """Sweeps at small n: 320 replicas on a grid of 296 CTAs (every CTA serves one or two replicas per pass; with
+    tracing, the parallel tracer loops over them too)."""
+    c = util.Case("italy_tracing" if tracing else "italy_policy")
+    params = dict(c.params) if tracing else c.no_tracing_params()
+    R = 320
+    seeds = list(range(3000, 3000 + R))
+    eng = c.gpu_engine(gpu_engine_module, params, "native", n_replicas=R)
+    pro = [tables_mod.prologue(s, c.age_groups, c.n, c.fraction_stay_home, params["initial_infected_fraction"]) for s in seeds]
+    eng.run(seeds, [p[0] for p in pro], [p[1] for p in pro])
+    for k in (0, 1, 150, 295, 296, 319):
+        tup, ex, _, _ = c.keyed_oracle("native", params, seed=seeds[k])
+        _compare(eng, tup, ex, c, int(params["T"]), replica=k)
     eng.close()
 
 
