@@ -1,6 +1,7 @@
 // seir_capi.cu -- kernels' launch side and the C ABI declared in include/seir_b200.h.
 // Built into libseir_b200.so by covid19-demography_b200/build.py (nvcc, sm_100a, -lineinfo).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -28,9 +29,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
         ++epoch;
         grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
     }
+    const bool defer_counters = cx.n_rep <= reps_per_sweep;  // this CTA serves one replica: its run counters are added once, below
+    if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
     for (int t = 1; t <= cx.T; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
-        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep);
+        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep, defer_counters);
         if (t < cx.T) {
             if (cx.n_shards > 1) {
                 ++epoch;
@@ -39,8 +42,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
             }
             grid_barrier(cx.barrier, ++epoch * gridDim.x);
             if (TR && cx.trace_from >= 1 && t >= cx.trace_from) {  // :241-242 tracing is on: resolve the day's traces
-                bool any = false;  // (grid-uniform: the counts are final after the barrier)
-                for (int r = 0; r < cx.n_rep; ++r) any = any || __ldcg(cx.root_cnt + (size_t)r * (cx.T + 2) + t) != 0u;
+                // any root today?  (grid-uniform: the counts are final after the barrier; read by ONE warp per CTA --
+                // the same word requested by every warp of the grid queues up at its L2 slice)
+                if (threadIdx.x < 32) {
+                    bool mine = false;
+                    for (int r = threadIdx.x; r < cx.n_rep; r += 32) mine = mine || __ldcg(cx.root_cnt + (size_t)r * (cx.T + 2) + t) != 0u;
+                    const bool warp_any = __any_sync(0xFFFFFFFFu, mine);
+                    if (threadIdx.x == 0) sm.base_new = warp_any ? 1u : 0u;
+                }
+                __syncthreads();
+                const bool any = sm.base_new != 0u;
+                __syncthreads();  // (base_new is reused below)
                 if (any) {
                     if (cx.tcomp) trace_parallel(cx, sm, t, epoch);  // components in parallel, ordered inside
                     else trace_pass(cx, *reinterpret_cast<TraceSmem *>(sm.out_old), t);
@@ -50,6 +62,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
             }
         }
     }
+    if (defer_counters && threadIdx.x < 3 && my_slot < cx.n_rep && sm.run_cnt[threadIdx.x])
+        atomicAdd(&cx.counters[my_slot * 4 + 1 + threadIdx.x], (unsigned long long)sm.run_cnt[threadIdx.x]);
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[cx.T + 1] = global_timer_ns();
 }
 
@@ -530,6 +544,7 @@ static void fill_ctx(seir_handle *h)
     c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
     c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
+    { const char *dp = getenv("SEIR_DEBUG_PASS"); c.dbg_pass = dp ? atoi(dp) : -1; }
     c.n_shards = h->n_shards; c.my_shard = h->my_shard;
     for (int g = 0; g <= kMaxShards; ++g) c.shard_lo[g] = (uint32_t)h->shard_lo[g < h->n_shards ? g : (h->n_shards > 0 ? h->n_shards : 0)];
     for (int g = 0; g < kMaxShards; ++g) {

@@ -172,6 +172,7 @@ struct DevCtx {
     struct TraceCtl *tctl;         // [rep]
     uint32_t *tcta;                // [rep][grid] roots found by each CTA in its slice of the root bitmap
     uint32_t *tbig;                // [rep][kBigCap] leaders (root slots) of the components that get a whole CTA
+    int dbg_pass;                  // (debug builds with -DSEIR_CTA_STAMPS) the pass whose per-CTA stage stamps go to fine_ns; env SEIR_DEBUG_PASS
     uint32_t tday0;                // run number << 12: the tracer's day stamps (tmark, tcomp, tlead) are tday0 + t and never need clearing
     unsigned long long *ttotal;    // nodes ever appended to a frontier (grows monotonically: the BFS loop's stop test)
     // one population across the GPUs of a box (household-aligned shards, peer memory over NVLink)
@@ -225,12 +226,12 @@ __device__ __forceinline__ int t_critical_of(const AgentRec &r) { return t_sever
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v) : : "memory");  // (memory: the stamps stay where they are written)
     return v;
 }
 
 #ifdef SEIR_FINE_STAMPS
-#define SEIR_FINE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && slot == 0) cx.fine_ns[(size_t)t * 16 + (k)] = global_timer_ns(); } while (0)
+#define SEIR_FINE(k) do { if (blockIdx.x == 0 && slot == 0) cx.fine_ns[(size_t)t * 16 + (k)] = global_timer_ns(); } while (0)
 #else
 #define SEIR_FINE(k) do { } while (0)
 #endif
@@ -358,6 +359,8 @@ struct __align__(16) PassSmem {
     double nat_enlam[2 * kAges * 2];
     int32_t grp_off[kAges + 1];
     uint32_t cnt[4];
+    uint32_t list_n[3];            // today's list lengths (new, transmitting, quarantined), read once per CTA
+    uint32_t run_cnt[3];           // this CTA's share of the run counters (persistent kernel: flushed once, at the end)
     uint32_t n_old, n_oldq, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_oldq, base_new, next_group;
 };
 
@@ -666,7 +669,9 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
     const bool have_db = want_doc || (!Qp && cx.mode == SEIR_MODE_NATIVE);
     sd_block db;
     db.w[0] = db.w[1] = db.w[2] = db.w[3] = 0u;
+    SEIR_FINE(3);
     if (have_db) db = draw_block(v.seed, i, (uint32_t)t, SD_SITE_DAY, 0);
+    SEIR_FINE(4);
     const int t_inf = t_infected_of(r);
     if (!Ep && due(t, t_inf, r.tt_recovery())) {  // :276-279
         ncomp = C_R;
@@ -719,6 +724,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
         dirty = true;
     }
     if (dirty) store_rec(v.rec + i, r);
+    SEIR_FINE(5);
 
     if (transmit) {
         // ---- household push :339-359; households are contiguous ranges [i-pos, i-pos+size)
@@ -732,6 +738,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
                 if (w == 0ull || wday(w) == t) smask |= 1u << j;  // S[t-1,c] (:346)
             }
         }
+        SEIR_FINE(6);
         // ---- community push :361-390: the first Knuth uniform of the kept-contact count is lane 1 of the day block
         const bool out = !at_home(v, i);
         if (out && cx.mode == SEIR_MODE_NATIVE) {
@@ -746,6 +753,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
             if (bits) push_draw(cx, sm, (slot << 16) | (DQ_HH << 14) | (jb << 2) | bits, t);
         }
     }
+    SEIR_FINE(7);
     return (ncomp >= C_E && ncomp <= C_CRIT) ? (nq ? DAY_KEEP_Q : DAY_KEEP) : DAY_DROP;
 }
 
@@ -762,6 +770,7 @@ static __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &
     } else {
         r = load_rec(v.rec + i);
     }
+    SEIR_FINE(2);
     const uint16_t stt = r.stat();
     const int age = stt & 127;
     const uint8_t st = r.state();
@@ -840,8 +849,15 @@ static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_
 // Pass t over all replicas.  CTA b serves replica (b / blocks_per_rep) [+ k * reps_per_sweep]; the CTAs of a
 // replica split its list: a list shorter than the replica's threads is dealt S threads apart (one entry
 // per warp while it fits), a longer one in equal contiguous chunks, kPerThread entries per thread and round.
+#ifdef SEIR_CTA_STAMPS  // (debug) the eight stage stamps of EVERY CTA (the first 2 (T + 2) of them) for pass cx.dbg_pass, into fine_ns
+#define SEIR_STAMP(k) do { if (tid == 0 && !stamped) { \
+        if (blockIdx.x == 0) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); \
+        if (t == cx.dbg_pass && blockIdx.x < (unsigned)((cx.T + 2) * 2)) cx.fine_ns[blockIdx.x * 8 + (k)] = global_timer_ns(); } } while (0)
+#else
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
-static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep)
+#endif
+static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep,
+                                bool defer_counters = false)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
@@ -870,7 +886,14 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             sm.v.tracing = cx.trace_from >= 1 && t >= cx.trace_from;          // :241-242
         }
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
-        const uint32_t n_new = __ldcg(cnt_new + t), n_old = __ldcg(cnt_old + t), n_oldq = __ldcg(cnt_oldq + t);
+        // today's list lengths: ONE request per CTA and counter (a load by every warp of the grid is 4 736 requests
+        // for the same L2 line, which its slice serves one at a time: 2 us at the start of every pass)
+        if (tid < 3) sm.list_n[tid] = __ldcg((tid == 0 ? cnt_new : tid == 1 ? cnt_old : cnt_oldq) + t);
+        for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
+        if (tid >= 32 && tid < 36) sm.cnt[tid - 32] = 0;
+        if (tid == 64) { sm.n_old = 0; sm.n_oldq = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
+        __syncthreads();
+        const uint32_t n_new = sm.list_n[0], n_old = sm.list_n[1], n_oldq = sm.list_n[2];
         // three segments, each starting on a multiple of 32: new infectees (their record build is the longest path),
         // agents that may transmit, quarantined agents -- a warp of a dense day serves one kind
         const uint32_t o_t = (n_new + 31u) & ~31u, o_q = o_t + ((n_old + 31u) & ~31u);
@@ -887,11 +910,6 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         const uint32_t my_groups = n_groups > (uint32_t)my_part ? (n_groups - (uint32_t)my_part + (uint32_t)bpr - 1u) / (uint32_t)bpr : 0u;
         constexpr uint32_t kGroupsPerRound = (uint32_t)(kSlots / 32);
         const uint32_t rounds = (my_groups + kGroupsPerRound - 1u) / kGroupsPerRound;
-
-        for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
-        if (tid < 4) sm.cnt[tid] = 0;
-        if (tid == 0) { sm.n_old = 0; sm.n_oldq = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
-        __syncthreads();
         SEIR_STAMP(0);
 
         for (uint32_t round = 0; round < rounds; ++round) {
@@ -907,6 +925,9 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 k = __shfl_sync(0xFFFFFFFFu, k, 0);
                 if (k >= g_hi) break;
                 const uint32_t lane = (uint32_t)tid & 31u;
+#ifdef SEIR_FINE_STAMPS
+                { const uint32_t slot = (k - g_lo) * 32u + lane; SEIR_FINE(0); }
+#endif
                 const uint32_t e = ((k * (uint32_t)bpr + (uint32_t)my_part) << lgG) + lane;
                 const bool is_new = e < n_new, is_t = e >= o_t && e - o_t < n_old, is_q = e >= o_q && e - o_q < n_oldq;
                 const bool has = lane < G && (is_new || is_t || is_q);
@@ -915,10 +936,13 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 uint32_t i = 0;
                 if (has) {
                     i = is_new ? __ldcg(cur_new + e) : is_t ? __ldcg(cur_old + (e - o_t)) : __ldcg(cur_old + (sm.v.n_pad_m1 - (e - o_q)));
+                    SEIR_FINE(1);
                     if (SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_oldq) <= cx.n, cx, rep))
                         keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
+                    SEIR_FINE(8);
                 }
                 append_survivors(sm, keep, i);
+                SEIR_FINE(9);
                 const unsigned hm = __ballot_sync(0xFFFFFFFFu, has), nm = __ballot_sync(0xFFFFFFFFu, has && is_new);
                 if (lane == 0 && hm) {
                     atomicAdd(&sm.cnt[0], (uint32_t)__popc(hm));
@@ -1013,18 +1037,22 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             }
         }
         if (tid == 0) {
-            if (sm.cnt[0]) atomicAdd(&cx.counters[rep * 4 + 1], (unsigned long long)sm.cnt[0]);
-            if (sm.cnt[1]) atomicAdd(&cx.counters[rep * 4 + 2], (unsigned long long)sm.cnt[1]);
-            if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
+            // run counters (agent-days stepped, infections, hits): 296 CTAs adding to the same three words every pass
+            // queue up at one L2 slice in front of the grid barrier's fence; a CTA that serves ONE replica for the
+            // whole kernel keeps its share in shared memory and adds it once, at the end (flush_run_counters)
+            if (defer_counters) {
+                sm.run_cnt[0] += sm.cnt[0]; sm.run_cnt[1] += sm.cnt[1]; sm.run_cnt[2] += sm.cnt[2];
+            } else {
+                if (sm.cnt[0]) atomicAdd(&cx.counters[rep * 4 + 1], (unsigned long long)sm.cnt[0]);
+                if (sm.cnt[1]) atomicAdd(&cx.counters[rep * 4 + 2], (unsigned long long)sm.cnt[1]);
+                if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
+            }
 #ifdef SEIR_CHECKS
             if (sm.cnt[3]) atomicOr(&cx.counters[rep * 4 + 0], 4ull);
 #endif
         }
         __syncthreads();
         SEIR_STAMP(7);
-#ifdef SEIR_CTA_STAMPS  // (debug) when does every CTA finish pass SEIR_CTA_STAMPS?  overwrites the stage stamps of the first passes
-        if (t == SEIR_CTA_STAMPS && tid == 0 && blockIdx.x < (unsigned)((cx.T + 2) * 8)) cx.stage_ns[blockIdx.x] = global_timer_ns();
-#endif
     }
 }
 
@@ -1497,7 +1525,10 @@ __device__ __forceinline__ uint32_t trace_collect_roots(const DevCtx &cx, int re
 }
 
 constexpr int kMaxRepsPerCta = 16;
-constexpr int kBigComponent = 96;  // agents: larger components are searched by a whole CTA
+#ifndef SEIR_BIG_COMPONENT
+#define SEIR_BIG_COMPONENT 16   // (measured on C2 with tracing from day 37: 96 -> 33.1 ms per run, 48 -> 30.8, 24 -> 29.5, 12 -> 29.3, 6 -> 28.9)
+#endif
+constexpr int kBigComponent = SEIR_BIG_COMPONENT;  // agents: larger components are searched by a whole CTA
 constexpr int kBigCap = 16384;     // such components per replica and day (more: searched by their leader's warp)
 __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int t, unsigned int &epoch)
 {
@@ -1540,11 +1571,20 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     const uint32_t n_words = (uint32_t)(cx.n_pad / 32);
     const uint32_t words_per_warp = ((n_words + ngw - 1u) / ngw + 31u) & ~31u;
     const uint32_t w_lo = min(gw * words_per_warp, n_words), w_hi = min(w_lo + words_per_warp, n_words);
+    // (Words that every warp of a replica's CTAs needs -- root counts, CTA totals, frontier bounds, the stop test -- are
+    // read by ONE thread per CTA and handed on through shared memory: thousands of warps asking for the same L2 line
+    // are served one at a time by its slice, microseconds per read.)
+    uint32_t *bc = sm.tally + 320;              // [2 + 2 * kMaxRepsPerCta] broadcast scratch (warp_cnt ends at 272)
+    if (serving && tid < kMaxRepsPerCta) {
+        const int rep = my_slot + tid * reps_per_sweep;
+        bc[2 + tid] = rep < cx.n_rep ? __ldcg(cx.root_cnt + (size_t)rep * (cx.T + 2) + t) : 0u;
+    }
+    __syncthreads();
     if (serving) {
         int k = 0;
         for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
             uint32_t cnt = 0;
-            if (__ldcg(cx.root_cnt + (size_t)rep * (cx.T + 2) + t) != 0u) {
+            if (bc[2 + k] != 0u) {
                 const uint32_t *bits = cx.rootbits + (size_t)rep * n_words;
                 for (uint32_t w = w_lo + (uint32_t)lane; w < w_hi; w += 32u) cnt += (uint32_t)__popc(__ldcg(bits + w));
 #pragma unroll
@@ -1562,22 +1602,31 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     }
     grid_barrier(cx.barrier, ++epoch * gridDim.x);
     if (serving) {
+        if (wib == 0) {  // the CTAs before mine and the replica's total, per replica of this CTA
+            int k = 0;
+            for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
+                uint32_t before = 0, all = 0;
+                for (int p0 = 0; p0 < bpr; p0 += 32) {
+                    const int pp = p0 + lane;
+                    const uint32_t v = pp < bpr ? __ldcg(cx.tcta + (size_t)rep * gridDim.x + pp) : 0u;
+                    all += v;
+                    if (pp < my_part) before += v;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+                    all += __shfl_xor_sync(0xFFFFFFFFu, all, o);
+                }
+                if (lane == 0) { bc[2 + 2 * k] = before; bc[3 + 2 * k] = all; }
+            }
+        }
+        __syncthreads();
         int k = 0;
         for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
             make(rep, tv, tp);
             // offset of this warp: the CTAs before mine, then the warps before mine
-            uint32_t before = 0, all = 0;
-            for (int p0 = 0; p0 < bpr; p0 += 32) {
-                const int pp = p0 + lane;
-                const uint32_t v = pp < bpr ? __ldcg(cx.tcta + (size_t)rep * gridDim.x + pp) : 0u;
-                all += v;
-                if (pp < my_part) before += v;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
-                all += __shfl_xor_sync(0xFFFFFFFFu, all, o);
-            }
+            uint32_t before = bc[2 + 2 * k];
+            const uint32_t all = bc[3 + 2 * k];
             for (int w = 0; w < wib; ++w) before += warp_cnt[k * (kWarps + 1) + w];
             if (my_part == 0 && tid == 0) {
                 tp.ctl->n_roots = all;
@@ -1629,16 +1678,18 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     //    allocator: it may run ahead of the entries written behind it, so it is never read inside the loop);
     //  * the loop ends after a level that appended nothing anywhere, counted the same way in total[i & 1], and every
     //    CTA takes the same decision (they meet at the grid barrier).
-    uint32_t lo[kMaxRepsPerCta], hi[kMaxRepsPerCta], seen[kMaxRepsPerCta][2];
+    uint32_t lo[kMaxRepsPerCta], hi[kMaxRepsPerCta], seen[kMaxRepsPerCta][2], n_r[kMaxRepsPerCta];
     if (serving) {
         int k = 0;
         for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
             lo[k] = 0;
-            hi[k] = __ldcg(&cx.tctl[rep].n_roots);
+            hi[k] = n_r[k] = bc[3 + 2 * k];  // the replica's roots (left there by the prefix step above)
             seen[k][0] = seen[k][1] = 0;
         }
     }
-    unsigned long long prev_total[2] = {__ldcg(total), __ldcg(total + 1)};
+    unsigned long long prev_total[2] = {0ull, 0ull};  // (thread 0 only)
+    if (tid == 0) { prev_total[0] = __ldcg(total); prev_total[1] = __ldcg(total + 1); }
+    __syncthreads();  // (bc is rewritten below)
     for (unsigned int level = 0;; ++level) {
         const int par = (int)(level & 1u);
         unsigned long long *counter = total + par;
@@ -1652,26 +1703,37 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
             }
         }
         grid_barrier(cx.barrier, ++epoch * gridDim.x);
-        const unsigned long long now = __ldcg(counter);
-        if (now == prev_total[par]) break;
-        prev_total[par] = now;
+        if (tid == 0) {
+            const unsigned long long now = __ldcg(counter);
+            bc[0] = now == prev_total[par] ? 1u : 0u;
+            prev_total[par] = now;
+        }
+        if (serving && tid >= 32 && tid < 32 + kMaxRepsPerCta) {
+            const int rep = my_slot + (tid - 32) * reps_per_sweep;
+            if (rep < cx.n_rep) bc[2 + (tid - 32)] = __ldcg(&cx.tctl[rep].appended[par]);
+        }
+        __syncthreads();
+        if (bc[0]) break;
         if (serving) {
             int k = 0;
             for (int rep = my_slot; rep < cx.n_rep && k < kMaxRepsPerCta; rep += reps_per_sweep, ++k) {
-                const uint32_t a = __ldcg(&cx.tctl[rep].appended[par]);
+                const uint32_t a = bc[2 + k];
                 lo[k] = hi[k];
                 hi[k] += a - seen[k][par];
                 seen[k][par] = a;
             }
         }
+        // (the next writes to bc come after the next grid barrier, which begins with a __syncthreads)
     }
     SEIR_TSTAMP(2);
 
     // ---- representatives of the roots, leader (smallest root slot) of every component
+    // (from here on hi[k] is the replica's n_reached -- the last level appended nothing -- and n_r[k] its n_roots)
     if (serving) {
-        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+        int kk = 0;
+        for (int rep = my_slot; rep < cx.n_rep && kk < kMaxRepsPerCta; rep += reps_per_sweep, ++kk) {
             make(rep, tv, tp);
-            const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            const uint32_t R = n_r[kk];
             for (uint32_t k = gw * 32u + (uint32_t)lane; k < R; k += ngw * 32u) {
                 const uint32_t rp = uf_find(tp.comp, __ldcg(tp.roots + k), stamp);
                 __stcg(tp.reps + k, rp);
@@ -1683,9 +1745,10 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     SEIR_TSTAMP(3);
     // ---- component sizes (the capacity of the leader's search stack)
     if (serving) {
-        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+        int kk = 0;
+        for (int rep = my_slot; rep < cx.n_rep && kk < kMaxRepsPerCta; rep += reps_per_sweep, ++kk) {
             make(rep, tv, tp);
-            const uint32_t NR = __ldcg(&tp.ctl->n_reached);
+            const uint32_t NR = hi[kk];
             for (uint32_t idx = gw * 32u + (uint32_t)lane; idx < NR; idx += ngw * 32u) {
                 const uint32_t L = (uint32_t)__ldcg(tp.lead + uf_find(tp.comp, __ldcg(tp.reached + idx), stamp));
                 atomicAdd(tp.csz + L, 1u);
@@ -1696,9 +1759,10 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     SEIR_TSTAMP(4);
     // ---- every component: its roots in ascending order -- by one warp, or by a whole CTA when the component is large
     if (serving) {
-        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+        int kk = 0;
+        for (int rep = my_slot; rep < cx.n_rep && kk < kMaxRepsPerCta; rep += reps_per_sweep, ++kk) {
             make(rep, tv, tp);
-            const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            const uint32_t R = n_r[kk];
             bool ok = true;
             for (uint32_t k = gw; k < R; k += ngw) {
                 const uint32_t rp = __ldcg(tp.reps + k);
@@ -1736,9 +1800,10 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
     SEIR_TSTAMP(5);
     if (serving) {
         uint32_t *wc = sm.tally;  // [kWarps + 2] scratch
-        for (int rep = my_slot; rep < cx.n_rep; rep += reps_per_sweep) {
+        int kk = 0;
+        for (int rep = my_slot; rep < cx.n_rep && kk < kMaxRepsPerCta; rep += reps_per_sweep, ++kk) {
             make(rep, tv, tp);
-            const uint32_t R = __ldcg(&tp.ctl->n_roots);
+            const uint32_t R = n_r[kk];
             const uint32_t n_big = min(__ldcg(&tp.ctl->n_big), (uint32_t)kBigCap);
             bool ok = true;
             for (uint32_t q = (uint32_t)my_part; q < n_big; q += (uint32_t)bpr) {  // (CTA-uniform)

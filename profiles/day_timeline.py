@@ -9,7 +9,7 @@ from covid19_demography_b200 import engine, population, tables
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-p, tabs = bench.workload_params(n, 60)
+p, tabs = bench.workload_params(n, int(os.environ.get("T", "60")))  # T=30: only sparse passes
 if os.environ.get("TRACING"):  # the reference as compiled: tracing switches on at day 37 (run_simulation.py:115-116)
     p["t_tracing_start"] = float(os.environ["TRACING"])
 hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
@@ -37,7 +37,7 @@ if os.environ.get("FINE"):
     f = out.reshape(-1, 16).astype(float)
     day = np.zeros(eng.T + 2, dtype=np.int64)
     eng.lib.seir_get_day_times(eng._h, day.ctypes.data)
-    names = "entry rec/build tallies dayblk progr store hhloads hhdraws comm-end ret".split()
+    names = "grab entry rec tallies dayblk progr+store hhloads pushes ret append".split()
     for t in range(1, eng.T):
         rel = [(f[t, k] - day[t]) / 1e3 if f[t, k] > 0 else float("nan") for k in range(10)]
         print("pass %2d fine: " % t + " ".join("%s=%.2f" % (n, x) for n, x in zip(names, rel)))
