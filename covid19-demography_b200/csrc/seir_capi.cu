@@ -423,7 +423,8 @@ struct seir_handle {
     DevBuf<uint32_t> log_head, log_cnt, rootbits, rootsum, root_cnt, trc, tstack, rootsum2, treached, troots, treps, tcsz;
     DevBuf<unsigned long long> tcomp, tlead, ttotal;
     DevBuf<TraceCtl> tctl;
-    DevBuf<uint32_t> tcta, tbig;
+    DevBuf<uint32_t> tcta, tbig, tedge_off, tedge_cnt, tedge;
+    uint32_t tedge_cap = 0;
     DevBuf<unsigned long long> tmark;
     double p_hh_scalar = 0.0;
     bool p_hh_uniform = true;
@@ -508,6 +509,13 @@ static int alloc_state(seir_handle *h)
         CK(h->tctl.alloc(R));
         CK(h->tcta.alloc(R * 2048));  // (grids of up to 2048 CTAs)
         CK(h->tbig.alloc(R * kBigCap));
+        // the day's edge cache: room for (household size - 1 + log entries) of every agent the frontier reaches; a day
+        // that needs more makes the searches evaluate the remaining agents' edges from the log again
+        h->tedge_cap = (uint32_t)(2 * np + 1024);
+        if (const char *dc = getenv("SEIR_DEBUG_TEDGE_CAP")) h->tedge_cap = (uint32_t)atoi(dc);  // (tests: exercise the fall-back)
+        CK(h->tedge_off.alloc(R * np));
+        CK(h->tedge_cnt.alloc(R * np));
+        CK(h->tedge.alloc(R * h->tedge_cap));
         CK(h->ttotal.alloc(2));
         CK(cudaMemset(h->ttotal.p, 0, 16));
         h->trace_alloc = true;
@@ -570,6 +578,8 @@ static void fill_ctx(seir_handle *h)
     c.treps = par ? h->treps.p : nullptr; c.tcsz = par ? h->tcsz.p : nullptr;
     c.tctl = par ? h->tctl.p : nullptr; c.ttotal = par ? h->ttotal.p : nullptr;
     c.tcta = par ? h->tcta.p : nullptr; c.tbig = par ? h->tbig.p : nullptr;
+    c.tedge_off = par ? h->tedge_off.p : nullptr; c.tedge_cnt = par ? h->tedge_cnt.p : nullptr;
+    c.tedge = par ? h->tedge.p : nullptr; c.tedge_cap = par ? h->tedge_cap : 0u;
     c.t_lockdown = p.t_lockdown; c.t_stayhome = p.t_stayhome_start; c.mode = p.mode;
     c.p_doc = p.p_documented_in_mild; c.p_contact = p.p_infect_given_contact; c.asym = p.asymptomatic_transmissibility;
     c.m_sev = p.mean_time_to_severe; c.m_mild_rec = p.mean_time_mild_recovery; c.m_crit = p.mean_time_to_critical;
@@ -1118,6 +1128,7 @@ void seir_destroy(seir_handle *h)
     h->root_cnt.release(); h->tmark.release(); h->trc.release(); h->tstack.release();
     h->rootsum2.release(); h->tcomp.release(); h->tlead.release(); h->treached.release(); h->troots.release();
     h->treps.release(); h->tcsz.release(); h->tctl.release(); h->ttotal.release(); h->tcta.release(); h->tbig.release();
+    h->tedge_off.release(); h->tedge_cnt.release(); h->tedge.release();
     h->alias_idx.release(); h->stage_ns.release(); h->fine_ns.release();
     if (h->ev3) cudaEventDestroy(h->ev3);
     if (h->ev0) cudaEventDestroy(h->ev0);

@@ -171,6 +171,9 @@ struct DevCtx {
     uint32_t *treached, *troots, *treps, *tcsz;  // [rep][n_pad]
     struct TraceCtl *tctl;         // [rep]
     uint32_t *tcta;                // [rep][grid] roots found by each CTA in its slice of the root bitmap
+    uint32_t *tedge_off, *tedge_cnt;  // [rep][n_pad] the day's successful edges of a reached agent: first slot in tedge / how many (kEdgeNotCached: none kept)
+    uint32_t *tedge;               // [rep][tedge_cap] target | kEdgeHH | kEdgeToday, written by the frontier step, read by every root's search
+    uint32_t tedge_cap;
     uint32_t *tbig;                // [rep][kBigCap] leaders (root slots) of the components that get a whole CTA
     int dbg_pass;                  // (debug builds with -DSEIR_CTA_STAMPS) the pass whose per-CTA stage stamps go to fine_ns; env SEIR_DEBUG_PASS
     uint32_t tday0;                // run number << 12: the tracer's day stamps (tmark, tcomp, tlead) are tday0 + t and never need clearing
@@ -1069,6 +1072,8 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
 // explicit stack; its 32 lanes evaluate the edges of the node being expanded (household members and log
 // entries) in parallel.  Every draw is keyed on (tracer, day, site, edge slot), so re-expansions by later
 // roots -- which the reference performs, its outside edges have no `traced` guard -- repeat the same draws.
+// the day's edge cache (see trace_expand_superset): one word per successful edge
+constexpr uint32_t kEdgeHH = 0x80000000u, kEdgeToday = 0x40000000u, kEdgeTarget = 0x3FFFFFFFu, kEdgeNotCached = 0xFFFFFFFFu;
 struct TraceView {
     int rep, t;
     uint32_t root;
@@ -1079,6 +1084,7 @@ struct TraceView {
     uint32_t *trc;
     unsigned long long *tmark;
     uint32_t *tally_day;  // tally rows of day t
+    const uint32_t *eoff, *ecnt, *edge;  // the day's edge cache (parallel tracer; nullptr: evaluate the edges from the log)
 };
 
 __device__ __forceinline__ unsigned long long tkey(int t, uint32_t root) { return ((unsigned long long)t << 32) | ((unsigned long long)root + 1ull); }
@@ -1152,6 +1158,55 @@ __device__ __forceinline__ bool trace_expand_exact(const DevCtx &cx, const Trace
     const uint32_t *log_head = cx.log_head + (size_t)tv.rep * cx.n_pad;
     const uint4 *log_ent = cx.log_ent + (size_t)tv.rep * cx.log_cap;
     bool ok_all = true;
+    // ---- the edges whose draws succeeded, kept by the frontier step of the parallel tracer: only the guards that
+    // depend on the root and on what earlier roots did remain to be checked
+    const uint32_t n_cached = tv.ecnt ? __ldcg(tv.ecnt + c) : kEdgeNotCached;
+    if (n_cached != kEdgeNotCached) {
+        const uint32_t *edges = tv.edge + __ldcg(tv.eoff + c);
+        for (uint32_t e0 = 0; e0 < n_cached; e0 += 32u) {
+            const uint32_t e = e0 + (uint32_t)lane;
+            bool ok = false;
+            uint32_t target = 0;
+            unsigned long long w = 0ull;
+            AgentRec mrec;
+            mrec.clear();
+            if (e < n_cached) {
+                const uint32_t ed = __ldcg(edges + e);
+                target = ed & kEdgeTarget;
+                if (ed & kEdgeHH) {  // (:68-77) not S[t-1, contact] held when the edge was kept; traced[contact] is today's state
+                    w = __ldcg(tv.winner + target);
+                    mrec = load_rec(tv.rec + target);
+                    bool traced = (mrec.state() & ST_DOC) != 0;
+                    if (traced && (int)mrec.t_documented() == t && target > root &&
+                        (int)(__ldcg(tv.tmark + target) >> 32) != td)
+                        traced = false;
+                    ok = !traced;
+                } else if (!(ed & kEdgeToday) || c < root) {  // (:79-88) today's entries exist only if c's iteration came first
+                    w = __ldcg(tv.winner + target);
+                    if (wday(w) != t) mrec = load_rec(tv.rec + target);
+                    ok = true;
+                }
+            }
+            if (ok) {
+                const unsigned long long old = atomicExch(tv.tmark + target, key);
+                if (old == key) ok = false;  // already reached under this root
+                else trace_mark(cx, tv, target, w, mrec);
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (m) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(n_ptr, (uint32_t)__popc(m));
+                at = __shfl_sync(0xFFFFFFFFu, at, 0);
+                if (ok) {
+                    const uint32_t mine = at + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    if (mine < cap) __stcg(list + mine, target);
+                }
+                if (at + (uint32_t)__popc(m) > cap) ok_all = false;
+            }
+            __syncwarp();
+        }
+        return ok_all;
+    }
     const uint16_t stt = __ldg(cx.stat + c);
     const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
     const uint32_t base = c - (uint32_t)pos;
@@ -1288,6 +1343,7 @@ __device__ __noinline__ void trace_pass(const DevCtx &cx, TraceSmem &ts, int t)
         tv.trc = cx.trc + (size_t)rep * cx.n_pad;
         tv.tmark = cx.tmark + (size_t)rep * cx.n_pad;
         tv.tally_day = cx.tally + ((size_t)rep * cx.T + t) * TAL_ROWS * kAges;
+        tv.eoff = tv.ecnt = tv.edge = nullptr;  // (no frontier step here: every edge is evaluated from the log)
         uint32_t *bits = cx.rootbits + (size_t)rep * (cx.n_pad / 32);
         uint32_t *sums = cx.rootsum + (size_t)rep * (cx.n_pad / 1024);
         uint32_t *stack = cx.tstack + (size_t)rep * cx.n_pad;
@@ -1362,6 +1418,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 // calls trace_parallel().
 struct TraceCtl {          // per replica
     uint32_t n_roots, n_reached, alloc, n_big;
+    uint32_t edges;        // slots of the edge cache handed out today
     uint32_t appended[2];  // nodes appended to the frontier by the even / odd levels of the day (cumulative)
 };
 
@@ -1420,13 +1477,24 @@ __device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const Tr
     L = __shfl_sync(0xFFFFFFFFu, L, 0);
     __syncwarp();
     const uint32_t n_edges = (uint32_t)(size - 1) + L;
+    // The successful edges of c are kept for the searches of the roots (trace_expand_exact): every root that reaches c
+    // would otherwise walk c's log, rank its entries and draw again.  Room for all n_edges is reserved up front (the
+    // successes are written compactly at its start); when the cache is full the searches fall back to the log.
+    uint32_t ebase = kEdgeNotCached, ekept = 0;
+    if (lane == 0 && n_edges != 0u) {
+        const uint32_t at = atomicAdd(&tp.ctl->edges, n_edges);
+        if (at + n_edges <= cx.tedge_cap) ebase = at;
+    }
+    ebase = __shfl_sync(0xFFFFFFFFu, ebase, 0);
+    uint32_t *epool = cx.tedge + (size_t)tv.rep * cx.tedge_cap;
     for (uint32_t e0 = 0; e0 < n_edges; e0 += 32u) {
         const uint32_t e = e0 + (uint32_t)lane;
         bool ok = false;
-        uint32_t target = 0;
+        uint32_t target = 0, eflags = 0;
         if (e < (uint32_t)(size - 1)) {
             const int j = (int)e;
             target = base + (uint32_t)j + (j >= pos ? 1u : 0u);
+            eflags = kEdgeHH;
             const unsigned long long w = __ldcg(tv.winner + target);
             if (w != 0ull && wday(w) != t) {
                 const AgentRec m = load_rec(tv.rec + target);
@@ -1439,8 +1507,14 @@ __device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const Tr
             uint32_t rank = 0;
             for (uint32_t q = 0; q < L; ++q) rank += ts.ent_key[q] < kk ? 1u : 0u;
             target = ts.ent_x[k];
+            if ((int)(kk >> 16) >= t) eflags = kEdgeToday;
             if (rank < (uint32_t)kLogWidth)
                 ok = sd_lane(draw_block(tv.seed, c, (uint32_t)t, SD_SITE_TR_OUT, rank), 0) < cx.p_trace_out;
+        }
+        {
+            const unsigned mk = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok && ebase != kEdgeNotCached) __stcg(epool + ebase + ekept + (uint32_t)__popc(mk & ((1u << lane) - 1u)), target | eflags);
+            ekept += (uint32_t)__popc(mk);
         }
         bool fresh = false;
         if (ok) {
@@ -1463,6 +1537,10 @@ __device__ __forceinline__ void trace_expand_superset(const DevCtx &cx, const Tr
             if (fresh) __stcg(tp.reached + at + (uint32_t)__popc(m & ((1u << lane) - 1u)), target);
         }
         __syncwarp();
+    }
+    if (lane == 0) {
+        __stcg(cx.tedge_off + (size_t)tv.rep * cx.n_pad + c, ebase);
+        __stcg(cx.tedge_cnt + (size_t)tv.rep * cx.n_pad + c, ebase != kEdgeNotCached || n_edges == 0u ? ekept : kEdgeNotCached);
     }
 }
 
@@ -1553,6 +1631,9 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
         tv.trc = cx.trc + (size_t)rep * cx.n_pad;
         tv.tmark = cx.tmark + (size_t)rep * cx.n_pad;
         tv.tally_day = cx.tally + ((size_t)rep * cx.T + t) * TAL_ROWS * kAges;
+        tv.eoff = cx.tedge_off + (size_t)rep * cx.n_pad;
+        tv.ecnt = cx.tedge_cnt + (size_t)rep * cx.n_pad;
+        tv.edge = cx.tedge + (size_t)rep * cx.tedge_cap;
         tp.comp = cx.tcomp + (size_t)rep * cx.n_pad;
         tp.lead = cx.tlead + (size_t)rep * cx.n_pad;
         tp.reached = cx.treached + (size_t)rep * cx.n_pad;
@@ -1635,6 +1716,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                 tp.ctl->n_big = 0;
                 tp.ctl->appended[0] = 0;
                 tp.ctl->appended[1] = 0;
+                tp.ctl->edges = 0;
             }
             if (warp_cnt[k * (kWarps + 1) + wib] == 0u) continue;
             uint32_t *bits = cx.rootbits + (size_t)rep * n_words;

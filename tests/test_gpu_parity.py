@@ -135,6 +135,19 @@ def test_tracing_with_replicas_and_launch_modes(gpu_engine_module, launch):
     eng.close()
 
 
+def test_tracing_with_a_full_edge_cache(gpu_engine_module, monkeypatch):
+    """The parallel tracer keeps the day's successful edges for the searches of the roots; with room for only 40 of them
+    most agents fall back to evaluating their edges from the log again -- same result."""
+    monkeypatch.setenv("SEIR_DEBUG_TEDGE_CAP", "40")
+    c = util.Case("italy_tracing")
+    params = dict(c.params)
+    tup, ex, home, init = c.keyed_oracle("native", params)
+    eng = c.gpu_engine(gpu_engine_module, params, "native")
+    eng.run([c.seed], [home], [init])
+    _compare(eng, tup, ex, c, int(params["T"]))
+    eng.close()
+
+
 def test_tracing_off_is_the_papers_semantics(gpu_engine_module):
     """tracing_enabled = 0: `tracing_enabled` False at :241, whatever t_tracing_start says."""
     c = util.Case("italy_tracing")
