@@ -321,7 +321,7 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - e0
     home_used = 1 <= p["t_stayhome_start"] < T  # (C2: stay-home never starts, Home_real is never read nor copied)
     h2d = R * ((n if home_used else 0) + 8 * n_init + 8)
-    d2h = R * (T * 9 * 101 * 4)
+    d2h = R * (T * 10 * 101 * 4 + 32)  # the device's ten tally rows per day and age (uint32) + the run counters, to pinned host memory
 
     agent_days_step = float(n) * (T - 1) * R
     loop_ms_local = loop_ms  # the roofline line describes rank 0's own kernel

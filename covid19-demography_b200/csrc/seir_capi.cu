@@ -423,6 +423,12 @@ struct seir_handle {
     DevBuf<uint32_t> log_head, log_cnt, rootbits, rootsum, root_cnt, trc, tstack, rootsum2, treached, troots, treps, tcsz;
     DevBuf<unsigned long long> tcomp, tlead, ttotal;
     DevBuf<TraceCtl> tctl;
+    // results every caller reads after a run (tallies, counters): copied to pinned host memory by the run itself, on a
+    // second stream, while the history is being materialised
+    uint32_t *tally_host = nullptr;
+    unsigned long long *counters_host = nullptr;
+    bool host_results = false;  // the pinned copies hold the last run's results
+    cudaStream_t copy_stream = nullptr;
     DevBuf<uint32_t> tcta, tbig, tedge_off, tedge_cnt, tedge;
     uint32_t tedge_cap = 0;
     DevBuf<unsigned long long> tmark;
@@ -525,6 +531,16 @@ static int alloc_state(seir_handle *h)
     CK(h->list_cnt.alloc(R * 3 * (T + 2)));
     CK(h->day_ns.alloc(T + 2));
     CK(cudaMemset(h->day_ns.p, 0, (T + 2) * 8));
+    {
+        const size_t tb = R * T * TAL_ROWS * kAges * 4;
+        h->host_results = false;
+        if (h->tally_host) { cudaFreeHost(h->tally_host); h->tally_host = nullptr; }  // (re-allocation for a longer T)
+        if (h->counters_host) { cudaFreeHost(h->counters_host); h->counters_host = nullptr; }
+        if (tb <= ((size_t)256 << 20)) {  // (beyond that the getters copy on demand)
+            CK(cudaHostAlloc((void **)&h->tally_host, tb, cudaHostAllocDefault));
+            CK(cudaHostAlloc((void **)&h->counters_host, R * 4 * 8, cudaHostAllocDefault));
+        }
+    }
     CK(h->fine_ns.alloc((T + 2) * 16));
     CK(cudaMemset(h->fine_ns.p, 0, (T + 2) * 16 * 8));
     CK(h->stage_ns.alloc((T + 2) * 8));
@@ -684,6 +700,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CKB(cudaEventCreate(&h->ev0)); CKB(cudaEventCreate(&h->ev1)); CKB(cudaEventCreate(&h->ev2));
         CKB(cudaEventCreate(&h->ev3));
+        CKB(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CKB(h->stat.alloc((size_t)h->n_pad));
         CKB(cudaMemcpy(h->stat.p, stat.data(), (size_t)h->n_pad * 2, cudaMemcpyHostToDevice));
         CKB(h->grp_off.alloc(kAges + 1));
@@ -894,11 +911,21 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(h->ev2, h->stream));
+    h->host_results = false;
+    if (h->tally_host) {  // tallies and counters are final here: bring them home while the history is written
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev2, 0));
+        CK(cudaMemcpyAsync(h->counters_host, h->counters.p, (size_t)R * 4 * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(h->tally_host, h->tally.p, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     seir_materialize_kernel<<<h->sms * 8, kMatThreads, 0, h->stream>>>(h->cx);
     ++h->launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev3, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->tally_host) {
+        CK(cudaStreamSynchronize(h->copy_stream));
+        h->host_results = true;
+    }
     CK(cudaEventElapsedTime(&h->loop_ms, h->ev1, h->ev2));
     CK(cudaEventElapsedTime(&h->mat_ms, h->ev2, h->ev3));
     CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev3));
@@ -917,7 +944,8 @@ int seir_run(seir_handle *h, const seir_replica *reps)
 #endif
     if (tracing) {
         std::vector<unsigned long long> c((size_t)R * 4);
-        CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));
+        if (h->host_results) memcpy(c.data(), h->counters_host, c.size() * 8);
+        else CK(cudaMemcpy(c.data(), h->counters.p, c.size() * 8, cudaMemcpyDeviceToHost));
         for (int r = 0; r < R; ++r) {
             if (c[(size_t)r * 4] & 1ull) return fail("contact tracing: the outside-infection log overflowed (more hits than 1.25 n)");
             if (c[(size_t)r * 4] & 2ull) {
@@ -955,12 +983,19 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
     CK(cudaSetDevice(h->device));
     const int T = h->prm.T;
     const size_t per = (size_t)T * TAL_ROWS * kAges;
-    std::vector<uint32_t> raw(per);
-    CK(cudaMemcpy(raw.data(), h->tally.p + (size_t)replica * per, per * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> own;
+    const uint32_t *raw_p;
+    if (h->host_results) {
+        raw_p = h->tally_host + (size_t)replica * per;
+    } else {
+        own.resize(per);
+        CK(cudaMemcpy(own.data(), h->tally.p + (size_t)replica * per, per * 4, cudaMemcpyDeviceToHost));
+        raw_p = own.data();
+    }
     // planes in the order of seir_individual.py:392: S,E,Mild,Documented,Severe,Critical,R,D,Q
     std::vector<int64_t> cumE(kAges, 0), cumR(kAges, 0), cumD(kAges, 0), cumDoc(kAges, 0), cumQ2(kAges, 0);
     for (int t = 0; t < T; ++t) {
-        const uint32_t *d = raw.data() + (size_t)t * TAL_ROWS * kAges;
+        const uint32_t *d = raw_p + (size_t)t * TAL_ROWS * kAges;
         int64_t *o = out + (size_t)t * SEIR_N_TALLY * kAges;
         for (int a = 0; a < kAges; ++a) {
             cumE[a] += d[TAL_NEW_E * kAges + a];
@@ -1071,7 +1106,8 @@ int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
     if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
     CK(cudaSetDevice(h->device));
     unsigned long long c[4];
-    CK(cudaMemcpy(c, h->counters.p + (size_t)replica * 4, sizeof c, cudaMemcpyDeviceToHost));
+    if (h->host_results) memcpy(c, h->counters_host + (size_t)replica * 4, sizeof c);
+    else CK(cudaMemcpy(c, h->counters.p + (size_t)replica * 4, sizeof c, cudaMemcpyDeviceToHost));
     out4[0] = h->launches; out4[1] = (int64_t)c[1]; out4[2] = (int64_t)c[2]; out4[3] = (int64_t)c[3];
     return 0;
 }
@@ -1135,6 +1171,9 @@ void seir_destroy(seir_handle *h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->tally_host) cudaFreeHost(h->tally_host);
+    if (h->counters_host) cudaFreeHost(h->counters_host);
     delete h;
 }
 
