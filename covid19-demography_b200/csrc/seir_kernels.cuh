@@ -821,7 +821,24 @@ static __device__ __forceinline__ void append_survivors(PassSmem &sm, int keep, 
 }
 
 // both staging halves to tomorrow's list (the whole CTA; ends with the staging counters reset)
-static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_new)
+// right after stage A, when the round's survivors are staged: thread 0 / thread 32 reserve their room in tomorrow's
+// lists.  The returned offsets stay in a register until the flush, so the two round trips to L2 overlap the stages
+// in between instead of standing in front of the grid barrier.
+static __device__ __forceinline__ uint32_t reserve_survivors(PassSmem &sm)
+{
+    const RepView &v = sm.v;
+    uint32_t base = 0;
+    if (threadIdx.x == 0) {
+        const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
+        if (so) base = atomicAdd(v.next_old_cnt, so);
+    } else if (threadIdx.x == 32) {
+        const uint32_t sq = sm.n_oldq < (uint32_t)kOutHalf ? sm.n_oldq : (uint32_t)kOutHalf;
+        if (sq) base = atomicAdd(v.next_oldq_cnt, sq);
+    }
+    return base;
+}
+
+static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_new, uint32_t reserved)
 {
     const RepView &v = sm.v;
     const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
@@ -829,9 +846,8 @@ static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_
     const uint32_t sn = flush_new ? (sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew) : 0u;
     __syncthreads();
     if (so | sq | sn) {
-        // (the three reservations are independent round trips to L2: three warps issue them side by side)
-        if (threadIdx.x == 0 && so) { sm.base_old = atomicAdd(v.next_old_cnt, so); sm.n_old = 0; }
-        if (threadIdx.x == 32 && sq) { sm.base_oldq = atomicAdd(v.next_oldq_cnt, sq); sm.n_oldq = 0; }
+        if (threadIdx.x == 0 && so) { sm.base_old = reserved; sm.n_old = 0; }
+        if (threadIdx.x == 32 && sq) { sm.base_oldq = reserved; sm.n_oldq = 0; }
         if (threadIdx.x == 64 && sn) { sm.base_new = atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
         __syncthreads();
 #ifdef SEIR_CHECKS
@@ -915,6 +931,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         const uint32_t rounds = (my_groups + kGroupsPerRound - 1u) / kGroupsPerRound;
         SEIR_STAMP(0);
 
+        uint32_t reserved = 0;  // thread 0 / 32: offset of the round's staged survivors in tomorrow's list
         for (uint32_t round = 0; round < rounds; ++round) {
             // ================= stage A: the round's groups, grabbed by the warps =================
             const uint32_t g_lo = round * kGroupsPerRound;
@@ -973,6 +990,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 __syncthreads();
             }
             SEIR_STAMP(2);
+            reserved = reserve_survivors(sm);  // (nobody stages a survivor after this point of the round)
             // ================= stage D: draw items =================
             if (sm.n_draw) {
                 const uint32_t nd = sm.n_draw < (uint32_t)kDrawCap ? sm.n_draw : (uint32_t)kDrawCap;
@@ -1020,7 +1038,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             __syncthreads();
             // more rounds follow: empty the staging buffers
             if (round + 1u < rounds) {
-                flush_survivors(sm, sm.n_new > (uint32_t)(kOutNew - kHitCap));
+                flush_survivors(sm, sm.n_new > (uint32_t)(kOutNew - kHitCap), reserved);
                 if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
                 __syncthreads();
             }
@@ -1028,7 +1046,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             stamped = true;
         }
         stamped = false;
-        flush_survivors(sm, true);
+        flush_survivors(sm, true, reserved);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
@@ -1378,30 +1396,42 @@ __device__ __noinline__ void trace_pass(const DevCtx &cx, TraceSmem &ts, int t)
     }
 }
 
-// grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency)
-// Two levels: the CTAs arrive in groups of kBarGroup on per-group counters (one 128 B line each -- 296 atomics
-// on ONE word serialise at its L2 slice), the last CTA of a group arrives on the global counter, everybody polls
-// the global counter.  `target` = barrier number * gridDim.x as before (kept for the call sites); word 0 of the
-// buffer is the flat counter of the sharded barrier, words 32.. the global / group counters of this one.
+// grid-wide barrier on a monotonically increasing counter (cooperative launch guarantees residency): thread 0 of
+// every CTA arrives with ONE release reduction (nothing to wait for) and polls the same word with acquire loads.
+// What counts is the time from the LAST arrival to the release of everybody, and the CTAs that arrive early have long
+// finished by then.  The two-level variant (groups of kBarGroup CTAs on their own lines, the last of a group arrives
+// on the global word) needs two dependent atomics on that path and measured slower.  `target` = barrier number *
+// gridDim.x; word 0 of the buffer is the counter of the sharded barrier, words 32.. belong to this one.
+#ifndef SEIR_FLAT_BARRIER
+#define SEIR_FLAT_BARRIER 1   // (measured on C2: day loop 1.391 ms flat against 1.430 ms two-level)
+#endif
+
 constexpr unsigned int kBarGroup = 16, kBarStride = 32;
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int epoch = target / gridDim.x;
+        unsigned int seen;
+#if SEIR_FLAT_BARRIER
+        // one word: a release reduction (no return value to wait for) and an acquire poll
+        unsigned int *global = counter + kBarStride;
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(global), "r"(1u) : "memory");
+        do {  // (polling with relaxed loads and one fence at the end measured slower: 1.400 against 1.385 ms)
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(global) : "memory");
+        } while (seen < epoch * gridDim.x);
+#else
         const unsigned int g = blockIdx.x / kBarGroup, n_groups = (gridDim.x + kBarGroup - 1u) / kBarGroup;
         const unsigned int size = min(kBarGroup, gridDim.x - g * kBarGroup);
         unsigned int *global = counter + kBarStride, *group = counter + (2u + g) * kBarStride;
-        __threadfence();
-        if (atomicAdd(group, 1u) + 1u == epoch * size) {  // the last one of the group
-            __threadfence();
-            atomicAdd(global, 1u);
-        }
-        unsigned int seen;
+        unsigned int before;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(before) : "l"(group), "r"(1u) : "memory");
+        if (before + 1u == epoch * size)  // the last one of the group
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(global), "r"(1u) : "memory");
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(global) : "memory");
         } while (seen < epoch * n_groups);
-        __threadfence();
+#endif
     }
     __syncthreads();
 }
