@@ -284,6 +284,12 @@ def run_gpu_arm(args):
 
     for w in range(args.warmup):
         eng.run(*inputs(-1 - w))
+    # the K timed steps: the SAME seeds and initial cases for the device-timed pass and for the end-to-end pass (a
+    # run costs 1.1-2.0 ms depending on how large its epidemic grows, so different draws would not be comparable)
+    ins = [inputs(k) for k in range(args.steps)]
+    for _, _, init in ins:
+        for a in init:
+            engine.pin(a)
     # ---- device-timed region
     sync_all()
     sampler.mark_start()
@@ -296,7 +302,7 @@ def run_gpu_arm(args):
             flush.zero_()
             import torch
             torch.cuda.synchronize()
-        eng.run(*inputs(k))
+        eng.run(*ins[k])
         a, b = eng.last_run_ms()
         loop_ms += a
         dev_ms += b
@@ -307,10 +313,6 @@ def run_gpu_arm(args):
     clocks = sampler.finish()
     last_tal = eng.tallies(0)
     # ---- end to end through the C ABI with host buffers (wall clock)
-    ins = [inputs(10000 + k) for k in range(args.steps)]
-    for _, _, init in ins:
-        for a in init:
-            engine.pin(a)
     sync_all()
     e0 = time.perf_counter()
     for k in range(args.steps):

@@ -425,6 +425,8 @@ struct seir_handle {
     DevBuf<TraceCtl> tctl;
     // results every caller reads after a run (tallies, counters): copied to pinned host memory by the run itself, on a
     // second stream, while the history is being materialised
+    unsigned char *in_host = nullptr;  // pinned staging of a run's small inputs
+    size_t in_host_bytes = 0;
     uint32_t *tally_host = nullptr;
     unsigned long long *counters_host = nullptr;
     bool host_results = false;  // the pinned copies hold the last run's results
@@ -829,24 +831,37 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     const int R = h->n_rep;
     const int64_t n = h->n;
     // ---- per-run host inputs -> device
-    std::vector<uint64_t> seeds(R);
-    std::vector<int64_t> off(R + 1, 0);
+    // the run's small inputs (seeds, offsets, the ids of the initial cases as int32) are assembled in ONE pinned host
+    // buffer and copied from there: truly asynchronous copies, no pageable staging inside the driver
+    int64_t n_ids = 0;
+    for (int r = 0; r < R; ++r) {
+        if (reps[r].n_initial < 0 || (reps[r].n_initial > 0 && !reps[r].initial_infected)) return fail("seir_replica.initial_infected is invalid");
+        n_ids += reps[r].n_initial;
+    }
+    const size_t in_bytes = (size_t)R * 8 + (size_t)(R + 1) * 8 + (size_t)n_ids * 4;
+    if (in_bytes > h->in_host_bytes) {
+        if (h->in_host) cudaFreeHost(h->in_host);
+        h->in_host = nullptr; h->in_host_bytes = 0;
+        CK(cudaHostAlloc((void **)&h->in_host, in_bytes + 4096, cudaHostAllocDefault));
+        h->in_host_bytes = in_bytes + 4096;
+    }
+    uint64_t *seeds = reinterpret_cast<uint64_t *>(h->in_host);
+    int64_t *off = reinterpret_cast<int64_t *>(h->in_host + (size_t)R * 8);
+    int32_t *ids = reinterpret_cast<int32_t *>(h->in_host + (size_t)R * 8 + (size_t)(R + 1) * 8);
+    off[0] = 0;
     for (int r = 0; r < R; ++r) {
         seeds[r] = reps[r].seed;
-        if (reps[r].n_initial < 0 || (reps[r].n_initial > 0 && !reps[r].initial_infected)) return fail("seir_replica.initial_infected is invalid");
         off[r + 1] = off[r] + reps[r].n_initial;
-    }
-    std::vector<int32_t> ids((size_t)off[R]);
-    for (int r = 0; r < R; ++r)
         for (int64_t k = 0; k < reps[r].n_initial; ++k) {
             const int64_t a = reps[r].initial_infected[k];
             if (a < 0 || a >= n) return fail("seir_replica.initial_infected holds an id outside [0, n)");
             ids[(size_t)(off[r] + k)] = (int32_t)a;
         }
-    CK(h->init_ids.alloc(ids.size()));
-    CK(cudaMemcpyAsync(h->seeds.p, seeds.data(), R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->init_off.p, off.data(), (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    if (!ids.empty()) CK(cudaMemcpyAsync(h->init_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(h->init_ids.alloc((size_t)n_ids));
+    CK(cudaMemcpyAsync(h->seeds.p, seeds, R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->init_off.p, off, (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (n_ids) CK(cudaMemcpyAsync(h->init_ids.p, ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, h->stream));
     const int64_t n_words = h->n_pad / 32;
     // Home = Home_real only from t_stayhome_start on (:243-244): a run that never gets there never reads the bitmap
     const bool home_used = h->prm.t_stayhome_start >= 1 && h->prm.t_stayhome_start < h->prm.T;
@@ -886,7 +901,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     }
     seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
     ++h->launches;
-    if (!ids.empty()) {
+    if (n_ids) {
         dim3 g(32, R);
         seir_init_infected_kernel<<<g, 128, 0, h->stream>>>(h->cx, h->init_ids.p, h->init_off.p);
         ++h->launches;
@@ -1172,6 +1187,7 @@ void seir_destroy(seir_handle *h)
     if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->in_host) cudaFreeHost(h->in_host);
     if (h->tally_host) cudaFreeHost(h->tally_host);
     if (h->counters_host) cudaFreeHost(h->counters_host);
     delete h;
