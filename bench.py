@@ -362,7 +362,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic if args.traffic is not None else measured_traffic("seir_persistent_kernel"),
                          "kernel": "seir_persistent_kernel" if args.launch == "persistent" else "seir_day_kernel x T",
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": balg * R,
+                         "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0, "algorithmic_bytes_per_launch": balg * R,
                          "active_agent_days": a_sum, "infections": i_sum,
                          "note": "the day loop visits only E/Mild/Severe/Critical agents (L2-resident); the 2n bytes per "
                                  "agent-day of the algorithmic figure are paid once by seir_materialize_kernel as a streaming "
@@ -373,6 +373,7 @@ def run_gpu_arm(args):
         }
         if world == 1 and not args.no_tracing_leg:
             line["config"]["as_reference_tracing"] = tracing_leg(engine, population, tables, args, n, T, local)
+            line["config"]["stress_variant"] = stress_leg(engine, population, tables, args, n, T, local, peak)
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_sample, T)
@@ -505,6 +506,38 @@ def tracing_leg(engine, population, tables, args, n, T, device):
     eng.close()
     return {"t_tracing_start": 37, "ms_per_run": ms[-1], "agent_days_per_sec": float(n) * (T - 1) / (ms[-1] / 1e3),
             "documented_at_end": int(tal[-1, 3].sum()), "deaths_at_end": int(tal[-1, 7].sum())}
+
+
+def stress_leg(engine, population, tables, args, n, T, device, peak):
+    """with 5 initial cases the active fraction stays tiny for 30 days, so the same workload is
+    also run as a stress variant -- 0.1 % of the agents infected at t = 0, no lockdown -- in which up to half of the
+    population is in E/Mild/Severe/Critical at once.  One warm-up + two timed runs; the roofline figure uses the same
+    algorithmic-byte formula on this run's own tallies."""
+    p, tabs = workload_params(n, T)
+    p["initial_infected_fraction"] = 0.001
+    p["t_lockdown"] = 1.0e6
+    hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
+    tb = tables.build_tables(tabs["contact_matrix"], np.array([len(g) for g in groups]), tables.params_to_dict(p),
+                             tabs["mean_time_to_isolate_factor"], tabs["p_mild_severe"], tabs["p_severe_critical"],
+                             tabs["p_critical_death"], with_replay=(args.mode == "replay"))
+    eng = engine.Engine(p, hh, age, groups, diab, hyp, np.full(n, tabs["p_infect_household"]), tb, n_replicas=1,
+                        device=device, mode=args.mode, launch=args.launch)
+    rng = np.random.default_rng(11)
+    loop, total = [], []
+    for k in range(3):
+        init = [rng.choice(n, size=int(p["initial_infected_fraction"] * n), replace=False).astype(np.int64)]
+        eng.run([700 + k], None, init)
+        a, b = eng.last_run_ms()
+        loop.append(a)
+        total.append(b)
+    tal = eng.tallies(0)
+    eng.close()
+    balg, a_sum, i_sum = algorithmic_bytes(tal, n)
+    act = tal[:, [1, 2, 4, 5], :].sum(axis=(1, 2))
+    return {"initial_infected_fraction": 0.001, "lockdown": "never", "ms_per_run": float(np.mean(total[1:])),
+            "day_loop_ms": float(np.mean(loop[1:])), "agent_days_per_sec": float(n) * (T - 1) / (np.mean(total[1:]) / 1e3),
+            "active_agent_days": a_sum, "peak_active_fraction": float(act.max()) / n, "infections": i_sum,
+            "algorithmic_bytes_per_launch": balg, "roofline_frac": balg / (loop[-1] / 1e3) / 1e9 / peak}
 
 
 def main():
