@@ -1090,6 +1090,13 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
 // explicit stack; its 32 lanes evaluate the edges of the node being expanded (household members and log
 // entries) in parallel.  Every draw is keyed on (tracer, day, site, edge slot), so re-expansions by later
 // roots -- which the reference performs, its outside edges have no `traced` guard -- repeat the same draws.
+#ifdef SEIR_TRACE_STATS  // (debug) per-day counters of the parallel tracer in fine_ns[t][k], replica 0 only
+#define SEIR_TSTAT_ADD(k, v) do { if (tv.rep == 0) atomicAdd(cx.fine_ns + (size_t)tv.t * 16 + (k), (unsigned long long)(v)); } while (0)
+#define SEIR_TSTAT_MAX(k, v) do { if (tv.rep == 0) atomicMax(cx.fine_ns + (size_t)tv.t * 16 + (k), (unsigned long long)(v)); } while (0)
+#else
+#define SEIR_TSTAT_ADD(k, v) do { } while (0)
+#define SEIR_TSTAT_MAX(k, v) do { } while (0)
+#endif
 // the day's edge cache (see trace_expand_superset): one word per successful edge
 constexpr uint32_t kEdgeHH = 0x80000000u, kEdgeToday = 0x40000000u, kEdgeTarget = 0x3FFFFFFFu, kEdgeNotCached = 0xFFFFFFFFu;
 struct TraceView {
@@ -1314,6 +1321,7 @@ __device__ __forceinline__ bool trace_root(const DevCtx &cx, const TraceView &tv
         const uint32_t n = min(*(volatile uint32_t *)&ts.n, cap);
         if (lo >= n) break;
         ok_all = trace_expand_exact(cx, tv, ts, __ldcg(list + lo), list, cap, &ts.n) && ok_all;
+        if (lane == 0) SEIR_TSTAT_ADD(5, 1);
         __syncwarp();
     }
     return ok_all;
@@ -1328,6 +1336,7 @@ __device__ __forceinline__ bool trace_root_cta(const DevCtx &cx, const TraceView
         __stcg(tv.tmark + tv.root, tkey((int)cx.tday0 + tv.t, tv.root));
         __stcg(list, tv.root);
         *n_shared = 1;
+        SEIR_TSTAT_ADD(7, 1);
     }
     __syncthreads();
     bool ok_all = true;
@@ -1336,6 +1345,7 @@ __device__ __forceinline__ bool trace_root_cta(const DevCtx &cx, const TraceView
         const uint32_t hi = min(*(volatile uint32_t *)n_shared, cap);
         __syncthreads();  // (everybody has read the level's end before anybody appends)
         if (lo >= hi) break;
+        if (threadIdx.x == 0) { SEIR_TSTAT_ADD(8, 1); SEIR_TSTAT_ADD(4, hi - lo); }
         for (uint32_t idx = lo + (uint32_t)wib; idx < hi; idx += (uint32_t)(kThreads / 32))
             ok_all = trace_expand_exact(cx, tv, ts, __ldcg(list + idx), list, cap, n_shared) && ok_all;
         lo = hi;
@@ -1815,6 +1825,9 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
             }
         }
         grid_barrier(cx.barrier, ++epoch * gridDim.x);
+#ifdef SEIR_TRACE_STATS
+        if (blockIdx.x == 0 && tid == 0) atomicAdd(cx.fine_ns + (size_t)t * 16 + 6, 1ull);
+#endif
         if (tid == 0) {
             const unsigned long long now = __ldcg(counter);
             bc[0] = now == prev_total[par] ? 1u : 0u;
@@ -1846,6 +1859,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
         for (int rep = my_slot; rep < cx.n_rep && kk < kMaxRepsPerCta; rep += reps_per_sweep, ++kk) {
             make(rep, tv, tp);
             const uint32_t R = n_r[kk];
+            if (my_part == 0 && tid == 0) { SEIR_TSTAT_ADD(0, R); SEIR_TSTAT_ADD(1, hi[kk]); }
             for (uint32_t k = gw * 32u + (uint32_t)lane; k < R; k += ngw * 32u) {
                 const uint32_t rp = uf_find(tp.comp, __ldcg(tp.roots + k), stamp);
                 __stcg(tp.reps + k, rp);
@@ -1880,6 +1894,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                 const uint32_t rp = __ldcg(tp.reps + k);
                 if ((uint32_t)__ldcg(tp.lead + rp) != k) continue;
                 const uint32_t cap = __ldcg(tp.csz + k);
+                if (lane == 0 && cap > (uint32_t)kBigComponent) { SEIR_TSTAT_ADD(2, 1); SEIR_TSTAT_MAX(3, cap); }
                 if (cap > (uint32_t)kBigComponent) {  // queued for the CTA pass below
                     uint32_t pos = 0;
                     if (lane == 0) pos = atomicAdd(&tp.ctl->n_big, 1u);
@@ -1946,6 +1961,7 @@ __device__ __noinline__ void trace_parallel(const DevCtx &cx, PassSmem &sm, int 
                     __syncthreads();
                 }
                 const uint32_t n_cr = wc[kWarps + 1];
+                if (tid == 0) SEIR_TSTAT_MAX(9, n_cr);
                 for (uint32_t j = 0; j < n_cr; ++j) {
                     tv.root = __ldcg(croots + j);
                     ok = trace_root_cta(cx, tv, ts, list, cap, &sm.base_old) && ok;
