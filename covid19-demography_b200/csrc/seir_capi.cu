@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
         ++epoch;
         grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
     }
-    const bool defer_counters = cx.n_rep <= reps_per_sweep;  // this CTA serves one replica: its run counters are added once, below
+    const bool defer_counters = cx.n_rep == 1;  // this CTA serves the one replica throughout: its run counters are added once, below
     if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
     for (int t = 1; t <= cx.T; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
@@ -870,8 +870,9 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         if (reps[r].home_real) {
             CK(h->stage_u8.alloc((size_t)n));
             CK(cudaMemcpyAsync(h->stage_u8.p, reps[r].home_real, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+            // (the one staging buffer is reused by the next replica: stream order keeps its copy behind this kernel;
+            // the caller's buffers are borrowed until seir_run returns, and it synchronises before it does)
             seir_pack_home_kernel<<<h->sms * 4, 256, 0, h->stream>>>(h->stage_u8.p, bm, n, n_words);
-            CK(cudaStreamSynchronize(h->stream));  // the borrowed host buffer / staging is reused per replica
         } else {
             CK(cudaMemsetAsync(bm, 0, (size_t)n_words * 4, h->stream));
         }

@@ -313,6 +313,9 @@ constexpr int kSlots = kPerThread * kThreads;        // agents per round and CTA
 constexpr int kConCap = kSlots / SEIR_QUEUE_DIV;                      // contact queue entries per round
 constexpr int kHitCap = kSlots / 2 / SEIR_QUEUE_DIV;                  // hit queue entries per round
 constexpr int kDrawCap = 2 * kSlots / SEIR_QUEUE_DIV;                 // draw-item queue entries per round
+#ifndef SEIR_DYNAMIC_MAP
+#define SEIR_DYNAMIC_MAP 1   // replica ensembles: CTAs are dealt to the replicas anew in every pass, in proportion to their lists
+#endif
 #ifndef SEIR_QUEUE_EVENTS
 #define SEIR_QUEUE_EVENTS 0   // 1: progression events run compacted in stage E; 0: in place in stage A (measured faster on C2)
 #endif
@@ -364,6 +367,7 @@ struct __align__(16) PassSmem {
     uint32_t cnt[4];
     uint32_t list_n[3];            // today's list lengths (new, transmitting, quarantined), read once per CTA
     uint32_t run_cnt[3];           // this CTA's share of the run counters (persistent kernel: flushed once, at the end)
+    int dyn[3];                    // replica ensembles: the replica this CTA serves in the current pass, its part, the replica's CTAs
     uint32_t n_old, n_oldq, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_oldq, base_new, next_group;
 };
 
@@ -881,9 +885,52 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
     const int tid = threadIdx.x;
     bool stamped = false;
     const bool finalize = t >= cx.T;
-    const int bpr = cx.blocks_per_rep;
-    // (CTAs beyond the last full group idle through the pass; they must still reach the grid barrier)
-    for (int rep = my_slot; rep < cx.n_rep && my_slot < reps_per_sweep; rep += reps_per_sweep) {
+    int bpr = cx.blocks_per_rep;
+    int rep_first = my_slot < reps_per_sweep ? my_slot : cx.n_rep, rep_step = reps_per_sweep;
+#if SEIR_DYNAMIC_MAP
+    // Replica ensembles (one CTA never serves two replicas in a pass): the epidemics of an ensemble grow at different
+    // times, and with a fixed share of the grid per replica a pass lasts as long as its largest replica.  So warp 0 of
+    // every CTA reads the list lengths of ALL replicas and deals the grid anew: one CTA per replica, the others in
+    // proportion to the lists; the result does not depend on who processes what.
+    if (cx.n_rep > 1 && cx.n_rep <= (int)gridDim.x && cx.n_shards <= 1) {
+        const int R = cx.n_rep;
+        if (tid < 32) {
+            uint32_t *scratch = sm.hit_n;  // (free until the first round starts)
+            unsigned long long W = 0;
+            for (int r = tid; r < R; r += 32) {
+                const uint32_t *c0 = cx.list_cnt + (size_t)r * 3 * (cx.T + 2) + t;
+                const uint32_t c = __ldcg(c0) + __ldcg(c0 + (cx.T + 2)) + __ldcg(c0 + 2 * (cx.T + 2));
+                scratch[r] = c;
+                W += c;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) W += __shfl_xor_sync(0xFFFFFFFFu, W, o);
+            if (tid == 0) sm.dyn[0] = R;  // (idle unless an interval below holds this CTA)
+            __syncwarp();
+            const uint32_t spare = gridDim.x - (uint32_t)R, b = blockIdx.x;
+            uint32_t carry = 0;
+            for (int r0 = 0; r0 < R; r0 += 32) {
+                const int r = r0 + tid;
+                const uint32_t k = r < R ? 1u + (W ? (uint32_t)((unsigned long long)spare * scratch[r] / W) : 0u) : 0u;
+                uint32_t incl = k;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (tid >= o) incl += up;
+                }
+                const uint32_t excl = carry + incl - k;
+                if (r < R && b >= excl && b < excl + k) { sm.dyn[0] = r; sm.dyn[1] = (int)(b - excl); sm.dyn[2] = (int)k; }
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+        }
+        __syncthreads();
+        rep_first = sm.dyn[0];
+        rep_step = R;
+        if (rep_first < R) { my_part = sm.dyn[1]; bpr = sm.dyn[2]; }
+    }
+#endif
+    // (CTAs without a replica idle through the pass; they must still reach the grid barrier)
+    for (int rep = rep_first; rep < cx.n_rep; rep += rep_step) {
         const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
         uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_oldq = cnt_new + (cx.T + 2);
         const RepView &v = sm.v;
