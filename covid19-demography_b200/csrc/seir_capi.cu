@@ -7,6 +7,10 @@
 #include <vector>
 
 #include "seir_kernels.cuh"
+#ifdef SEIR_SORT_PROBE  // (experiment) what would ID-ordered active lists be worth?  see the per-day branch of seir_run
+#include <thrust/execution_policy.h>
+#include <thrust/sort.h>
+#endif
 
 using namespace seir;
 
@@ -425,6 +429,7 @@ struct seir_handle {
     DevBuf<TraceCtl> tctl;
     // results every caller reads after a run (tallies, counters): copied to pinned host memory by the run itself, on a
     // second stream, while the history is being materialised
+    float probe_ms = 0.0f;             // (SEIR_SORT_PROBE) sum of the day kernels' durations
     unsigned char *in_host = nullptr;  // pinned staging of a run's small inputs
     size_t in_host_bytes = 0;
     uint32_t *tally_host = nullptr;
@@ -915,10 +920,40 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
         ++h->launches;
     } else {
+#ifdef SEIR_SORT_PROBE
+        const bool sort_lists = getenv("SEIR_DEBUG_SORT") && atoi(getenv("SEIR_DEBUG_SORT")) != 0;
+        cudaEvent_t pa, pb;
+        CK(cudaEventCreate(&pa)); CK(cudaEventCreate(&pb));
+        h->probe_ms = 0.0f;
+#endif
         for (int t = 1; t <= h->prm.T; ++t) {
+#ifdef SEIR_SORT_PROBE
+            CK(cudaEventRecord(pa, h->stream));
+#endif
             if (tracing) seir_day_kernel<true><<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
             else seir_day_kernel<false><<<h->grid, kThreads, sizeof(PassSmem), h->stream>>>(h->cx, t);
             ++h->launches;
+#ifdef SEIR_SORT_PROBE
+            {   // the day kernels alone are timed; with SEIR_DEBUG_SORT=1 tomorrow's three list segments are sorted by agent id
+                CK(cudaEventRecord(pb, h->stream));
+                CK(cudaEventSynchronize(pb));
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, pa, pb));
+                h->probe_ms += ms;
+                if (sort_lists && R == 1 && t < h->prm.T) {
+                    uint32_t c[3];
+                    const size_t T2 = (size_t)h->prm.T + 2;
+                    CK(cudaMemcpy(&c[0], h->list_cnt.p + 0 * T2 + (t + 1), 4, cudaMemcpyDeviceToHost));  // transmitting
+                    CK(cudaMemcpy(&c[1], h->list_cnt.p + 1 * T2 + (t + 1), 4, cudaMemcpyDeviceToHost));  // new
+                    CK(cudaMemcpy(&c[2], h->list_cnt.p + 2 * T2 + (t + 1), 4, cudaMemcpyDeviceToHost));  // quarantined
+                    uint32_t *lo = h->list_old.p + (size_t)((t + 1) & 1) * h->n_pad, *ln = h->list_new.p + (size_t)((t + 1) & 1) * h->n_pad;
+                    auto pol = thrust::cuda::par.on(h->stream);
+                    thrust::sort(pol, lo, lo + c[0]);
+                    thrust::sort(pol, lo + (h->n_pad - c[2]), lo + h->n_pad);
+                    thrust::sort(pol, ln, ln + c[1]);
+                }
+            }
+#endif
             if (tracing && t >= h->cx.trace_from && t < h->prm.T) {
                 seir_trace_kernel<<<R < h->grid ? R : h->grid, 32, sizeof(TraceSmem), h->stream>>>(h->cx, t);
                 ++h->launches;
@@ -943,6 +978,9 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         h->host_results = true;
     }
     CK(cudaEventElapsedTime(&h->loop_ms, h->ev1, h->ev2));
+#ifdef SEIR_SORT_PROBE
+    if (h->prm.launch == SEIR_LAUNCH_PER_DAY) h->loop_ms = h->probe_ms;  // (the day kernels alone)
+#endif
     CK(cudaEventElapsedTime(&h->mat_ms, h->ev2, h->ev3));
     CK(cudaEventElapsedTime(&h->total_ms, h->ev0, h->ev3));
     if (h->n_shards > 1) {
