@@ -81,6 +81,27 @@ def test_replicas_are_independent_runs(gpu_engine_module):
     eng.close()
 
 
+@pytest.mark.parametrize("launch", ["persistent", "per_day"])
+def test_uneven_replicas(gpu_engine_module, launch):
+    """An ensemble whose replicas differ wildly in size (no initial case, one, five, 50, 500): the CTAs are dealt to the
+    replicas anew in every pass, in proportion to their active lists -- every replica still equals its own single run."""
+    import oracle
+    c = util.Case("italy_seeded")
+    params = c.no_tracing_params()
+    rng = np.random.default_rng(3)
+    inits = [np.sort(rng.choice(c.n, size=k, replace=False)).astype(np.int64) for k in (0, 1, 5, 50, 500)]
+    seeds = [41, 42, 43, 44, 45]
+    home = np.zeros(c.n, dtype=bool)
+    eng = c.gpu_engine(gpu_engine_module, params, "native", launch=launch, n_replicas=len(seeds))
+    eng.run(seeds, [home] * len(seeds), inits)
+    for r, (s, init) in enumerate(zip(seeds, inits)):
+        tup, ex = oracle.run_model(s, *c.model_args(params), provider="native", tracing_enabled=1, home_real=home,
+                                   initial_infected=init, tables=c.tables(params))
+        _compare(eng, tup, ex, c, int(params["T"]), replica=r)
+    assert eng.tallies(0)[:, 0].sum(axis=1).tolist() == [c.n] * int(params["T"])  # (nobody is ever infected in replica 0)
+    eng.close()
+
+
 def test_draw_contract_on_device(gpu_engine_module):
     """include/seir_draws.h evaluated by the device == by the host compiler, bit for bit."""
     import ctypes as C
