@@ -921,7 +921,8 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         ++h->launches;
     } else {
 #ifdef SEIR_SORT_PROBE
-        const bool sort_lists = getenv("SEIR_DEBUG_SORT") && atoi(getenv("SEIR_DEBUG_SORT")) != 0;
+        const int sort_mask = getenv("SEIR_DEBUG_SORT") ? atoi(getenv("SEIR_DEBUG_SORT")) : 0;  // 1 transmitting, 2 new, 4 quarantined
+        const bool sort_lists = sort_mask != 0;
         cudaEvent_t pa, pb;
         CK(cudaEventCreate(&pa)); CK(cudaEventCreate(&pb));
         h->probe_ms = 0.0f;
@@ -948,9 +949,9 @@ int seir_run(seir_handle *h, const seir_replica *reps)
                     CK(cudaMemcpy(&c[2], h->list_cnt.p + 2 * T2 + (t + 1), 4, cudaMemcpyDeviceToHost));  // quarantined
                     uint32_t *lo = h->list_old.p + (size_t)((t + 1) & 1) * h->n_pad, *ln = h->list_new.p + (size_t)((t + 1) & 1) * h->n_pad;
                     auto pol = thrust::cuda::par.on(h->stream);
-                    thrust::sort(pol, lo, lo + c[0]);
-                    thrust::sort(pol, lo + (h->n_pad - c[2]), lo + h->n_pad);
-                    thrust::sort(pol, ln, ln + c[1]);
+                    if (sort_mask & 1) thrust::sort(pol, lo, lo + c[0]);
+                    if (sort_mask & 4) thrust::sort(pol, lo + (h->n_pad - c[2]), lo + h->n_pad);
+                    if (sort_mask & 2) thrust::sort(pol, ln, ln + c[1]);
                 }
             }
 #endif
