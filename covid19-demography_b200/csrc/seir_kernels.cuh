@@ -842,7 +842,7 @@ static __device__ __forceinline__ uint32_t reserve_survivors(PassSmem &sm)
     return base;
 }
 
-static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_new, uint32_t reserved)
+static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_new, uint32_t reserved, bool new_reserved = false)
 {
     const RepView &v = sm.v;
     const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
@@ -852,7 +852,7 @@ static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_
     if (so | sq | sn) {
         if (threadIdx.x == 0 && so) { sm.base_old = reserved; sm.n_old = 0; }
         if (threadIdx.x == 32 && sq) { sm.base_oldq = reserved; sm.n_oldq = 0; }
-        if (threadIdx.x == 64 && sn) { sm.base_new = atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
+        if (threadIdx.x == 64 && sn) { sm.base_new = new_reserved ? reserved : atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
         __syncthreads();
 #ifdef SEIR_CHECKS
         if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sq && sm.base_oldq + sq > v.n_pad_m1 + 1u) ||
@@ -1060,6 +1060,12 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 __syncthreads();
             }
             SEIR_STAMP(5);
+            // (last round: the day's new infectees of this CTA are all staged -- thread 64 reserves their room in tomorrow's
+            // list now, and the round trip overlaps stage W instead of standing in front of the grid barrier)
+            if (round + 1u == rounds && tid == 64) {
+                const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
+                if (sn) reserved = atomicAdd_system(v.next_new_cnt, sn);
+            }
             // ================= stage W: infector counters (:357-359, :386-390) =================
             {
                 const uint32_t ns = (g_hi - g_lo) * 32u;
@@ -1093,7 +1099,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             stamped = true;
         }
         stamped = false;
-        flush_survivors(sm, true, reserved);
+        flush_survivors(sm, true, reserved, rounds != 0u);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
