@@ -29,16 +29,30 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
+    """Compile to a temporary file and rename it into place under a file lock: bench.py --gpus N, the sharded and the
+    ensemble runs start one process per GPU, and each of them lands here."""
     if not force and not is_stale():
         return LIB
-    cmd = [NVCC] + FLAGS + os.environ.get("SEIR_NVCC_EXTRA", "").split() + ["-o", LIB] + SOURCES
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libseir_b200.so")
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
-        f.write(res.stdout)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():   # another process built it while this one waited
+                return LIB
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [NVCC] + FLAGS + os.environ.get("SEIR_NVCC_EXTRA", "").split() + ["-o", tmp] + SOURCES
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libseir_b200.so")
+            os.replace(tmp, LIB)
+            with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:   # (git-ignored: registers / spills of this build)
+                f.write(res.stdout)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -35,10 +35,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     }
     const bool defer_counters = cx.n_rep == 1;  // this CTA serves the one replica throughout: its run counters are added once, below
     if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
-    for (int t = 1; t <= cx.T; ++t) {
+    int bank_staged = -1;  // the table set whose kept-contact table sits in shared memory
+    for (int t = 1; t <= cx.T_loop; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
-        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep, defer_counters);
-        if (t < cx.T) {
+        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep, bank_staged, defer_counters);
+        if (t < cx.T_loop) {
             if (cx.n_shards > 1) {
                 ++epoch;
                 grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
     stage_tables(cx, sm);
-    Pass<TR>::day_pass(cx, sm, t, blockIdx.x / cx.blocks_per_rep, blockIdx.x % cx.blocks_per_rep, gridDim.x / cx.blocks_per_rep);
+    int bank_staged = -1;
+    Pass<TR>::day_pass(cx, sm, t, blockIdx.x / cx.blocks_per_rep, blockIdx.x % cx.blocks_per_rep, gridDim.x / cx.blocks_per_rep, bank_staged);
 }
 
 // contact tracing of day t as its own launch (per-day launch mode)
@@ -102,6 +104,59 @@ __global__ void seir_init_state_kernel(DevCtx cx)
 #pragma unroll
             for (int k = 0; k < 4; ++k) __stcs(hz + k, z);
         }
+    }
+}
+
+// Keyed prologue (:176-187 on the device): replica blockIdx.y makes its own picks.  kcum[rep][0..102] are the prefix
+// sums of the pick counts -- per age int(fraction_stay_home[a] * N_a), then the initial cases int(fraction * n) --
+// or all 0 for a replica whose picks came from the host.  Pick r of group g is entry r of the keyed permutation of
+// the group (include/seir_draws.h, sd_perm): no scan over the n candidates, no counter to contend for.
+__global__ void seir_prologue_kernel(DevCtx cx, const int64_t *kcum_all, int32_t *init_ids, const int64_t *init_off, int home_used)
+{
+    __shared__ int64_t kcum[kAges + 2];
+    __shared__ sd_perm perm[kAges + 1];
+    const int rep = blockIdx.y;
+    for (int g = threadIdx.x; g < kAges + 2; g += blockDim.x) kcum[g] = kcum_all[(size_t)rep * (kAges + 2) + g];
+    __syncthreads();
+    const int64_t total = kcum[kAges + 1];
+    if (total == 0) return;
+    const uint64_t seed = cx.seeds[rep];
+    for (int g = threadIdx.x; g <= kAges; g += blockDim.x) {
+        const uint32_t N = g < kAges ? (uint32_t)(cx.grp_off[g + 1] - cx.grp_off[g]) : (uint32_t)cx.n;
+        if (kcum[g + 1] > kcum[g]) perm[g] = sd_perm_make(seed, g < kAges ? SD_SITE_HOME : SD_SITE_CASES, g < kAges ? (uint32_t)g : 0u, N);
+    }
+    __syncthreads();
+    uint32_t *home = cx.home_rw + (size_t)rep * (cx.n_pad / 32);
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = kAges + 1;  // group g with kcum[g] <= q < kcum[g + 1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (kcum[mid] <= q) lo = mid; else hi = mid; }
+        const int g = lo;
+        const uint32_t x = sd_perm_at(&perm[g], (uint32_t)(q - kcum[g]));
+        if (g < kAges) {
+            if (home_used) {
+                const uint32_t a = (uint32_t)cx.grp_members[cx.grp_off[g] + (int64_t)x];
+                atomicOr(home + (a >> 5), 1u << (a & 31));
+            }
+        } else {
+            init_ids[init_off[rep] + (q - kcum[kAges])] = (int32_t)x;
+        }
+    }
+}
+
+// SEIR_HISTORY_ON_DEMAND: rows [t0, t1) of one replica's packed history straight from the records
+__global__ void seir_rows_kernel(DevCtx cx, int rep, int t0, int t1, uint8_t *out)
+{
+    const uint32_t *inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+    const AgentRec *rec = cx.rec + (size_t)rep * cx.n_pad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cx.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool ever = (inbox[i >> 4] & inbox_infected_bit((int)(i & 15))) != 0;
+        if (!ever) {
+            for (int t = t0; t < t1; ++t) out[(size_t)(t - t0) * cx.n_pad + i] = 0;
+            continue;
+        }
+        const AgentRec r = load_rec(rec + i);
+        const int t_q2 = (r.flags() & F_TRX) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
+        for (int t = t0; t < t1; ++t) out[(size_t)(t - t0) * cx.n_pad + i] = state_on_day(r, t, t_q2);
     }
 }
 
@@ -181,6 +236,7 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
         const int rep = (int)(g / groups_per_rep);
         const int64_t vi = (g % groups_per_rep) * 32 + lane;  // my vector (16 agents) in the row
         uint8_t *hist = cx.hist + (size_t)rep * cx.T * cx.n_pad;
+        const int Tr = __ldg(&cx.rp[rep].T);  // the replica's own horizon (rows beyond it are never read)
         const AgentRec *rec = cx.rec + (size_t)rep * cx.n_pad + (g % groups_per_rep) * 512;
         uint4 *row = reinterpret_cast<uint4 *>(hist) + vi;
         uint32_t m = __ldcs(cx.inbox + (size_t)rep * row_stride + vi) & 0x0F0F0F0Fu;  // "ever infected" bits
@@ -202,12 +258,12 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
         __syncwarp();
         const uint4 z = make_uint4(0, 0, 0, 0);
         if (n_inf == 0) {
-            for (int t = 0; t < cx.T; ++t) __stcs(row + (int64_t)t * row_stride, z);
+            for (int t = 0; t < Tr; ++t) __stcs(row + (int64_t)t * row_stride, z);
             continue;
         }
         // ---- my share of the agents: entries lane, lane+32, ... (at most kMatPerLane in registers)
         MatAgent ag[kMatPerLane];
-        int t_first = cx.T;
+        int t_first = Tr;
 #pragma unroll
         for (int k = 0; k < kMatPerLane; ++k) {
             const int e = lane + 32 * k;
@@ -223,7 +279,7 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
         for (int o = 16; o > 0; o >>= 1) t_first = min(t_first, __shfl_xor_sync(0xFFFFFFFFu, t_first, o));
         const int n_slots = min(kMatPerLane, (n_inf + 31) / 32);  // warp-uniform
         for (int t = 0; t < t_first; ++t) __stcs(row + (int64_t)t * row_stride, z);  // S everywhere
-        for (int t = t_first; t < cx.T; ++t) {
+        for (int t = t_first; t < Tr; ++t) {
             reinterpret_cast<uint4 *>(tile)[lane] = z;
             __syncwarp();
 #pragma unroll
@@ -243,7 +299,7 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
             const AgentRec r = load_rec(rec + local);
             const int64_t i = (g % groups_per_rep) * 512 + local;
             const int t_q2 = (r.flags() & F_TRX) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
-            for (int t = r.t_exposed(); t < cx.T; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t, t_q2);
+            for (int t = r.t_exposed(); t < Tr; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t, t_q2);
         }
         __syncwarp();
     }
@@ -400,13 +456,23 @@ struct seir_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t ev3 = nullptr;
     float loop_ms = 0.f, total_ms = 0.f, mat_ms = 0.f;
-    long long launches = 0;
+    long long launches = 0, visits = 0;
     DevBuf<uint16_t> stat;
     DevBuf<int32_t> grp_off, grp_members, init_ids, alias_idx;
     DevBuf<int64_t> init_off;
     DevBuf<double> p_hh, tables, enlam, stage_d;
-    DevBuf<uint8_t> hist, stage_u8;
+    DevBuf<uint8_t> hist, stage_u8, hist_prev;
+    int prev_T = 0;   // rows of the history set aside by seir_history_preserve (0: none)
     DevBuf<uint32_t> inbox, tally, home, list_old, list_new, list_cnt;
+    DevBuf<uint32_t> pk_pool;   // day buckets of the parked agents
+    DevBuf<RepParams> rp;       // per-replica overrides of the current run
+    DevBuf<double> bank;        // table sets (seir_set_table_bank); set 0 = the handle's own tables
+    DevBuf<int64_t> kcum;       // keyed prologue: prefix sums of the pick counts per replica
+    int n_sets = 1;
+    std::vector<RepParams> rp_host;
+    std::vector<int64_t> n_init_run;   // initial cases per replica of the last run
+    bool home_valid = false;           // the home bitmaps hold the last run's picks
+    int history_mode = SEIR_HISTORY_EAGER;
     DevBuf<unsigned long long> winner, counters, day_ns, stage_ns, fine_ns;
     DevBuf<AgentRec> rec;
     DevBuf<uint64_t> seeds;
@@ -476,6 +542,32 @@ static int upload_tables(seir_handle *h, const seir_tables *tb)
     return 0;
 }
 
+// one table set of the bank (what a sweep's grid changes, see kBank* in seir_kernels.cuh)
+static void pack_bank_set(const seir_tables *tb, double p_contact, double *dst)
+{
+    memcpy(dst + kBankPms, tb->p_mild_severe, 404 * sizeof(double));
+    memcpy(dst + kBankPsc, tb->p_severe_critical, 404 * sizeof(double));
+    memcpy(dst + kBankPcd, tb->p_critical_death, 404 * sizeof(double));
+    memcpy(dst + kBankNatEn, tb->nat_enlam, 404 * sizeof(double));
+    for (int k = kBankPcontact; k < kBankStride; ++k) dst[k] = p_contact;
+}
+
+static int upload_bank(seir_handle *h, int n_sets, const seir_tables *sets, const double *p_contact)
+{
+    std::vector<double> host((size_t)n_sets * kBankStride);
+    for (int k = 0; k < n_sets; ++k) {
+        const seir_tables *tb = sets + k;
+        if (!tb->p_mild_severe || !tb->p_severe_critical || !tb->p_critical_death || !tb->nat_enlam)
+            return fail("seir_set_table_bank: a set needs p_mild_severe, p_severe_critical, p_critical_death and nat_enlam");
+        pack_bank_set(tb, p_contact[k], host.data() + (size_t)k * kBankStride);
+    }
+    CK(h->bank.alloc(host.size()));
+    CK(cudaMemcpyAsync(h->bank.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_sets = n_sets;
+    return 0;
+}
+
 static int check_params(const seir_params *p, int64_t n)
 {
     if (!p) return fail("seir_params is NULL");
@@ -533,7 +625,7 @@ static int alloc_state(seir_handle *h)
         CK(cudaMemset(h->ttotal.p, 0, 16));
         h->trace_alloc = true;
     }
-    CK(h->hist.alloc(R * T * np));
+    if (h->history_mode == SEIR_HISTORY_EAGER) CK(h->hist.alloc(R * T * np));
     CK(h->tally.alloc(R * T * TAL_ROWS * kAges));
     CK(h->list_cnt.alloc(R * 3 * (T + 2)));
     CK(h->day_ns.alloc(T + 2));
@@ -565,6 +657,8 @@ static void fill_ctx(seir_handle *h)
     if (bpr < 1) bpr = 1;
     c.blocks_per_rep = bpr;
     c.list_old = h->list_old.p; c.list_new = h->list_new.p; c.list_cnt = h->list_cnt.p;
+    c.pk_pool = h->pk_pool.p;
+    c.rp = h->rp.p; c.bank = h->bank.p; c.home_rw = h->home.p; c.T_loop = p.T;
     c.stat = h->stat.p; c.grp_off = h->grp_off.p; c.grp_members = h->grp_members.p;
     c.p_hh_vec = h->p_hh_uniform ? nullptr : h->p_hh.p; c.p_hh_scalar = h->p_hh_scalar;
     c.p_ms = h->tables.p + kTabPms; c.p_sc = h->tables.p + kTabPsc; c.p_cd = h->tables.p + kTabPcd;
@@ -627,6 +721,12 @@ const char *seir_build_info(void)
            SEIR_STR(__CUDACC_VER_MINOR__) ", -lineinfo, event-driven active lists, " SEIR_STR(SEIR_THREADS) " threads/CTA";
 }
 
+void seir_abi_sizes(int64_t out5[5])
+{
+    out5[0] = sizeof(seir_params); out5[1] = sizeof(seir_population); out5[2] = sizeof(seir_tables);
+    out5[3] = sizeof(seir_replica); out5[4] = sizeof(seir_overrides);
+}
+
 int seir_create(const seir_params *params, const seir_population *pop, const seir_tables *tables, int n_replicas,
                 int device, seir_handle **out)
 {
@@ -651,6 +751,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
 
     seir_handle *h = new seir_handle();
     h->device = device; h->sms = prop.multiProcessorCount; h->n_rep = n_replicas; h->prm = *params; h->n = n;
+    h->history_mode = params->history_mode == SEIR_HISTORY_ON_DEMAND ? SEIR_HISTORY_ON_DEMAND : SEIR_HISTORY_EAGER;
     h->n_pad = (n + kPad - 1) / kPad * kPad;
     int rc = 1;
     do {
@@ -724,17 +825,21 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(h->rec.alloc(R * np));
         CKB(h->list_old.alloc(R * 2 * np));
         CKB(h->list_new.alloc(R * 2 * np));
+        CKB(h->pk_pool.alloc(R * kParkRing * np));  // day buckets of the parked agents (64 B per agent and replica)
         CKB(h->home.alloc(R * np / 32));
         CKB(cudaMemset(h->home.p, 0, R * np / 32 * 4));
         CKB(h->seeds.alloc(R));
         CKB(h->counters.alloc(R * 4));
         CKB(h->barrier.alloc(kBarStride * (2 + 64)));  // flat word, global word, up to 64 group counters (1024 CTAs)
         CKB(h->init_off.alloc(R + 1));
+        CKB(h->rp.alloc(R));
+        CKB(h->kcum.alloc(R * (kAges + 2)));
         CKB(h->flags.alloc(kMaxShards + 2));
         CKB(cudaMemset(h->flags.p, 0, (kMaxShards + 2) * 4));
 #undef CKB
         if (alloc_state(h)) break;
         if (upload_tables(h, tables)) break;
+        if (upload_bank(h, 1, tables, &params->p_infect_given_contact)) break;
         // persistent grid: every CTA must be co-resident
         int occ = 0;
         if (cudaFuncSetAttribute(seir_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
@@ -818,11 +923,24 @@ int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables
         if ((params->T > h->T_alloc || (tracing_can_start(*params) && !h->trace_alloc)) && alloc_state(h)) return 1;
     }
     if (tables && upload_tables(h, tables)) return 1;
+    if (tables && upload_bank(h, 1, tables, &h->prm.p_infect_given_contact)) return 1;  // (a new parameter set: back to one table set)
     fill_ctx(h);
     return 0;
 }
 
-int seir_run(seir_handle *h, const seir_replica *reps)
+int seir_set_table_bank(seir_handle *h, int n_sets, const seir_tables *sets, const double *p_infect_given_contact)
+{
+    if (!h || !sets || !p_infect_given_contact) return fail("seir_set_table_bank: NULL argument");
+    if (n_sets < 1 || n_sets > 4096) return fail("seir_set_table_bank: n_sets must be in [1, 4096]");
+    CK(cudaSetDevice(h->device));
+    if (upload_bank(h, n_sets, sets, p_infect_given_contact)) return 1;
+    fill_ctx(h);
+    return 0;
+}
+
+int seir_run(seir_handle *h, const seir_replica *reps) { return seir_run_ex(h, reps, nullptr); }
+
+int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *ovr)
 {
     if (!h || !reps) return fail("seir_run: NULL argument");
     CK(cudaSetDevice(h->device));
@@ -831,48 +949,98 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         if (h->n_rep != 1) return fail("a sharded run takes one replica");
         if (h->prm.launch != SEIR_LAUNCH_PERSISTENT) return fail("a sharded run needs the persistent launch (the GPUs meet at a device-side barrier every day)");
         if (tracing_can_start(h->prm)) return fail("contact tracing is not available in sharded runs (pass t_tracing_start >= T or tracing_enabled = 0)");
-        ++h->run_count;  // every rank runs the same sequence of seir_run calls: the barrier epochs stay in step
+        if (ovr) return fail("per-replica overrides are not available in sharded runs");
     }
     const int R = h->n_rep;
     const int64_t n = h->n;
-    // ---- per-run host inputs -> device
-    // the run's small inputs (seeds, offsets, the ids of the initial cases as int32) are assembled in ONE pinned host
-    // buffer and copied from there: truly asynchronous copies, no pageable staging inside the driver
-    int64_t n_ids = 0;
+    // ---- per-replica overrides: day numbers and table set (defaults: the handle's parameters)
+    h->rp_host.assign((size_t)R, RepParams{});
+    int T_loop = 2, t_home_min = 0x7FFFFFFF, trace_min = 0;
     for (int r = 0; r < R; ++r) {
-        if (reps[r].n_initial < 0 || (reps[r].n_initial > 0 && !reps[r].initial_infected)) return fail("seir_replica.initial_infected is invalid");
-        n_ids += reps[r].n_initial;
+        RepParams &q = h->rp_host[(size_t)r];
+        q.T = ovr ? ovr[r].T : h->prm.T;
+        q.t_lockdown = ovr ? ovr[r].t_lockdown : h->prm.t_lockdown;
+        q.t_stayhome = ovr ? ovr[r].t_stayhome_start : h->prm.t_stayhome_start;
+        const int tts = ovr ? ovr[r].t_tracing_start : h->prm.t_tracing_start;
+        q.trace_from = (h->prm.tracing_enabled && tts >= 1 && tts < q.T && h->trace_alloc) ? tts : 0;
+        q.bank = ovr ? ovr[r].table_set : 0;
+        if (q.T < 2 || q.T > h->prm.T) return fail("seir_overrides.T must be in [2, the handle's T]");
+        if (q.bank < 0 || q.bank >= h->n_sets) return fail("seir_overrides.table_set is not a registered set (seir_set_table_bank)");
+        if (ovr && h->prm.tracing_enabled && tts >= 1 && tts < q.T && !h->trace_alloc)
+            return fail("seir_overrides.t_tracing_start switches tracing on, but the handle was created without tracing state "
+                        "(create it with a t_tracing_start below T)");
+        if (q.T > T_loop) T_loop = q.T;
+        if (q.t_stayhome >= 1 && q.t_stayhome < q.T && q.t_stayhome < t_home_min) t_home_min = q.t_stayhome;
+        if (q.trace_from && (!trace_min || q.trace_from < trace_min)) trace_min = q.trace_from;
     }
-    const size_t in_bytes = (size_t)R * 8 + (size_t)(R + 1) * 8 + (size_t)n_ids * 4;
+    if (h->n_shards > 1) ++h->run_count;  // every rank runs the same sequence of seir_run calls: the barrier epochs stay in step
+    // ---- per-run host inputs -> device
+    // the run's small inputs (seeds, offsets, the ids of the initial cases as int32, the pick counts of the keyed
+    // prologue, the overrides) are assembled in ONE pinned host buffer and copied from there: truly asynchronous
+    // copies, no pageable staging inside the driver
+    int64_t n_ids = 0;
+    bool any_keyed = false;
+    h->n_init_run.assign((size_t)R, 0);
+    for (int r = 0; r < R; ++r) {
+        if (reps[r].keyed_prologue) {
+            if (!(reps[r].initial_infected_fraction >= 0.0) || reps[r].initial_infected_fraction > 1.0)
+                return fail("seir_replica.initial_infected_fraction must be in [0, 1]");
+            h->n_init_run[(size_t)r] = (int64_t)(reps[r].initial_infected_fraction * (double)n);  // int(frac * n) (:186)
+            any_keyed = true;
+        } else {
+            if (reps[r].n_initial < 0 || (reps[r].n_initial > 0 && !reps[r].initial_infected)) return fail("seir_replica.initial_infected is invalid");
+            h->n_init_run[(size_t)r] = reps[r].n_initial;
+        }
+        n_ids += h->n_init_run[(size_t)r];
+    }
+    const size_t kc = (size_t)R * (kAges + 2);
+    const size_t in_bytes = (size_t)R * 8 + (size_t)(R + 1) * 8 + kc * 8 + (size_t)R * sizeof(RepParams) + (size_t)n_ids * 4;
     if (in_bytes > h->in_host_bytes) {
         if (h->in_host) cudaFreeHost(h->in_host);
         h->in_host = nullptr; h->in_host_bytes = 0;
         CK(cudaHostAlloc((void **)&h->in_host, in_bytes + 4096, cudaHostAllocDefault));
         h->in_host_bytes = in_bytes + 4096;
     }
-    uint64_t *seeds = reinterpret_cast<uint64_t *>(h->in_host);
-    int64_t *off = reinterpret_cast<int64_t *>(h->in_host + (size_t)R * 8);
-    int32_t *ids = reinterpret_cast<int32_t *>(h->in_host + (size_t)R * 8 + (size_t)(R + 1) * 8);
+    unsigned char *cur = h->in_host;
+    uint64_t *seeds = reinterpret_cast<uint64_t *>(cur); cur += (size_t)R * 8;
+    int64_t *off = reinterpret_cast<int64_t *>(cur); cur += (size_t)(R + 1) * 8;
+    int64_t *kcum = reinterpret_cast<int64_t *>(cur); cur += kc * 8;
+    RepParams *rp = reinterpret_cast<RepParams *>(cur); cur += (size_t)R * sizeof(RepParams);
+    int32_t *ids = reinterpret_cast<int32_t *>(cur);
+    const bool home_used = t_home_min != 0x7FFFFFFF;  // Home = Home_real only from t_stayhome_start on (:243-244): a run that never gets there never reads the bitmap
     off[0] = 0;
     for (int r = 0; r < R; ++r) {
         seeds[r] = reps[r].seed;
-        off[r + 1] = off[r] + reps[r].n_initial;
-        for (int64_t k = 0; k < reps[r].n_initial; ++k) {
-            const int64_t a = reps[r].initial_infected[k];
-            if (a < 0 || a >= n) return fail("seir_replica.initial_infected holds an id outside [0, n)");
-            ids[(size_t)(off[r] + k)] = (int32_t)a;
+        rp[r] = h->rp_host[(size_t)r];
+        off[r + 1] = off[r] + h->n_init_run[(size_t)r];
+        int64_t *kc_r = kcum + (size_t)r * (kAges + 2);
+        kc_r[0] = 0;
+        if (reps[r].keyed_prologue) {
+            for (int a = 0; a < kAges; ++a) {
+                const double f = reps[r].fraction_stay_home ? reps[r].fraction_stay_home[a] : 0.0;
+                if (!(f >= 0.0) || f > 1.0) return fail("seir_replica.fraction_stay_home must be in [0, 1]");
+                kc_r[a + 1] = kc_r[a] + (home_used ? (int64_t)(f * (double)h->group_sizes[(size_t)a]) : 0);  // int(frac * len(matches)) (:181)
+            }
+            kc_r[kAges + 1] = kc_r[kAges] + h->n_init_run[(size_t)r];
+        } else {
+            for (int a = 0; a <= kAges; ++a) kc_r[a + 1] = 0;
+            for (int64_t k = 0; k < reps[r].n_initial; ++k) {
+                const int64_t a = reps[r].initial_infected[k];
+                if (a < 0 || a >= n) return fail("seir_replica.initial_infected holds an id outside [0, n)");
+                ids[(size_t)(off[r] + k)] = (int32_t)a;
+            }
         }
     }
     CK(h->init_ids.alloc((size_t)n_ids));
     CK(cudaMemcpyAsync(h->seeds.p, seeds, R * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->init_off.p, off, (R + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    if (n_ids) CK(cudaMemcpyAsync(h->init_ids.p, ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->rp.p, rp, (size_t)R * sizeof(RepParams), cudaMemcpyHostToDevice, h->stream));
+    if (any_keyed) CK(cudaMemcpyAsync(h->kcum.p, kcum, kc * 8, cudaMemcpyHostToDevice, h->stream));
+    if (n_ids) CK(cudaMemcpyAsync(h->init_ids.p, ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, h->stream));  // (the keyed replicas' slots are overwritten by the device)
     const int64_t n_words = h->n_pad / 32;
-    // Home = Home_real only from t_stayhome_start on (:243-244): a run that never gets there never reads the bitmap
-    const bool home_used = h->prm.t_stayhome_start >= 1 && h->prm.t_stayhome_start < h->prm.T;
     for (int r = 0; r < R && home_used; ++r) {
         uint32_t *bm = h->home.p + (size_t)r * n_words;
-        if (reps[r].home_real) {
+        if (!reps[r].keyed_prologue && reps[r].home_real) {
             CK(h->stage_u8.alloc((size_t)n));
             CK(cudaMemcpyAsync(h->stage_u8.p, reps[r].home_real, (size_t)n, cudaMemcpyHostToDevice, h->stream));
             // (the one staging buffer is reused by the next replica: stream order keeps its copy behind this kernel;
@@ -882,7 +1050,10 @@ int seir_run(seir_handle *h, const seir_replica *reps)
             CK(cudaMemsetAsync(bm, 0, (size_t)n_words * 4, h->stream));
         }
     }
+    h->home_valid = home_used;
     fill_ctx(h);
+    h->cx.T_loop = T_loop;
+    h->cx.trace_from = trace_min;  // the first day on which ANY replica traces (each replica records roots from its own day on)
     h->launches = 0;
     // ---- init + day loop, timed on the launching stream
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -907,6 +1078,11 @@ int seir_run(seir_handle *h, const seir_replica *reps)
     }
     seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
     ++h->launches;
+    if (any_keyed) {  // the prologue's picks (:176-187), made on the device
+        dim3 g(h->sms * 2 > 64 ? 64 : h->sms * 2, R);
+        seir_prologue_kernel<<<g, 256, 0, h->stream>>>(h->cx, h->kcum.p, h->init_ids.p, h->init_off.p, home_used ? 1 : 0);
+        ++h->launches;
+    }
     if (n_ids) {
         dim3 g(32, R);
         seir_init_infected_kernel<<<g, 128, 0, h->stream>>>(h->cx, h->init_ids.p, h->init_off.p);
@@ -927,7 +1103,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaEventCreate(&pa)); CK(cudaEventCreate(&pb));
         h->probe_ms = 0.0f;
 #endif
-        for (int t = 1; t <= h->prm.T; ++t) {
+        for (int t = 1; t <= T_loop; ++t) {
 #ifdef SEIR_SORT_PROBE
             CK(cudaEventRecord(pa, h->stream));
 #endif
@@ -955,7 +1131,7 @@ int seir_run(seir_handle *h, const seir_replica *reps)
                 }
             }
 #endif
-            if (tracing && t >= h->cx.trace_from && t < h->prm.T) {
+            if (tracing && t >= h->cx.trace_from && t < T_loop) {
                 seir_trace_kernel<<<R < h->grid ? R : h->grid, 32, sizeof(TraceSmem), h->stream>>>(h->cx, t);
                 ++h->launches;
             }
@@ -969,8 +1145,10 @@ int seir_run(seir_handle *h, const seir_replica *reps)
         CK(cudaMemcpyAsync(h->counters_host, h->counters.p, (size_t)R * 4 * 8, cudaMemcpyDeviceToHost, h->copy_stream));
         CK(cudaMemcpyAsync(h->tally_host, h->tally.p, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, cudaMemcpyDeviceToHost, h->copy_stream));
     }
-    seir_materialize_kernel<<<h->sms * 8, kMatThreads, 0, h->stream>>>(h->cx);
-    ++h->launches;
+    if (h->history_mode == SEIR_HISTORY_EAGER) {
+        seir_materialize_kernel<<<h->sms * 8, kMatThreads, 0, h->stream>>>(h->cx);
+        ++h->launches;
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev3, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1031,42 +1209,47 @@ int seir_last_run_ms3(seir_handle *h, float *init_ms, float *day_loop_ms, float 
     return 0;
 }
 
+// the device's tally rows of one replica: from the pinned copy the run left behind, else copied now
+static int raw_tallies(seir_handle *h, int replica, std::vector<uint32_t> &own, const uint32_t **raw_p)
+{
+    const size_t per = (size_t)h->prm.T * TAL_ROWS * kAges;
+    if (h->host_results) {
+        *raw_p = h->tally_host + (size_t)replica * per;
+    } else {
+        own.resize(per);
+        CK(cudaMemcpy(own.data(), h->tally.p + (size_t)replica * per, per * 4, cudaMemcpyDeviceToHost));
+        *raw_p = own.data();
+    }
+    return 0;
+}
+
 int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
 {
     if (!h || !out) return fail("seir_get_tallies: NULL argument");
     if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
     CK(cudaSetDevice(h->device));
     const int T = h->prm.T;
-    const size_t per = (size_t)T * TAL_ROWS * kAges;
     std::vector<uint32_t> own;
     const uint32_t *raw_p;
-    if (h->host_results) {
-        raw_p = h->tally_host + (size_t)replica * per;
-    } else {
-        own.resize(per);
-        CK(cudaMemcpy(own.data(), h->tally.p + (size_t)replica * per, per * 4, cudaMemcpyDeviceToHost));
-        raw_p = own.data();
-    }
-    // planes in the order of seir_individual.py:392: S,E,Mild,Documented,Severe,Critical,R,D,Q
-    std::vector<int64_t> cumE(kAges, 0), cumR(kAges, 0), cumD(kAges, 0), cumDoc(kAges, 0), cumQ2(kAges, 0);
+    if (raw_tallies(h, replica, own, &raw_p)) return 1;
+    // planes in the order of seir_individual.py:392: S,E,Mild,Documented,Severe,Critical,R,D,Q.  The device rows are
+    // per-day changes (the day loop visits an agent only when something can happen to it): accumulate them.
+    std::vector<int64_t> cum((size_t)TAL_ROWS * kAges, 0);
     for (int t = 0; t < T; ++t) {
         const uint32_t *d = raw_p + (size_t)t * TAL_ROWS * kAges;
         int64_t *o = out + (size_t)t * SEIR_N_TALLY * kAges;
+        for (int k = 0; k < TAL_ROWS * kAges; ++k) cum[(size_t)k] += (int64_t)(int32_t)d[k];  // (signed rows wrap around 2^32)
         for (int a = 0; a < kAges; ++a) {
-            cumE[a] += d[TAL_NEW_E * kAges + a];
-            cumR[a] += d[TAL_NEW_R * kAges + a];
-            cumD[a] += d[TAL_NEW_D * kAges + a];
-            cumDoc[a] += d[TAL_NEW_DOC * kAges + a];
-            cumQ2[a] += d[TAL_NEW_Q2 * kAges + a];
-            o[0 * kAges + a] = (h->n_shards > 1 ? h->shard_group_sizes[a] : h->group_sizes[a]) - cumE[a];
-            o[1 * kAges + a] = d[TAL_E * kAges + a];
-            o[2 * kAges + a] = d[TAL_MILD * kAges + a];
-            o[3 * kAges + a] = cumDoc[a];
-            o[4 * kAges + a] = d[TAL_SEV * kAges + a];
-            o[5 * kAges + a] = d[TAL_CRIT * kAges + a];
-            o[6 * kAges + a] = cumR[a];
-            o[7 * kAges + a] = cumD[a];
-            o[8 * kAges + a] = d[TAL_QACT * kAges + a] + cumQ2[a];
+            auto c = [&](int row) { return cum[(size_t)row * kAges + a]; };
+            o[0 * kAges + a] = (h->n_shards > 1 ? h->shard_group_sizes[a] : h->group_sizes[a]) - c(TAL_NEW_E);
+            o[1 * kAges + a] = c(TAL_NEW_E) + c(TAL_D_E);
+            o[2 * kAges + a] = c(TAL_D_MILD);
+            o[3 * kAges + a] = c(TAL_NEW_DOC);
+            o[4 * kAges + a] = c(TAL_D_SEV);
+            o[5 * kAges + a] = c(TAL_D_CRIT);
+            o[6 * kAges + a] = c(TAL_NEW_R);
+            o[7 * kAges + a] = c(TAL_NEW_D);
+            o[8 * kAges + a] = c(TAL_NEW_QE) + c(TAL_D_Q) + c(TAL_NEW_Q2);
         }
     }
     return 0;
@@ -1103,24 +1286,88 @@ int seir_get_cohorts(seir_handle *h, int replica, int64_t *out)
     return 0;
 }
 
+int seir_history_preserve(seir_handle *h)
+{
+    if (!h) return fail("handle is NULL");
+    if (h->history_mode != SEIR_HISTORY_EAGER) return fail("SEIR_HISTORY_ON_DEMAND keeps no history to set aside");
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->n_rep * h->prm.T * h->n_pad;
+    CK(h->hist_prev.alloc(bytes));
+    CK(cudaMemcpyAsync(h->hist_prev.p, h->hist.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->prev_T = h->prm.T;
+    return 0;
+}
+
 int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uint8_t *out)
 {
     if (!h || !out) return fail("seir_get_history: NULL argument");
     if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    const bool previous = (which & SEIR_H_PREVIOUS) != 0;
+    which &= ~SEIR_H_PREVIOUS;
     if (which < 0 || which > SEIR_H_PACKED) return fail("history plane out of range");
-    if (t0 < 0 || t1 > h->prm.T || t0 > t1) return fail("day range out of bounds");
+    if (previous && !h->prev_T) return fail("no history has been set aside (seir_history_preserve)");
+    const int T_rows = previous ? h->prev_T : h->prm.T;
+    const int T_rep = previous || h->rp_host.empty() ? T_rows : h->rp_host[(size_t)replica].T;
+    if (t0 < 0 || t1 > T_rep || t0 > t1) return fail("day range out of bounds");
+    if (h->history_mode == SEIR_HISTORY_ON_DEMAND) {
+        if (previous) return fail("SEIR_HISTORY_ON_DEMAND keeps no earlier history");
+        if (h->rp_host.empty()) return fail("no run yet");
+        CK(cudaSetDevice(h->device));
+        const int64_t n = h->n, np = h->n_pad;
+        int rows_per = (int)((int64_t)(256ll << 20) / np);
+        if (rows_per < 1) rows_per = 1;
+        DevBuf<uint8_t> rows;
+        CK(rows.alloc((size_t)rows_per * np));
+        CK(h->stage_u8.alloc((size_t)rows_per * n));
+        for (int t = t0; t < t1; t += rows_per) {
+            const int nr = t1 - t < rows_per ? t1 - t : rows_per;
+            seir_rows_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx, replica, t, t + nr, rows.p);
+            seir_history_plane_kernel<<<h->sms * 8, 256, 0, h->stream>>>(rows.p, n, np, nr, which, h->stage_u8.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out + (size_t)(t - t0) * n, h->stage_u8.p, (size_t)nr * n, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        rows.release();
+        return 0;
+    }
     CK(cudaSetDevice(h->device));
     const int64_t n = h->n;
     int rows_per = (int)((int64_t)(256ll << 20) / (n > 0 ? n : 1));
     if (rows_per < 1) rows_per = 1;
     CK(h->stage_u8.alloc((size_t)rows_per * n > (size_t)n ? (size_t)rows_per * n : (size_t)n));
-    const uint8_t *base = h->hist.p + (size_t)replica * h->prm.T * h->n_pad;
+    const uint8_t *base = (previous ? h->hist_prev.p : h->hist.p) + (size_t)replica * T_rows * h->n_pad;
     for (int t = t0; t < t1; t += rows_per) {
         const int nr = t1 - t < rows_per ? t1 - t : rows_per;
         seir_history_plane_kernel<<<h->sms * 8, 256, 0, h->stream>>>(base + (size_t)t * h->n_pad, n, h->n_pad, nr, which, h->stage_u8.p);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(out + (size_t)(t - t0) * n, h->stage_u8.p, (size_t)nr * n, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int seir_get_prologue(seir_handle *h, int replica, uint8_t *home_out, int64_t *init_out, int64_t cap, int64_t *n_init)
+{
+    if (!h || !n_init) return fail("seir_get_prologue: NULL argument");
+    if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    if (h->n_init_run.empty()) return fail("no run yet");
+    CK(cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    if (home_out) {
+        std::vector<uint32_t> bm((size_t)(h->n_pad / 32), 0u);
+        if (h->home_valid) CK(cudaMemcpy(bm.data(), h->home.p + (size_t)replica * (h->n_pad / 32), bm.size() * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; ++i) home_out[i] = (uint8_t)((bm[(size_t)(i >> 5)] >> (i & 31)) & 1u);
+    }
+    int64_t off = 0;
+    for (int r = 0; r < replica; ++r) off += h->n_init_run[(size_t)r];
+    const int64_t k = h->n_init_run[(size_t)replica];
+    *n_init = k;
+    if (init_out) {
+        if (cap < k) return fail("seir_get_prologue: init_out is too small");
+        std::vector<int32_t> ids((size_t)k);
+        if (k) CK(cudaMemcpy(ids.data(), h->init_ids.p + off, (size_t)k * 4, cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < k; ++j) init_out[j] = ids[(size_t)j];
     }
     return 0;
 }
@@ -1163,7 +1410,32 @@ int seir_get_counters(seir_handle *h, int replica, int64_t *out4)
     unsigned long long c[4];
     if (h->host_results) memcpy(c, h->counters_host + (size_t)replica * 4, sizeof c);
     else CK(cudaMemcpy(c, h->counters.p + (size_t)replica * 4, sizeof c, cudaMemcpyDeviceToHost));
-    out4[0] = h->launches; out4[1] = (int64_t)c[1]; out4[2] = (int64_t)c[2]; out4[3] = (int64_t)c[3];
+    out4[0] = h->launches; out4[2] = (int64_t)c[2]; out4[3] = (int64_t)c[3];
+    // sum over the days of A(t-1), the agents in E/Mild/Severe/Critical: from the tallies (the day loop visits an
+    // active agent only on the days on which something can happen to it; c[1] counts those visits)
+    std::vector<uint32_t> own;
+    const uint32_t *raw_p;
+    if (raw_tallies(h, replica, own, &raw_p)) return 1;
+    int64_t active = 0, sum = 0;
+    const int T_rep = h->rp_host.empty() ? h->prm.T : h->rp_host[(size_t)replica].T;
+    for (int t = 0; t + 1 < T_rep; ++t) {
+        const uint32_t *d = raw_p + (size_t)t * TAL_ROWS * kAges;
+        for (int a = 0; a < kAges; ++a)
+            active += (int64_t)(int32_t)d[TAL_NEW_E * kAges + a] + (int32_t)d[TAL_D_E * kAges + a] + (int32_t)d[TAL_D_MILD * kAges + a] +
+                      (int32_t)d[TAL_D_SEV * kAges + a] + (int32_t)d[TAL_D_CRIT * kAges + a];
+        sum += active;
+    }
+    out4[1] = sum;
+    h->visits = (long long)c[1];
+    return 0;
+}
+
+int seir_get_visits(seir_handle *h, int replica, int64_t *out)
+{
+    int64_t c4[4];
+    if (!out) return fail("seir_get_visits: NULL argument");
+    if (seir_get_counters(h, replica, c4)) return 1;
+    *out = h->visits;
     return 0;
 }
 

@@ -9,7 +9,10 @@
 //   inbox[n/16]    u32           2 bits per agent: "ever infected", "an isolation draw of a hit was 0 => Q" (:353-354)
 //   rec[n]         32 B          one sector per EVER-INFECTED agent: state byte, static word, every event day and
 //                                drawn time-to-event; the whole T-day history of the agent is a function of it.
-//   list_old/new[2][n] u32       active lists: agents that are E/Mild/Severe/Critical, and agents infected yesterday
+//   list_old/new[2][n] u32       daily lists: agents that may TRANSMIT today (E / Mild, not quarantined), and agents
+//                                infected yesterday (record not built yet)
+//   pk_pool[16][n] (day buckets) quarantined agents (Q: they neither transmit nor draw) are PARKED in the bucket of the
+//                                next day on which one of their `t - t0 == draw` tests can fire, and visited only then
 //   hist[T][n]     u8            packed state rows (bits 0-2 compartment, bit 3 Q, bit 4 Documented): the
 //                                reference's nine bool[T,n] outputs, written ONCE by the materialise kernel.
 //
@@ -44,12 +47,21 @@ constexpr int kMinBlocks = SEIR_MIN_BLOCKS;
 constexpr int kVec = 16;                 // agents per 16 B vector of state bytes
 constexpr int kPad = 4096;               // row stride is a multiple of this many agents
 constexpr int kOutCap = 3 * kThreads;    // per-CTA staging of list appends
+constexpr int kParkHorizon = 15;         // an agent is parked at most this many days ahead (it is looked at again then),
+constexpr int kParkRing = kParkHorizon + 1;  // so the buckets of days t .. t + 15 are the live ones: day d uses slab d mod 16
+constexpr int kDocScan = 8;              // days of documentation draws (:280-289) evaluated ahead when a Mild agent is parked
 
 // device tally rows (per day, per age)
-enum { TAL_E = 0, TAL_MILD, TAL_SEV, TAL_CRIT, TAL_QACT, TAL_NEW_E, TAL_NEW_R, TAL_NEW_D, TAL_NEW_DOC,
-       TAL_NEW_Q2,  // recovered / dead agents quarantined by a tracer (:72-76 traces every non-S contact)
+// Every row is a per-day CHANGE (an agent is only visited on days on which something may happen to it, so nothing
+// is recounted): the host accumulates them into the reference's daily counts (seir_get_tallies).
+enum { TAL_NEW_E = 0,  // infections of the day (S -> E)
+       TAL_NEW_QE,     // of them quarantined on infection (:353-354, or reached by a tracer the same day)
+       TAL_D_E, TAL_D_MILD, TAL_D_SEV, TAL_D_CRIT,  // signed: change of the E / Mild / Severe / Critical head counts by the day's transitions
+       TAL_D_Q,        // signed: change of the number of quarantined E/Mild/Severe/Critical agents
+       TAL_NEW_R, TAL_NEW_D, TAL_NEW_DOC,
+       TAL_NEW_Q2,     // recovered / dead agents quarantined by a tracer (:72-76 traces every non-S contact)
        TAL_ROWS };
-constexpr int kTalLagRows = TAL_NEW_E + 1;  // rows [0, kTalLagRows) describe day t-1, the rest day t
+constexpr int kTalLagRows = TAL_NEW_QE + 1;  // rows [0, kTalLagRows) of a pass describe day t-1 (the records built today), the rest day t
 
 // compartments (bits 0-2 of the state byte)
 enum { C_S = 0, C_E = 1, C_MILD = 2, C_SEV = 3, C_CRIT = 4, C_R = 5, C_D = 6 };
@@ -115,6 +127,11 @@ __host__ __device__ inline uint16_t pack_static(int age, int diab, int hyp, int 
 __host__ __device__ inline uint32_t inbox_infected_bit(int k) { return 1u << (8 * (k & 3) + (k >> 2)); }
 __host__ __device__ inline uint32_t inbox_q_bit(int k) { return 1u << (8 * (k & 3) + 4 + (k >> 2)); }
 
+// per-replica overrides (seir_overrides): day numbers and the table set of the replica's grid point
+struct RepParams { int T, t_lockdown, t_stayhome, trace_from, bank, pad[3]; };
+// one table set of the bank: what parameter_sweep.py's grid changes (:54-56) -- the three severity tables
+// (mortality_multiplier), the kept-contact Poisson table and the contact probability (p_infect_given_contact)
+constexpr int kBankPms = 0, kBankPsc = 404, kBankPcd = 808, kBankNatEn = 1212, kBankPcontact = 1616, kBankStride = 1624;
 struct TraceCtl;
 struct DevCtx {
     // population, shared by all replicas
@@ -122,8 +139,11 @@ struct DevCtx {
     int64_t n_pad;        // row stride, multiple of kPad
     int n_rep;
     int blocks_per_rep;   // CTAs that share one replica's list in a pass (>= 1)
-    int T;
+    int T;                // rows of the per-day arrays (the handle's horizon)
+    int T_loop;           // the longest horizon of this launch's replicas (<= T)
     int mode;
+    const RepParams *rp;  // [rep]
+    const double *bank;   // [sets][kBankStride]
     const uint16_t *stat;
     const int32_t *grp_off;      // [102]
     const int32_t *grp_members;  // [n]
@@ -141,12 +161,14 @@ struct DevCtx {
     uint32_t *inbox;               // [rep][n_pad/16]
     unsigned long long *winner;    // [rep][n_pad]
     AgentRec *rec;                 // [rep][n_pad]
-    uint32_t *list_old;            // [rep][2][n_pad]  agents that were active yesterday and still are: the ones that may
-                                   //                  transmit from the front, the quarantined ones from the back
+    uint32_t *list_old;            // [rep][2][n_pad]  agents that transmitted yesterday and may transmit today
     uint32_t *list_new;            // [rep][2][n_pad]  agents infected yesterday (record not built yet)
-    uint32_t *list_cnt;            // [rep][3][T+2]    entries of the old (transmitting) / new / old (quarantined) list consumed by pass t
+    uint32_t *list_cnt;            // [rep][3][T+2]    entries pass t consumes: transmitting list / new list / parked agents due on day t
+    // day buckets of the parked (quarantined) agents: the agents due on day d are pk_pool[d mod 16][0 .. list_cnt[2][d])
+    uint32_t *pk_pool;             // [rep][kParkRing][n_pad]
     uint32_t *tally;               // [rep][T][TAL_ROWS][101]
     const uint32_t *home;          // [rep][n_pad/32] bitmap of Home_real
+    uint32_t *home_rw;             // (the same, for the keyed prologue kernel)
     const uint64_t *seeds;         // [rep]
     unsigned long long *counters;  // [rep][4]
     unsigned int *barrier;         // grid barrier counter
@@ -316,14 +338,14 @@ constexpr int kDrawCap = 2 * kSlots / SEIR_QUEUE_DIV;                 // draw-it
 #ifndef SEIR_DYNAMIC_MAP
 #define SEIR_DYNAMIC_MAP 1   // replica ensembles: CTAs are dealt to the replicas anew in every pass, in proportion to their lists
 #endif
-#ifndef SEIR_QUEUE_EVENTS
-#define SEIR_QUEUE_EVENTS 0   // 1: progression events run compacted in stage E; 0: in place in stage A (measured faster on C2)
+#ifndef SEIR_PREFETCH
+#define SEIR_PREFETCH 0       // 1: stage A asks the L2 for the records of the group kWarps grabs ahead
 #endif
 #ifndef SEIR_QUEUE_DRAWS
 #define SEIR_QUEUE_DRAWS 1    // 1: household draw blocks / kept-contact counts run in stage D; 0: in place in stage A
 #endif
 constexpr int kWarps = kThreads / 32;
-constexpr int kOutOld = 2 * kSlots;                  // staged survivors
+constexpr int kOutOld = kSlots;                      // staged survivors that may transmit tomorrow
 constexpr int kOutNew = kSlots;                      // staged new infectees
 static_assert(kSlots <= 65536, "slot ids travel in 16 bits");
 struct RepView {
@@ -332,13 +354,18 @@ struct RepView {
     AgentRec *rec;
     const uint32_t *home;
     uint32_t *next_old, *next_new;          // tomorrow's lists
-    uint32_t *next_old_cnt, *next_new_cnt, *next_oldq_cnt;
-    uint32_t n_pad_m1;                      // the quarantined survivors fill tomorrow's old list from index n_pad - 1 downwards
+    uint32_t *next_old_cnt, *next_new_cnt;
+    uint32_t *pk_cnt;                       // [T+2] entries of the day buckets (row 2 of list_cnt)
+    uint32_t *pk_pool;
+    uint32_t n_pad_m1;
     uint64_t seed;
     bool home_on;
     int phase;
     int rep;
     bool tracing;                           // contact_tracing is True today (:241-242)
+    int T;                                  // the replica's horizon (seir_overrides.T)
+    const double *p_ms, *p_sc, *p_cd;       // the replica's severity tables (its table set)
+    const double *p_contact;                // -> p_infect_given_contact of the set (:146; read by the replay mode only)
 };
 
 // draw-queue items: slot<<16 | kind<<14 | payload
@@ -349,13 +376,14 @@ enum { DQ_HH = 0,      // payload = jb<<2 | two S-mask bits: household members 2
 struct __align__(16) PassSmem {
     RepView v;                     // the replica this CTA serves in the current pass (uniform per CTA)
     uint32_t out_old[kOutOld];
+    uint32_t pk_agent[kSlots];     // agents parked this round ...
+    uint16_t pk_meta[kSlots];      // ... (wake day - t - 1) << 11 | rank among the CTA's parks for that day
     uint32_t out_new[kOutNew];
     uint32_t hit_c[kHitCap];       // infectee
     uint32_t hit_meta[kHitCap];    // slot<<16 | ord
     uint8_t hit_age[kHitCap];      // age of the infectee, 127 = look it up
     uint32_t conq[kConCap];        // slot<<16 | payload (native: k; replay: age<<8 | j)
     uint32_t drawq[kDrawCap];
-    uint16_t evq[kSlots];          // slots with a progression event due
     uint32_t slot_agent[kSlots];
     uint32_t hit_n[kSlots];        // hits of the slot's agent this round: total | outside<<16
     uint16_t slot_info[kSlots];    // age | E<<7 | household position<<8
@@ -365,10 +393,12 @@ struct __align__(16) PassSmem {
     double nat_enlam[2 * kAges * 2];
     int32_t grp_off[kAges + 1];
     uint32_t cnt[4];
+    RepParams rp;                  // the replica's overrides, read once per CTA and pass
     uint32_t list_n[3];            // today's list lengths (new, transmitting, quarantined), read once per CTA
     uint32_t run_cnt[3];           // this CTA's share of the run counters (persistent kernel: flushed once, at the end)
     int dyn[3];                    // replica ensembles: the replica this CTA serves in the current pass, its part, the replica's CTAs
-    uint32_t n_old, n_oldq, n_new, n_hit, n_con, n_ev, n_draw, base_old, base_oldq, base_new, next_group;
+    uint32_t pk_n[32], pk_base[32]; // parks of the round per wake-day offset; their first slot in the day's bucket
+    uint32_t n_old, n_pk, n_new, n_hit, n_con, n_draw, base_old, base_new, next_group;
 };
 
 __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
@@ -377,8 +407,8 @@ __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
         sm.iso_asym[k] = cx.iso_asym[k];
         sm.iso_mean[k] = cx.iso_mean[k];
     }
-    for (int k = threadIdx.x; k < 4 * kAges; k += kThreads) sm.nat_enlam[k] = cx.nat_enlam[k];
     for (int k = threadIdx.x; k <= kAges; k += kThreads) sm.grp_off[k] = cx.grp_off[k];
+    // (nat_enlam belongs to the replica's table set: staged by the pass)
     __syncthreads();
 }
 
@@ -497,7 +527,7 @@ static __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &
         a = (int)(payload >> 8);
         const uint32_t j = payload & 255u;
         b = draw_block(v.seed, i, (uint32_t)t, SD_SITE_KEEP, payload);
-        double p_c = cx.p_contact;
+        double p_c = __ldg(v.p_contact);
         if (info & 128u) p_c = SD_MUL(p_c, cx.asym);
         if (!(sd_lane(b, 0) < p_c)) return;  // :373
         ord = SD_ORD_COMM_REPLAY(a, j);
@@ -588,7 +618,11 @@ static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSm
     r.set_t_q_on(NEVER);
     r.set_stat(stt);
     r.set_state(C_E);
-    if (ib & inbox_q_bit((int)(i & 15))) { r.set_state(r.state() | ST_Q); r.set_t_q_on((uint16_t)tx); }
+    if (ib & inbox_q_bit((int)(i & 15))) {
+        r.set_state(r.state() | ST_Q);
+        r.set_t_q_on((uint16_t)tx);
+        atomicAdd(&sm.tally[TAL_NEW_QE * kAges + (stt & 127)], 1u);
+    }
     if (w & W_TRACED) {  // a tracer reached the agent on the day it was infected (:83-87): Documented, Q (inbox bit), traced
         r.set_state(r.state() | ST_DOC);
         r.set_t_documented((uint16_t)tx);
@@ -607,7 +641,7 @@ static __device__ __forceinline__ void progression_events(const DevCtx &cx, cons
         ncomp = C_MILD;
         r.set_flags(r.flags() | F_MILD);
         sd_block b = draw_block(seed, i, (uint32_t)t, SD_SITE_ACT, 0);
-        if (sd_lane(b, 0) < __ldg(cx.p_ms + k3)) {
+        if (sd_lane(b, 0) < __ldg(sm.v.p_ms + k3)) {
             r.set_tt_severe(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_sev)));
             r.set_tt_recovery(NEVER);
         } else {
@@ -627,7 +661,7 @@ static __device__ __forceinline__ void progression_events(const DevCtx &cx, cons
         }
         nq = true;
         sd_block b = draw_block(seed, i, (uint32_t)t, SD_SITE_SEV, 0);
-        if (sd_lane(b, 0) < __ldg(cx.p_sc + k3)) {
+        if (sd_lane(b, 0) < __ldg(sm.v.p_sc + k3)) {
             r.set_tt_critical(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_crit)));
             r.set_tt_recovery(NEVER);
         } else {
@@ -638,7 +672,7 @@ static __device__ __forceinline__ void progression_events(const DevCtx &cx, cons
         ncomp = C_CRIT;
         r.set_flags(r.flags() | F_CRIT);
         sd_block b = draw_block(seed, i, (uint32_t)t, SD_SITE_CRIT, 0);
-        if (sd_lane(b, 0) < __ldg(cx.p_cd + k3)) {
+        if (sd_lane(b, 0) < __ldg(sm.v.p_cd + k3)) {
             r.set_tt_death(sd_enc16(exp_days_ni(sd_lane(b, 1), cx.m_death)));
             r.set_tt_recovery(NEVER);
         } else {
@@ -648,13 +682,48 @@ static __device__ __forceinline__ void progression_events(const DevCtx &cx, cons
     }
 }
 
+// The next day after t on which something can happen to a QUARANTINED agent (it neither transmits nor enters
+// isolation, :328-337 are guarded by not Q[t-1]): one of its `t - t0 == draw` tests (:257, :276, :291, :312, :324)
+// fires, or -- Mild and not Documented -- its daily documentation draw (:280-289) succeeds.  The draws are keyed on
+// (agent, day), so the days ahead can be evaluated now: at most kDocScan of them, after which the agent is looked at
+// again.  0x7FFFFFFF: nothing can ever happen (a draw of 0 froze the agent).
+// (out of line, the record's six day fields by value: the scan loop must not cost stage A its registers)
+static __device__ __noinline__ int next_wake_day(const DevCtx &cx, uint64_t seed, uint32_t i, uint32_t w0, uint32_t w1, uint32_t w2,
+                                                 int comp, bool doc, int t)
+{
+    const int t_exposed = (int)(w0 & 0xFFFFu);
+    const uint16_t tt_activation = (uint16_t)(w0 >> 16), tt_severe = (uint16_t)(w1 & 0xFFFFu), tt_recovery = (uint16_t)(w1 >> 16),
+                   tt_critical = (uint16_t)(w2 & 0xFFFFu), tt_death = (uint16_t)(w2 >> 16);
+    int w = 0x7FFFFFFF;
+#define SEIR_CAND(t0, tt) do { if ((tt) != NEVER) { const int d_ = (int)(t0) + (int)(tt); if (d_ > t && d_ < w) w = d_; } } while (0)
+    if (comp == C_E) {
+        SEIR_CAND(t_exposed, tt_activation);
+    } else {
+        const int t_inf = t_exposed + (int)tt_activation;
+        SEIR_CAND(t_inf, tt_recovery);
+        if (comp == C_MILD) SEIR_CAND(t_inf, tt_severe);
+        else if (comp == C_SEV) SEIR_CAND(t_inf + (int)tt_severe, tt_critical);
+        else SEIR_CAND(t_inf + (int)tt_severe + (int)tt_critical, tt_death);
+    }
+#undef SEIR_CAND
+    if (comp == C_MILD && !doc && cx.p_doc > 0.0) {
+        const int hi = w < t + kDocScan + 1 ? w : t + kDocScan + 1;  // the draws of days t+1 .. hi-1; day hi is visited anyway
+        int first = hi;
+#pragma unroll
+        for (int k = kDocScan; k >= 1; --k) {  // (all blocks, no early exit: the Philox rounds of the independent days interleave)
+            const sd_block b = sd_draw(seed, i, (uint32_t)(t + k), SD_SITE_DAY, 0);
+            if (t + k < hi && sd_lane(b, 0) < cx.p_doc) first = t + k;
+        }
+        w = first;
+    }
+    return w;
+}
+
 // ---- the agent's own day (:256-337) and the set-up of its transmission (:339-390) ---------------------
-// IN_EV = false: stage A.  An agent with a progression event due is handed to stage E untouched
-//                (returns DAY_DEFER); everything else is finished here.
-// IN_EV = true : stage E, the same statements with the event.
-// Returns DAY_KEEP if the agent stays on the active list.
-enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_DEFER = 2, DAY_KEEP_Q = 3 };  // KEEP_Q: stays active and is quarantined
-template <bool IN_EV>
+// Returns DAY_KEEP if the agent may transmit tomorrow, DAY_KEEP_Q if it stays active and quarantined (then `wake`
+// is the next day it has to be looked at), DAY_DROP if it left the active compartments or is frozen for good.
+// (DAY_KEEP_Q carries the wake day's offset: DAY_KEEP_Q | (wake - t - 1) << 2)
+enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_KEEP_Q = 3 };
 static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i, AgentRec &r,
                                          bool dirty, int t)
 {
@@ -688,11 +757,6 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
     } else {
         const bool ev = (Ep && due(t, r.t_exposed(), r.tt_activation())) || (Mp && due(t, t_inf, r.tt_severe())) ||
                         (Sevp && due(t, t_severe_of(r), r.tt_critical()));
-        if (!IN_EV && ev) {
-            if (dirty) store_rec(v.rec + i, r);
-            sm.evq[atomicAdd(&sm.n_ev, 1u)] = (uint16_t)slot;  // (at most one entry per slot: cannot overflow)
-            return DAY_DEFER;
-        }
         if (want_doc) {  // :280-289 (lane 0 of the agent's day block)
             if (sd_lane(db, 0) < cx.p_doc) {
                 ndoc = true;
@@ -701,7 +765,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
                 r.set_t_documented((uint16_t)t);
             }
         }
-        if (IN_EV && ev) {
+        if (ev) {
             progression_events(cx, sm, v.seed, i, t, r, comp, ncomp, nq, ndoc, root);
             dirty = true;
         } else if (Cp && due(t, t_critical_of(r), r.tt_death())) {  // :323-327
@@ -722,6 +786,13 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
         if (!Ep && due(t, t_infected_of(r), r.tt_isolate())) { nq = true; transmit = false; }
         else if (Ep && due(t, r.t_exposed(), r.tt_isolate())) { nq = true; transmit = false; }
     }
+    // the day's changes of the head counts (every tally row is a change: nobody recounts the agents that were not visited)
+    const bool active = ncomp <= C_CRIT;  // (ncomp >= C_E always)
+    if (ncomp != comp) {
+        atomicAdd(&sm.tally[(TAL_D_E + comp - C_E) * kAges + age], 0xFFFFFFFFu);
+        if (active) atomicAdd(&sm.tally[(TAL_D_E + ncomp - C_E) * kAges + age], 1u);
+    }
+    if ((nq && active) != Qp) atomicAdd(&sm.tally[TAL_D_Q * kAges + age], Qp ? 0xFFFFFFFFu : 1u);
     // the agent's own record is final for today except for the infector counters (stage W)
     const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
     if (nst != st) {
@@ -761,7 +832,12 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
         }
     }
     SEIR_FINE(7);
-    return (ncomp >= C_E && ncomp <= C_CRIT) ? (nq ? DAY_KEEP_Q : DAY_KEEP) : DAY_DROP;
+    if (!active) return DAY_DROP;
+    if (!nq) return DAY_KEEP;
+    int wake = next_wake_day(cx, v.seed, i, r.w[0], r.w[1], r.w[2], ncomp, ndoc, t);
+    if (wake >= v.T) return DAY_DROP;  // nothing more can happen to it within the horizon: its record is final
+    if (wake > t + kParkHorizon) wake = t + kParkHorizon;  // (the bucket offset travels in 5 bits: look again then)
+    return DAY_KEEP_Q | ((wake - t - 1) << 2);
 }
 
 // ---- stage A: one list entry -----------------------------------------------------------------------------
@@ -780,91 +856,114 @@ static __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &
     SEIR_FINE(2);
     const uint16_t stt = r.stat();
     const int age = stt & 127;
-    const uint8_t st = r.state();
-    const int comp = st & 7;
+    const int comp = r.state() & 7;
     sm.slot_agent[slot] = i;
     sm.slot_info[slot] = (uint16_t)(age | (comp == C_E ? 128 : 0) | (((stt >> 9) & 7) << 8));
-    // state tallies of day t-1
-    atomicAdd(&sm.tally[(comp - C_E) * kAges + age], 1u);
-    if (st & ST_Q) atomicAdd(&sm.tally[TAL_QACT * kAges + age], 1u);
-    if (finalize) {  // pass T: nothing moves
+    if (finalize) {  // pass T: nothing moves (only the agents infected on the last day are listed: their records)
         if (dirty) store_rec(v.rec + i, r);
         return DAY_DROP;
     }
-    return agent_day<SEIR_QUEUE_EVENTS == 0>(cx, sm, slot, i, r, dirty, t);
+    return agent_day(cx, sm, slot, i, r, dirty, t);
 }
 
-// survivors re-append themselves to tomorrow's list -- the quarantined ones (no transmission: a short path) apart
-// from the ones that may transmit, so that tomorrow's warps are homogeneous; one shared-memory atomic per warp and class
-static constexpr int kOutHalf = kOutOld / 2;
+// Survivors: the ones that may transmit tomorrow re-append themselves to tomorrow's list (one shared-memory atomic
+// per warp); the quarantined ones are staged for the bucket of their wake day -- `rank` numbers the CTA's parks of a day.
 static __device__ __forceinline__ void append_survivors(PassSmem &sm, int keep, uint32_t i)
 {
     const RepView &v = sm.v;
     const int lane = threadIdx.x & 31;
-    const unsigned mt = __ballot_sync(0xFFFFFFFFu, keep == DAY_KEEP), mq = __ballot_sync(0xFFFFFFFFu, keep == DAY_KEEP_Q);
+    const unsigned mt = __ballot_sync(0xFFFFFFFFu, keep == DAY_KEEP);
     if (mt) {
         uint32_t base = 0;
         if (lane == __ffs(mt) - 1) base = atomicAdd(&sm.n_old, (uint32_t)__popc(mt));
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mt) - 1);
         if (keep == DAY_KEEP) {
             const uint32_t pos = base + __popc(mt & ((1u << lane) - 1u));
-            if (pos < (uint32_t)kOutHalf) sm.out_old[pos] = i;
+            if (pos < (uint32_t)kOutOld) sm.out_old[pos] = i;
             else v.next_old[atomicAdd(v.next_old_cnt, 1u)] = i;
         }
     }
-    if (mq) {
+    const unsigned mq = __ballot_sync(0xFFFFFFFFu, (keep & 3) == DAY_KEEP_Q);
+    if (mq) {  // one shared-memory atomic per warp for the staging slot, one per warp and wake day for the rank
         uint32_t base = 0;
-        if (lane == __ffs(mq) - 1) base = atomicAdd(&sm.n_oldq, (uint32_t)__popc(mq));
+        if (lane == __ffs(mq) - 1) base = atomicAdd(&sm.n_pk, (uint32_t)__popc(mq));  // (at most one park per slot and round: < kSlots)
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mq) - 1);
-        if (keep == DAY_KEEP_Q) {
-            const uint32_t pos = base + __popc(mq & ((1u << lane) - 1u));
-            if (pos < (uint32_t)kOutHalf) sm.out_old[kOutHalf + pos] = i;
-            else v.next_old[v.n_pad_m1 - atomicAdd(v.next_oldq_cnt, 1u)] = i;
+        if ((keep & 3) == DAY_KEEP_Q) {
+            const uint32_t off = (uint32_t)keep >> 2;                // wake day - t - 1: 0 .. kParkHorizon - 1
+            const unsigned same = __match_any_sync(mq, off);
+            uint32_t r0 = 0;
+            if (lane == __ffs(same) - 1) r0 = atomicAdd(&sm.pk_n[off], (uint32_t)__popc(same));
+            r0 = __shfl_sync(same, r0, __ffs(same) - 1);
+            const uint32_t k = base + __popc(mq & ((1u << lane) - 1u));
+            sm.pk_agent[k] = i;
+            sm.pk_meta[k] = (uint16_t)((off << 11) | (r0 + __popc(same & ((1u << lane) - 1u))));
         }
     }
 }
 
-// both staging halves to tomorrow's list (the whole CTA; ends with the staging counters reset)
-// right after stage A, when the round's survivors are staged: thread 0 / thread 32 reserve their room in tomorrow's
-// lists.  The returned offsets stay in a register until the flush, so the two round trips to L2 overlap the stages
-// in between instead of standing in front of the grid barrier.
+// right after stage A, when the round's survivors are staged: thread 0 reserves their room in tomorrow's list.  The
+// returned offset stays in a register until the flush, so the round trip to L2 overlaps the stages in between
+// instead of standing in front of the grid barrier.
 static __device__ __forceinline__ uint32_t reserve_survivors(PassSmem &sm)
 {
     const RepView &v = sm.v;
     uint32_t base = 0;
     if (threadIdx.x == 0) {
-        const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
+        const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
         if (so) base = atomicAdd(v.next_old_cnt, so);
-    } else if (threadIdx.x == 32) {
-        const uint32_t sq = sm.n_oldq < (uint32_t)kOutHalf ? sm.n_oldq : (uint32_t)kOutHalf;
-        if (sq) base = atomicAdd(v.next_oldq_cnt, sq);
     }
     return base;
 }
 
-static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_new, uint32_t reserved, bool new_reserved = false)
+// The round's parks go to their day buckets.  Threads 128 .. 142 own one wake-day offset each and reserve the room
+// (one atomic per CTA and day); afterwards every staged agent is stored at its rank behind that base.
+static __device__ __forceinline__ void park_reserve(PassSmem &sm, int t)
+{
+    const int o = (int)threadIdx.x - 128;
+    if (o < 0 || o >= kParkHorizon) return;
+    const uint32_t cnt = sm.pk_n[o];
+    if (cnt) sm.pk_base[o] = atomicAdd(sm.v.pk_cnt + (t + 1 + o), cnt);
+}
+static __device__ __forceinline__ void park_store(const DevCtx &cx, PassSmem &sm, int t, uint32_t n_pk)
 {
     const RepView &v = sm.v;
-    const uint32_t so = sm.n_old < (uint32_t)kOutHalf ? sm.n_old : (uint32_t)kOutHalf;
-    const uint32_t sq = sm.n_oldq < (uint32_t)kOutHalf ? sm.n_oldq : (uint32_t)kOutHalf;
+    for (uint32_t k = threadIdx.x; k < n_pk; k += kThreads) {
+        const uint32_t meta = sm.pk_meta[k], o = meta >> 11, pos = sm.pk_base[o] + (meta & 2047u);
+        if (SEIR_CHECK((int64_t)pos < cx.n_pad, cx, v.rep))
+            __stcg(v.pk_pool + (size_t)((t + 1 + (int)o) & (kParkRing - 1)) * cx.n_pad + pos, sm.pk_agent[k]);
+    }
+}
+
+// the staged survivors, parks and (flush_new) new infectees to tomorrow's lists / the day buckets (the whole CTA;
+// ends with the staging counters reset)
+static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSmem &sm, int t, bool flush_new, uint32_t reserved,
+                                                       bool new_reserved = false)
+{
+    const RepView &v = sm.v;
+    const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
+    const uint32_t sp = sm.n_pk;
     const uint32_t sn = flush_new ? (sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew) : 0u;
     __syncthreads();
-    if (so | sq | sn) {
+    if (so | sp | sn) {
         if (threadIdx.x == 0 && so) { sm.base_old = reserved; sm.n_old = 0; }
-        if (threadIdx.x == 32 && sq) { sm.base_oldq = reserved; sm.n_oldq = 0; }
         if (threadIdx.x == 64 && sn) { sm.base_new = new_reserved ? reserved : atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
+        if (sp) park_reserve(sm, t);
         __syncthreads();
 #ifdef SEIR_CHECKS
-        if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sq && sm.base_oldq + sq > v.n_pad_m1 + 1u) ||
-                                 (sn && sm.base_new + sn > v.n_pad_m1 + 1u)))
+        if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sn && sm.base_new + sn > v.n_pad_m1 + 1u)))
             atomicOr(&sm.cnt[3], 1u);
         __syncthreads();
         if (sm.cnt[3]) return;
 #endif
         for (uint32_t k = threadIdx.x; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
-        for (uint32_t k = threadIdx.x; k < sq; k += kThreads) v.next_old[v.n_pad_m1 - (sm.base_oldq + k)] = sm.out_old[kOutHalf + k];
         for (uint32_t k = threadIdx.x; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
+        if (sp) park_store(cx, sm, t, sp);
         __syncthreads();
+        if (sp) {
+            if (threadIdx.x < 32) sm.pk_n[threadIdx.x] = 0;
+            if (threadIdx.x == 32) sm.n_pk = 0;
+            __syncthreads();
+        }
     }
 }
 
@@ -880,11 +979,10 @@ static __device__ __forceinline__ void flush_survivors(PassSmem &sm, bool flush_
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
 #endif
 static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep,
-                                bool defer_counters = false)
+                                int &bank_staged, bool defer_counters = false)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
-    const bool finalize = t >= cx.T;
     int bpr = cx.blocks_per_rep;
     int rep_first = my_slot < reps_per_sweep ? my_slot : cx.n_rep, rep_step = reps_per_sweep;
 #if SEIR_DYNAMIC_MAP
@@ -932,9 +1030,15 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
     // (CTAs without a replica idle through the pass; they must still reach the grid barrier)
     for (int rep = rep_first; rep < cx.n_rep; rep += rep_step) {
         const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
-        uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_oldq = cnt_new + (cx.T + 2);
+        uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_pk = cnt_new + (cx.T + 2);
         const RepView &v = sm.v;
         if (tid == 0) {
+            const RepParams rp = cx.rp[rep];  // (one request per CTA: the same line asked for by every warp queues up at its L2 slice)
+            sm.rp = rp;
+            sm.v.T = rp.T;
+            const double *bank = cx.bank + (size_t)rp.bank * kBankStride;
+            sm.v.p_ms = bank + kBankPms; sm.v.p_sc = bank + kBankPsc; sm.v.p_cd = bank + kBankPcd;
+            sm.v.p_contact = bank + kBankPcontact;
             sm.v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
             sm.v.winner = cx.winner + (size_t)rep * cx.n_pad;
             sm.v.rec = cx.rec + (size_t)rep * cx.n_pad;
@@ -943,27 +1047,47 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             sm.v.next_new = cx.list_new + lrow;
             sm.v.next_old_cnt = cnt_old + (t + 1);
             sm.v.next_new_cnt = cnt_new + (t + 1);
-            sm.v.next_oldq_cnt = cnt_oldq + (t + 1);
+            sm.v.pk_cnt = cnt_pk;
+            sm.v.pk_pool = cx.pk_pool + (size_t)rep * kParkRing * cx.n_pad;
             sm.v.n_pad_m1 = (uint32_t)(cx.n_pad - 1);
             sm.v.seed = cx.seeds[rep];
-            sm.v.home_on = cx.t_stayhome >= 1 && t >= cx.t_stayhome;          // :243-244
-            sm.v.phase = (cx.t_lockdown >= 1 && t >= cx.t_lockdown) ? 1 : 0;  // :234-240
+            sm.v.home_on = rp.t_stayhome >= 1 && t >= rp.t_stayhome;          // :243-244
+            sm.v.phase = (rp.t_lockdown >= 1 && t >= rp.t_lockdown) ? 1 : 0;  // :234-240
             sm.v.rep = rep;
-            sm.v.tracing = cx.trace_from >= 1 && t >= cx.trace_from;          // :241-242
+            sm.v.tracing = rp.trace_from >= 1 && t >= rp.trace_from;          // :241-242
         }
+
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
+        const uint32_t *cur_pk = cx.pk_pool + ((size_t)rep * kParkRing + (size_t)(t & (kParkRing - 1))) * cx.n_pad;  // today's bucket
         // today's list lengths: ONE request per CTA and counter (a load by every warp of the grid is 4 736 requests
         // for the same L2 line, which its slice serves one at a time: 2 us at the start of every pass)
-        if (tid < 3) sm.list_n[tid] = __ldcg((tid == 0 ? cnt_new : tid == 1 ? cnt_old : cnt_oldq) + t);
+        if (tid < 3) sm.list_n[tid] = __ldcg((tid == 0 ? cnt_new : tid == 1 ? cnt_old : cnt_pk) + t);
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
         if (tid >= 32 && tid < 36) sm.cnt[tid - 32] = 0;
-        if (tid == 64) { sm.n_old = 0; sm.n_oldq = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
+        if (tid == 64) { sm.n_old = 0; sm.n_pk = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_draw = 0; sm.next_group = 0; }
+        if (tid >= 96 && tid < 128) sm.pk_n[tid - 96] = 0;
         __syncthreads();
-        const uint32_t n_new = sm.list_n[0], n_old = sm.list_n[1], n_oldq = sm.list_n[2];
-        // three segments, each starting on a multiple of 32: new infectees (their record build is the longest path),
-        // agents that may transmit, quarantined agents -- a warp of a dense day serves one kind
-        const uint32_t o_t = (n_new + 31u) & ~31u, o_q = o_t + ((n_old + 31u) & ~31u);
-        const uint32_t count = o_q + n_oldq;
+        const RepParams rp = sm.rp;
+        if (t > rp.T) {  // (a replica with a shorter horizon than the launch's: finished)
+            __syncthreads();  // (sm.rp is rewritten for the next replica)
+            continue;
+        }
+        const bool finalize = t >= rp.T;
+        if (bank_staged != rp.bank) {  // (CTA-uniform: every thread keeps track of the set it saw staged; read after the round's first barrier)
+            const double *src = cx.bank + (size_t)rp.bank * kBankStride + kBankNatEn;
+            for (int k = tid; k < 4 * kAges; k += kThreads) sm.nat_enlam[k] = src[k];
+            bank_staged = rp.bank;
+        }
+        // yesterday's bucket has been consumed: its chunks go back to the free ring (one warp of the replica's first CTA;
+        // today's allocations cannot reach these ring slots: the ring holds twice the chunks that can be in use)
+        // (pass T only finalises: the agents infected on the last day get their records, nobody else is visited)
+        const uint32_t n_new = sm.list_n[0], n_old = finalize ? 0u : sm.list_n[1], n_pk = finalize ? 0u : sm.list_n[2];
+        // three segments, each starting on a multiple of 32 -- a warp of a dense day serves one kind -- the heaviest
+        // first (the warps grab the groups in this order, and the pass lasts as long as its last group): parked
+        // agents due today (every one of them has an event, most of them draws), new infectees (record build),
+        // agents that may transmit
+        const uint32_t o_n = (n_pk + 31u) & ~31u, o_t = o_n + ((n_new + 31u) & ~31u);
+        const uint32_t count = o_t + n_old;
         // this CTA's share of the list: groups of G = 32/S entries (one entry per group while the list is
         // shorter than the replica's warps: a warp pays for every divergent path of its lanes), dealt round-robin
         // to the replica's CTAs (the new infectees, whose record build is the longest path, lead the list: a
@@ -978,12 +1102,11 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         const uint32_t rounds = (my_groups + kGroupsPerRound - 1u) / kGroupsPerRound;
         SEIR_STAMP(0);
 
-        uint32_t reserved = 0;  // thread 0 / 32: offset of the round's staged survivors in tomorrow's list
+        uint32_t reserved = 0;  // thread 0: offset of the round's staged survivors in tomorrow's list
         for (uint32_t round = 0; round < rounds; ++round) {
             // ================= stage A: the round's groups, grabbed by the warps =================
             const uint32_t g_lo = round * kGroupsPerRound;
             const uint32_t g_hi = g_lo + kGroupsPerRound < my_groups ? g_lo + kGroupsPerRound : my_groups;
-            const uint32_t subs = (g_hi - g_lo + (uint32_t)kWarps - 1u) / (uint32_t)kWarps;  // slots in use: subs * kThreads (upper bound)
             for (uint32_t sl = tid; sl < (g_hi - g_lo) * 32u; sl += kThreads) sm.hit_n[sl] = 0;
             __syncthreads();  // (a full draw queue makes stage A process hits in place)
             for (;;) {
@@ -996,15 +1119,40 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 { const uint32_t slot = (k - g_lo) * 32u + lane; SEIR_FINE(0); }
 #endif
                 const uint32_t e = ((k * (uint32_t)bpr + (uint32_t)my_part) << lgG) + lane;
-                const bool is_new = e < n_new, is_t = e >= o_t && e - o_t < n_old, is_q = e >= o_q && e - o_q < n_oldq;
+                const bool is_q = e < n_pk, is_new = e >= o_n && e - o_n < n_new, is_t = e >= o_t && e - o_t < n_old;
                 const bool has = lane < G && (is_new || is_t || is_q);
                 const uint32_t slot = (k - g_lo) * 32u + lane;
                 int keep = DAY_DROP;
                 uint32_t i = 0;
+#if SEIR_PREFETCH
+                // the group one of this CTA's warps takes kWarps grabs from now: ask the L2 for its agents' records and
+                // household words now (the loads of a group are dependent DRAM round trips: entry -> record -> household)
+                uint32_t i2 = 0xFFFFFFFFu;
+                bool new2 = false;
+                {
+                    const uint32_t k2 = k + (uint32_t)kWarps;
+                    const uint32_t e2 = ((k2 * (uint32_t)bpr + (uint32_t)my_part) << lgG) + lane;
+                    if (k2 < g_hi && lane < G) {
+                        if (e2 < n_pk) i2 = __ldcg(cur_pk + e2);
+                        else if (e2 >= o_n && e2 - o_n < n_new) { i2 = __ldcg(cur_new + (e2 - o_n)); new2 = true; }
+                        else if (e2 >= o_t && e2 - o_t < n_old) i2 = __ldcg(cur_old + (e2 - o_t));
+                    }
+                }
+#endif
                 if (has) {
-                    i = is_new ? __ldcg(cur_new + e) : is_t ? __ldcg(cur_old + (e - o_t)) : __ldcg(cur_old + (sm.v.n_pad_m1 - (e - o_q)));
+                    i = is_q ? __ldcg(cur_pk + e) : is_new ? __ldcg(cur_new + (e - o_n)) : __ldcg(cur_old + (e - o_t));
+#if SEIR_PREFETCH
+                    if (!is_new && (int64_t)i < cx.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.rec + i));  // (its own record: in flight while i2 arrives)
+#endif
+#if SEIR_PREFETCH
+                    if (i2 != 0xFFFFFFFFu && (int64_t)i2 < cx.n) {
+                        if (!new2) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.rec + i2));
+                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(cx.stat + i2));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(v.winner + i2));
+                    }
+#endif
                     SEIR_FINE(1);
-                    if (SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_oldq) <= cx.n, cx, rep))
+                    if (SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_pk) <= cx.n, cx, rep))
                         keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
                     SEIR_FINE(8);
                 }
@@ -1018,24 +1166,6 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             }
             __syncthreads();
             SEIR_STAMP(1);
-            // ================= stage E: progression events, compacted =================
-            if (sm.n_ev) {
-                const uint32_t ne = sm.n_ev;
-                const uint32_t Sq = spread_of(ne, kThreads), per = kThreads / Sq;
-                for (uint32_t q0 = 0; q0 < ne; q0 += per) {
-                    const uint32_t q = q0 + (uint32_t)tid / Sq;
-                    int keep = DAY_DROP;
-                    uint32_t i = 0;
-                    if ((((uint32_t)tid & (Sq - 1u)) == 0u) && q < ne) {
-                        const uint32_t slot = sm.evq[q];
-                        i = sm.slot_agent[slot];
-                        AgentRec r = load_rec(v.rec + i);
-                        keep = agent_day<true>(cx, sm, slot, i, r, false, t);
-                    }
-                    append_survivors(sm, keep, i);
-                }
-                __syncthreads();
-            }
             SEIR_STAMP(2);
             reserved = reserve_survivors(sm);  // (nobody stages a survivor after this point of the round)
             // ================= stage D: draw items =================
@@ -1069,7 +1199,6 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             // ================= stage W: infector counters (:357-359, :386-390) =================
             {
                 const uint32_t ns = (g_hi - g_lo) * 32u;
-                (void)subs;
                 if (any_hit) {
                     for (uint32_t sl = tid; sl < ns; sl += kThreads) {
                         const uint32_t hn = sm.hit_n[sl];
@@ -1091,15 +1220,15 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             __syncthreads();
             // more rounds follow: empty the staging buffers
             if (round + 1u < rounds) {
-                flush_survivors(sm, sm.n_new > (uint32_t)(kOutNew - kHitCap), reserved);
-                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_ev = 0; sm.n_draw = 0; sm.next_group = 0; }
+                flush_survivors(cx, sm, t, sm.n_new > (uint32_t)(kOutNew - kHitCap), reserved);
+                if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_draw = 0; sm.next_group = 0; }
                 __syncthreads();
             }
             SEIR_STAMP(6);
             stamped = true;
         }
         stamped = false;
-        flush_survivors(sm, true, reserved, rounds != 0u);
+        flush_survivors(cx, sm, t, true, reserved, rounds != 0u);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {
@@ -1107,11 +1236,11 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             if (val) {
                 const int row = k / kAges;
                 const int day = row < kTalLagRows ? t - 1 : t;
-                if (day < cx.T) atomicAdd(&tal[(size_t)day * TAL_ROWS * kAges + k], val);
+                if (day < rp.T) atomicAdd(&tal[(size_t)day * TAL_ROWS * kAges + k], val);
             }
         }
         if (tid == 0) {
-            // run counters (agent-days stepped, infections, hits): 296 CTAs adding to the same three words every pass
+            // run counters (list entries visited, infections, hits): 296 CTAs adding to the same three words every pass
             // queue up at one L2 slice in front of the grid barrier's fence; a CTA that serves ONE replica for the
             // whole kernel keeps its share in shared memory and adds it once, at the end (flush_run_counters)
             if (defer_counters) {
@@ -1199,9 +1328,10 @@ __device__ __noinline__ void trace_mark(const DevCtx &cx, const TraceView &tv, u
             st |= ST_Q;
             atomicAdd(tv.tally_day + TAL_NEW_Q2 * kAges + age, 1u);
         }
-    } else if (!(st & ST_Q)) {
+    } else if (!(st & ST_Q)) {  // an E / Mild / Severe / Critical agent: one more quarantined active agent from today on
         st |= ST_Q;
         if (r.t_q_on() == NEVER) r.set_t_q_on((uint16_t)t);
+        atomicAdd(tv.tally_day + TAL_D_Q * kAges + age, 1u);
     }
     tw = (tw & 0xFFFFu) | ((uint32_t)t << 16);
     r.set_state(st);

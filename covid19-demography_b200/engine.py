@@ -13,6 +13,7 @@ from . import tables as _tables
 
 MODE_NATIVE, MODE_REPLAY = 0, 1
 LAUNCH_PERSISTENT, LAUNCH_PER_DAY = 0, 1
+HISTORY = {"eager": 0, "on_demand": 1}
 MODES = {"native": MODE_NATIVE, "replay": MODE_REPLAY}
 LAUNCHES = {"persistent": LAUNCH_PERSISTENT, "per_day": LAUNCH_PER_DAY}
 
@@ -28,14 +29,15 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_get_agent_vector", "seir_get_history", "seir_get_counters", "seir_destroy",
            "seir_last_error", "seir_device_count", "seir_build_info", "seir_probe_draws",
            "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
-           "seir_get_stage_times", "seir_get_cohorts", "seir_shard_export", "seir_shard_attach")
+           "seir_get_stage_times", "seir_get_cohorts", "seir_shard_export", "seir_shard_attach", "seir_get_visits",
+           "seir_history_preserve", "seir_run_ex", "seir_set_table_bank", "seir_get_prologue")
 
 
 class SeirParams(C.Structure):
     _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("t_lockdown", C.c_int32),
                 ("t_stayhome_start", C.c_int32), ("t_tracing_start", C.c_int32),
                 ("tracing_enabled", C.c_int32), ("mode", C.c_int32), ("launch", C.c_int32),
-                ("reserved0", C.c_int32)] + [(k, C.c_double) for k in (
+                ("history_mode", C.c_int32)] + [(k, C.c_double) for k in (
                     "p_documented_in_mild", "p_infect_given_contact", "asymptomatic_transmissibility",
                     "mean_time_to_severe", "mean_time_mild_recovery", "mean_time_to_critical",
                     "mean_time_severe_recovery", "mean_time_critical_recovery", "mean_time_to_death",
@@ -57,7 +59,13 @@ class SeirTables(C.Structure):
 
 class SeirReplica(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("home_real", C.c_void_p), ("initial_infected", C.c_void_p),
-                ("n_initial", C.c_int64)]
+                ("n_initial", C.c_int64), ("fraction_stay_home", C.c_void_p), ("initial_infected_fraction", C.c_double),
+                ("keyed_prologue", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class SeirOverrides(C.Structure):
+    _fields_ = [("T", C.c_int32), ("t_lockdown", C.c_int32), ("t_stayhome_start", C.c_int32),
+                ("t_tracing_start", C.c_int32), ("table_set", C.c_int32), ("reserved0", C.c_int32)]
 
 
 _lib = None
@@ -75,6 +83,9 @@ def load_library():
                                 C.c_int, C.c_int, C.POINTER(H)]
     lib.seir_set_params.argtypes = [H, C.POINTER(SeirParams), C.POINTER(SeirTables)]
     lib.seir_run.argtypes = [H, C.POINTER(SeirReplica)]
+    lib.seir_run_ex.argtypes = [H, C.POINTER(SeirReplica), C.POINTER(SeirOverrides)]
+    lib.seir_set_table_bank.argtypes = [H, C.c_int, C.POINTER(SeirTables), C.c_void_p]
+    lib.seir_get_prologue.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.seir_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.seir_last_run_ms3.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.seir_get_tallies.argtypes = [H, C.c_int, C.c_void_p]
@@ -82,6 +93,8 @@ def load_library():
     lib.seir_get_history.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.seir_get_counters.argtypes = [H, C.c_int, C.c_void_p]
     lib.seir_get_cohorts.argtypes = [H, C.c_int, C.c_void_p]
+    lib.seir_get_visits.argtypes = [H, C.c_int, C.c_void_p]
+    lib.seir_history_preserve.argtypes = [H]
     lib.seir_shard_export.argtypes = [H, C.c_void_p]
     lib.seir_shard_attach.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.seir_get_day_times.argtypes = [H, C.c_void_p]
@@ -111,7 +124,7 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def make_params(p, mode="native", launch="persistent", tracing_enabled=1):
+def make_params(p, mode="native", launch="persistent", tracing_enabled=1, history="eager"):
     """Pack the reference's `params` mapping into the POD struct of the C ABI."""
     d = _tables.params_to_dict(p)
     sp = SeirParams()
@@ -124,6 +137,7 @@ def make_params(p, mode="native", launch="persistent", tracing_enabled=1):
     sp.tracing_enabled = int(tracing_enabled)
     sp.mode = MODES[mode] if isinstance(mode, str) else int(mode)
     sp.launch = LAUNCHES[launch] if isinstance(launch, str) else int(launch)
+    sp.history_mode = HISTORY[history]
     for k in ("p_documented_in_mild", "p_infect_given_contact", "asymptomatic_transmissibility",
               "mean_time_to_severe", "mean_time_mild_recovery", "mean_time_to_critical",
               "mean_time_severe_recovery", "mean_time_critical_recovery", "mean_time_to_death",
@@ -136,14 +150,20 @@ class Engine:
     """One handle = one device-resident population + state for `n_replicas` concurrent runs."""
 
     def __init__(self, params, households, age, age_groups, diabetes, hypertension, p_infect_household,
-                 tables, n_replicas=1, device=0, mode="native", launch="persistent", tracing_enabled=1):
+                 tables, n_replicas=1, device=0, mode="native", launch="persistent", tracing_enabled=1,
+                 history="eager"):
         self.lib = load_library()
         if self.lib.seir_device_count() < 1:
             raise RuntimeError("no CUDA device: libseir_b200 has no CPU fallback")
         self._h = C.c_void_p()
+        self.run_serial = 0   # runs so far: a lazy history view knows which run it belongs to
+        self.prev_serial = -1  # the run whose history has been set aside on the device (seir_history_preserve)
+        self._views = []       # weak references to the lazy history views handed out for the last two runs
         self.mode, self.launch, self.tracing_enabled = mode, launch, tracing_enabled
-        self.sp = make_params(params, mode, launch, tracing_enabled)
+        self.history_mode = history   # "eager": every run writes the T x n history; "on_demand": rows computed when asked for
+        self.sp = make_params(params, mode, launch, tracing_enabled, history)
         self.n, self.T, self.n_replicas = int(self.sp.n), int(self.sp.T), int(n_replicas)
+        self.T_rep = [self.T] * self.n_replicas   # per-replica horizons of the last run (overrides)
         hh = np.ascontiguousarray(households, dtype=np.int64)
         if hh.ndim != 2 or hh.shape[0] != self.n:
             raise ValueError("households must be [n, W]")
@@ -174,6 +194,24 @@ class Engine:
         tb = self._pack_tables(tables)
         _check(self.lib.seir_create(C.byref(self.sp), C.byref(pop), C.byref(tb), self.n_replicas, int(device),
                                     C.byref(self._h)))
+
+    def set_table_bank(self, table_sets, p_infect_given_contact):
+        """Register table sets for per-replica overrides (`overrides=[{"table_set": k, ...}]` in run): one launch can
+        then batch runs of different grid points of a sweep (parameter_sweep.py:54-56).  Set 0 replaces the engine's own."""
+        arr = (SeirTables * len(table_sets))()
+        keep = []
+        for k, tables in enumerate(table_sets):
+            for name, _ in SeirTables._fields_:
+                v = tables.get(name)
+                if v is not None:
+                    v = np.ascontiguousarray(v, dtype=np.int32 if name == "nat_alias_idx" else np.float64)
+                keep.append(v)
+                setattr(arr[k], name, _ptr(v))
+        pc = np.ascontiguousarray(p_infect_given_contact, dtype=np.float64)
+        if pc.shape != (len(table_sets),):
+            raise ValueError("need one p_infect_given_contact per table set")
+        _check(self.lib.seir_set_table_bank(self._h, len(table_sets), arr, _ptr(pc)))
+        self.n_table_sets = len(table_sets)
 
     def _pack_tables(self, tables):
         tb = SeirTables()
@@ -210,7 +248,7 @@ class Engine:
         if tracing_enabled is not None:
             self.tracing_enabled = tracing_enabled
         if params is not None:
-            sp = make_params(params, self.mode, self.launch, self.tracing_enabled)
+            sp = make_params(params, self.mode, self.launch, self.tracing_enabled, self.history_mode)
             if int(sp.n) != self.n:
                 raise ValueError("params['n'] does not match the resident population")
         else:
@@ -222,18 +260,35 @@ class Engine:
         _check(self.lib.seir_set_params(self._h, C.byref(sp), C.byref(tb) if tb is not None else None))
         self.sp, self.T = sp, int(sp.T)
 
-    def run(self, seeds, home_real=None, initial_infected=None):
-        """seeds[r], home_real[r] (bool[n] or None), initial_infected[r] (int array) per replica."""
+    def run(self, seeds, home_real=None, initial_infected=None, keyed=None, overrides=None):
+        """seeds[r] per replica, and the prologue's picks (seir_individual.py:176-187) either from the caller --
+        home_real[r] (bool[n] or None), initial_infected[r] (int array) -- or made on the device from the keyed
+        contract: keyed[r] = (fraction_stay_home float[101] or None, initial_infected_fraction) (one tuple for all
+        replicas is accepted too).  overrides[r]: dict with any of T, t_lockdown, t_stayhome_start, t_tracing_start,
+        table_set (see set_table_bank) -- one launch over different grid points of a sweep."""
         R = self.n_replicas
         seeds = list(seeds)
         if len(seeds) != R:
             raise ValueError("need one seed per replica")
         home_real = list(home_real) if home_real is not None else [None] * R
         initial_infected = list(initial_infected) if initial_infected is not None else [np.zeros(0, np.int64)] * R
+        if keyed is not None and isinstance(keyed, tuple) and len(keyed) == 2 and not isinstance(keyed[0], tuple):
+            keyed = [keyed] * R
         reps = (SeirReplica * R)()
         keep = []
         for r in range(R):
             reps[r].seed = int(seeds[r]) & 0xFFFFFFFFFFFFFFFF
+            if keyed is not None and keyed[r] is not None:
+                fsh, frac = keyed[r]
+                if fsh is not None:
+                    fsh = np.ascontiguousarray(fsh, dtype=np.float64)
+                    if fsh.shape != (_tables.N_AGES,):
+                        raise ValueError("fraction_stay_home must have 101 entries")
+                keep.append(fsh)
+                reps[r].fraction_stay_home = _ptr(fsh)
+                reps[r].initial_infected_fraction = float(frac)
+                reps[r].keyed_prologue = 1
+                continue
             hr = home_real[r]
             if hr is not None:
                 hr = np.ascontiguousarray(hr, dtype=np.uint8)
@@ -244,7 +299,57 @@ class Engine:
             reps[r].home_real = _ptr(hr)
             reps[r].initial_infected = _ptr(ii) if ii.size else None
             reps[r].n_initial = ii.size
-        _check(self.lib.seir_run(self._h, reps))
+        ov = None
+        T_rep = [self.T] * R
+        if overrides is not None:
+            if len(overrides) != R:
+                raise ValueError("need one overrides entry per replica")
+            ov = (SeirOverrides * R)()
+            for r, o in enumerate(overrides):
+                o = o or {}
+                unknown = set(o) - {"T", "t_lockdown", "t_stayhome_start", "t_tracing_start", "table_set"}
+                if unknown:
+                    raise ValueError("unknown override(s): %s" % sorted(unknown))
+                clamp = lambda v: int(max(-2**31 + 1, min(2**31 - 1, v)))  # noqa: E731
+                ov[r].T = int(o.get("T", self.sp.T))
+                ov[r].t_lockdown = clamp(o.get("t_lockdown", self.sp.t_lockdown))
+                ov[r].t_stayhome_start = clamp(o.get("t_stayhome_start", self.sp.t_stayhome_start))
+                ov[r].t_tracing_start = clamp(o.get("t_tracing_start", self.sp.t_tracing_start))
+                ov[r].table_set = int(o.get("table_set", 0))
+                T_rep[r] = int(ov[r].T)
+        self._keep_live_histories()
+        self.run_serial += 1
+        _check(self.lib.seir_run_ex(self._h, reps, ov))
+        self.T_rep = T_rep
+
+    def prologue_picks(self, replica=0):
+        """(home_real bool[n], initial_infected int64[k]) as the device holds them for the last run."""
+        home = np.zeros(self.n, dtype=np.uint8)
+        k = np.zeros(1, dtype=np.int64)
+        _check(self.lib.seir_get_prologue(self._h, replica, _ptr(home), None, 0, _ptr(k)))
+        init = np.zeros(int(k[0]), dtype=np.int64)
+        _check(self.lib.seir_get_prologue(self._h, replica, None, _ptr(init), init.size, _ptr(k)))
+        return home.view(np.bool_), init
+
+    def register_view(self, view):
+        import weakref
+        self._views.append(weakref.ref(view))
+
+    def _keep_live_histories(self):
+        """The reference hands out fresh arrays per call; here the next run overwrites the device-resident history.
+        Views of the last run that somebody still holds keep working: their history is set aside on the device (one
+        device-to-device copy); views of the run before that, if still alive, take a host copy."""
+        live = [v for v in (r() for r in self._views) if v is not None]
+        older = [v for v in live if v._serial == self.prev_serial and v._host is None]
+        if older:
+            packed = self.history("packed", previous=True, rows=older[0].shape[0])
+            for v in older:
+                v._host = packed
+        last = [v for v in live if v._serial == self.run_serial and v._host is None]
+        if last:
+            _check(self.lib.seir_history_preserve(self._h))
+            self.prev_serial = self.run_serial
+        self._views = [r for r in self._views if r() is not None and r()._host is None]
 
     def last_run_ms(self):
         a, b = C.c_float(), C.c_float()
@@ -261,7 +366,7 @@ class Engine:
         """int64[T, 9, 101]: per-day counts by age, planes S,E,Mild,Documented,Severe,Critical,R,D,Q."""
         out = np.empty((self.T, 9, _tables.N_AGES), dtype=np.int64)
         _check(self.lib.seir_get_tallies(self._h, replica, _ptr(out)))
-        return out
+        return out[:self.T_rep[replica]]
 
     def cohorts(self, replica=0):
         """int64[T, 4, 101]: per exposure day and age -- agents exposed, sum of num_infected_by, dead at
@@ -276,11 +381,11 @@ class Engine:
                                               _ptr(out)))
         return out
 
-    def history(self, which, t0=0, t1=None, replica=0):
-        t1 = self.T if t1 is None else t1
+    def history(self, which, t0=0, t1=None, replica=0, previous=False, rows=None):
+        t1 = (self.T_rep[replica] if rows is None else rows) if t1 is None else t1
         out = np.empty((t1 - t0, self.n), dtype=np.uint8)
-        _check(self.lib.seir_get_history(self._h, replica, PLANE[which] if isinstance(which, str) else which,
-                                         t0, t1, _ptr(out)))
+        code = (PLANE[which] if isinstance(which, str) else which) | (16 if previous else 0)
+        _check(self.lib.seir_get_history(self._h, replica, code, t0, t1, _ptr(out)))
         return out if which in ("packed", 9) else out.view(np.bool_)
 
     def day_times_us(self):
@@ -302,8 +407,10 @@ class Engine:
     def counters(self, replica=0):
         out = np.zeros(4, dtype=np.int64)
         _check(self.lib.seir_get_counters(self._h, replica, _ptr(out)))
+        vis = np.zeros(1, dtype=np.int64)
+        _check(self.lib.seir_get_visits(self._h, replica, _ptr(vis)))
         return {"launches": int(out[0]), "active_agent_days": int(out[1]), "infections": int(out[2]),
-                "hits": int(out[3])}
+                "hits": int(out[3]), "visits": int(vis[0])}
 
     def close(self):
         if self._h:

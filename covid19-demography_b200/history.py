@@ -12,17 +12,39 @@ import numpy as np
 class HistoryPlane:
     __array_priority__ = 100
 
-    def __init__(self, engine, plane, replica=0):
+    def __init__(self, engine, plane, replica=0, tallies=None):
         self._e, self._plane, self._rep = engine, plane, replica
+        self._tallies = tallies   # int64[T, 9, 101] of the run (the per-day sums never touch the history)
+        self._host = None         # packed uint8[T, n] once the run's device history had to give way
         self.shape = (engine.T, engine.n)
         self.dtype = np.dtype(np.bool_)
         self.ndim = 2
+        self._row_t, self._row = None, None   # the last single row fetched (the drivers index X[-1, mask] in loops)
+        self._serial = getattr(engine, "run_serial", 0)
+        if hasattr(engine, "register_view"):
+            engine.register_view(self)
 
     def __len__(self):
         return self.shape[0]
 
     def _rows(self, t0, t1):
-        return self._e.history(self._plane, t0, t1, self._rep)
+        if self._host is not None:   # (two or more runs ago: served from the host copy taken when it was overwritten)
+            p = self._host[t0:t1]
+            k = _PLANE_INDEX[self._plane]
+            comp = {0: 0, 1: 1, 2: 2, 4: 3, 5: 4, 6: 5, 7: 6}.get(k)
+            return (p & 7) == comp if comp is not None else ((p >> 4) & 1) == 1 if k == 3 else ((p >> 3) & 1) == 1
+        cur = getattr(self._e, "run_serial", 0)
+        if cur == self._serial:
+            return self._e.history(self._plane, t0, t1, self._rep)
+        if getattr(self._e, "prev_serial", -1) == self._serial:
+            return self._e.history(self._plane, t0, t1, self._rep, previous=True, rows=self.shape[0])
+        raise RuntimeError("this history was overwritten by a later run on the same device-resident population")
+
+    def _one_row(self, t):
+        if self._row_t != t:
+            self._row, self._row_t = self._rows(t, t + 1)[0], t
+            self._row.setflags(write=False)
+        return self._row
 
     def __array__(self, dtype=None, copy=None):
         a = self._rows(0, self.shape[0])
@@ -30,7 +52,8 @@ class HistoryPlane:
 
     def sum(self, axis=None, **kw):
         """Per-day counts come from the per-age tallies fused into the day step -- no history read."""
-        per_day = self._e.tallies(self._rep)[:, _PLANE_INDEX[self._plane], :].sum(axis=1)
+        tal = self._tallies if self._tallies is not None else self._e.tallies(self._rep)
+        per_day = tal[:, _PLANE_INDEX[self._plane], :].sum(axis=1)
         if axis == 1 or axis == -1:
             return per_day
         if axis is None:
@@ -47,8 +70,9 @@ class HistoryPlane:
             t = int(row) + (T if row < 0 else 0)
             if not 0 <= t < T:
                 raise IndexError("day index out of range")
-            out = self._rows(t, t + 1)[0]
-        elif isinstance(row, slice):
+            out = self._one_row(t)
+            return out[rest] if rest else out
+        if isinstance(row, slice):
             idx = range(*row.indices(T))
             if len(idx) == 0:
                 out = np.zeros((0, self.shape[1]), dtype=np.bool_)
@@ -56,9 +80,8 @@ class HistoryPlane:
                 out = self._rows(idx.start, idx.stop)
             else:
                 out = np.stack([self._rows(t, t + 1)[0] for t in idx])
-        else:
-            out = np.asarray(self)[row]
-        return out[rest] if rest else out
+            return out[(slice(None),) + rest] if rest else out   # the rest indexes the AGENT axis
+        return np.asarray(self)[key]                              # (array / mask row keys: NumPy's own semantics)
 
     def __iter__(self):
         for t in range(self.shape[0]):

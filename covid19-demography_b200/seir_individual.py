@@ -39,7 +39,47 @@ OPTIONS = {
     "device": int(os.environ.get("SEIR_B200_DEVICE", "0")),
 }
 last_engine = None
-"""The Engine of the most recent run_model call (its histories stay valid while it is alive)."""
+"""The Engine of the most recent run_model call (its histories stay valid until the next call on the same population)."""
+_engine_cache = {}
+ENGINE_CACHE_SIZE = int(os.environ.get("SEIR_B200_ENGINE_CACHE", "2"))
+
+
+def _population_key(households, age, diabetes, hypertension, p_infect_household, opt):
+    """Identity of a device-resident population: shapes plus a strided checksum of every array (the drivers pass the
+    same arrays seed after seed -- run_simulation.py:437-444 -- or reload the same pickle, parameter_sweep.py:29).
+    A few hundred kB are read: microseconds against the 1.5 s an engine takes to create at n = 10 M."""
+    import zlib
+
+    def sig(a):
+        a = np.asarray(a)
+        flat = a.reshape(-1)
+        step = max(1, flat.shape[0] // 65536)
+        return (a.shape, str(a.dtype), zlib.crc32(np.ascontiguousarray(flat[::step]).tobytes()),
+                zlib.crc32(np.ascontiguousarray(flat[-4096:]).tobytes()))
+    return (sig(households), sig(age), sig(diabetes), sig(hypertension), sig(p_infect_household),
+            opt["mode"], opt["launch"], opt["device"])
+
+
+def _engine_for(key, build):
+    """Least-recently-used cache of engines (an engine owns O(100 B/agent) of HBM: keep few)."""
+    eng = _engine_cache.pop(key, None)
+    fresh = eng is None
+    if fresh and ENGINE_CACHE_SIZE <= 0:
+        return build(), True   # no cache: every call owns its engine (earlier histories stay readable)
+    if fresh:
+        while len(_engine_cache) >= max(1, ENGINE_CACHE_SIZE):
+            _engine_cache.pop(next(iter(_engine_cache))).close()
+        eng = build()
+    _engine_cache[key] = eng
+    return eng, fresh
+
+
+def clear_engine_cache():
+    global last_engine
+    for eng in _engine_cache.values():
+        eng.close()
+    _engine_cache.clear()
+    last_engine = None
 
 
 def run_complete_simulation(seed, country, contact_matrix, p_mild_severe, p_severe_critical, p_critical_death,
@@ -62,7 +102,7 @@ def run_complete_simulation(seed, country, contact_matrix, p_mild_severe, p_seve
         from covid19_demography_b200 import population as _population
         households, age = _population.sample_households(country, n)
         age_groups = tuple([np.where(age == i)[0] for i in range(0, n_ages)])
-        diabetes, hypertension = _population.sample_joint_comorbidities(age, country)
+        diabetes, hypertension = _population.sample_comorbidities(age, country)
         with open(fname, 'wb') as f:
             pickle.dump((age, households, diabetes, hypertension, age_groups), f)
     print('starting simulation')
@@ -92,13 +132,19 @@ def run_model(seed, households, age, age_groups, diabetes, hypertension, contact
                               p_severe_critical, p_critical_death, with_replay=(opt["mode"] == "replay"))
     home_real, initial_infected = _tables.prologue(seed, age_groups, n, fraction_stay_home,
                                                    p["initial_infected_fraction"])
-    eng = _engine.Engine(p, households, age, age_groups, diabetes, hypertension, p_infect_household, tb,
-                         n_replicas=1, device=opt["device"], mode=opt["mode"], launch=opt["launch"],
-                         tracing_enabled=tracing_enabled)
+    # the population stays resident on the device between calls (the drivers call once per seed with the same
+    # arrays): only the scalars, the tables and the per-run picks travel
+    key = _population_key(households, age, diabetes, hypertension, p_infect_household, opt)
+    eng, fresh = _engine_for(key, lambda: _engine.Engine(
+        p, households, age, age_groups, diabetes, hypertension, p_infect_household, tb, n_replicas=1,
+        device=opt["device"], mode=opt["mode"], launch=opt["launch"], tracing_enabled=tracing_enabled))
+    if not fresh:
+        eng.set_params(p, tb, tracing_enabled=tracing_enabled)
     print('run_model')
     eng.run([seed], [home_real], [initial_infected])
     last_engine = eng
-    planes = tuple(HistoryPlane(eng, k) for k in _engine.PLANES_IN_ORDER)
+    tal = eng.tallies(0)
+    planes = tuple(HistoryPlane(eng, k, tallies=tal) for k in _engine.PLANES_IN_ORDER)
     v = eng.agent_vector
     return planes + (v("num_infected_by"), v("time_documented"), v("time_to_activation"), v("time_to_death"),
                      v("time_to_recovery"), v("time_critical"), v("time_exposed"), v("num_infected_asympt"),

@@ -106,6 +106,79 @@ def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_facto
     return out
 
 
+SITE_HOME, SITE_CASES = 14, 15  # include/seir_draws.h
+
+
+def _philox4x32(k0, k1, c0, c1, c2, c3):
+    """Philox4x32-10 on NumPy arrays of counters (include/seir_draws.h, sd_philox)."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for c in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    lo32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, p1 & lo32, n2, p0 & lo32
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def _fmix32(x):
+    x = x.astype(np.uint64)
+    m = np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x85EBCA6B)) & m
+    x ^= x >> np.uint64(13); x = (x * np.uint64(0xC2B2AE35)) & m
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def keyed_picks(seed, site, group, n, k):
+    """The first k entries of the keyed permutation of [0, n) (include/seir_draws.h: sd_perm_make / sd_perm_at):
+    a 6-round Feistel network over the smallest even number of bits holding n, cycle-walked into [0, n)."""
+    if k <= 0:
+        return np.zeros(0, dtype=np.int64)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    a = _philox4x32(seed & 0xFFFFFFFF, seed >> 32, [group], [0], [site], [0])
+    b = _philox4x32(seed & 0xFFFFFFFF, seed >> 32, [group], [0], [site], [1])
+    keys = [np.uint64(int(a[j][0])) for j in range(4)] + [np.uint64(int(b[0][0])), np.uint64(int(b[1][0]))]
+    bits = 0
+    while bits < 32 and (1 << bits) < n:
+        bits += 1
+    half = np.uint64(1 if bits < 2 else (bits + 1) // 2)
+    mask = np.uint64((1 << int(half)) - 1)
+    x = np.arange(k, dtype=np.uint64)
+    todo = np.ones(k, dtype=bool)
+    while todo.any():
+        xs = x[todo]
+        L, R = xs >> half, xs & mask
+        for r in range(6):
+            f = _fmix32(R ^ keys[r]) & mask
+            L, R = R, L ^ f
+        xs = (L << half) | R
+        x[todo] = xs
+        todo[todo] = xs >= np.uint64(n)
+    return x.astype(np.int64)
+
+
+def prologue_keyed(seed, age_groups, n, fraction_stay_home, initial_infected_fraction):
+    """The prologue's picks (seir_individual.py:176-187) under the KEYED contract -- what the device draws itself
+    when a replica asks for it (Engine.run(..., keyed=(fraction_stay_home, initial_infected_fraction))): per age the
+    first int(fraction * size) entries of a keyed permutation of the age group shelter at home, the first
+    int(fraction * n) entries of a keyed permutation of the agents are the initial cases.  Same counts and the same
+    uniform-subset distribution as the reference's `np.random.choice(..., replace=False)`; not its picks per seed
+    (tables.prologue replays those).  Returns (home_real bool[n], initial_infected int64[k])."""
+    home = np.zeros(n, dtype=np.bool_)
+    fsh = np.asarray(fraction_stay_home, dtype=np.float64)
+    for a, matches in enumerate(age_groups):
+        m = len(matches)
+        k = int(fsh[a] * m) if m else 0
+        if k > 0:
+            home[np.asarray(matches)[keyed_picks(seed, SITE_HOME, a, m, k)]] = True
+    k0 = int(initial_infected_fraction * n)
+    return home, keyed_picks(seed, SITE_CASES, 0, n, k0)
+
+
 def prologue_fast(seed, age_groups, n, fraction_stay_home, initial_infected_fraction):
     """The prologue's picks (seir_individual.py:176-187) from the same distributions -- per age a uniform
     subset of int(fraction * size) agents shelters at home, int(fraction * n) uniform agents are the initial

@@ -29,6 +29,9 @@ extern "C" {
 #define SEIR_MODE_REPLAY 1         /* community: 101 Poisson draws per sender-day, as :367-374  */
 #define SEIR_LAUNCH_PERSISTENT 0   /* one cooperative kernel over all days, one grid barrier per day */
 #define SEIR_LAUNCH_PER_DAY 1      /* one kernel launch per day (debug / comparison)            */
+#define SEIR_HISTORY_EAGER 0       /* every run writes the reference's T x n history (one packed byte per agent-day)  */
+#define SEIR_HISTORY_ON_DEMAND 1   /* no T x n buffer: seir_get_history computes the rows asked for from the per-agent
+                                      records of the LAST run (ensembles and sweeps that consume tallies only)      */
 
 /* scalar parameters: the `params` dict of seir_individual.py:135-158 */
 typedef struct {
@@ -42,7 +45,7 @@ typedef struct {
                                   do_contact_tracing (:60-88) runs on the device from day t_tracing_start */
     int32_t mode;              /* SEIR_MODE_*                                         */
     int32_t launch;            /* SEIR_LAUNCH_*                                       */
-    int32_t reserved0;
+    int32_t history_mode;      /* SEIR_HISTORY_* (read by seir_create only)          */
     double p_documented_in_mild;          /* :143 */
     double p_infect_given_contact;        /* :146 */
     double asymptomatic_transmissibility; /* :145 */
@@ -89,13 +92,35 @@ typedef struct {
     const double *enlam_post;           /* [101,101] exp(-C/lockdown_factor)  (replay mode)                             */
 } seir_tables;
 
-/* per-run inputs (one per replica): the prologue of :176-187 is host code */
+/* per-run inputs (one per replica): the prologue of :176-187.
+ * keyed_prologue == 0: the caller made the picks (tables.prologue replays the reference's Mersenne-Twister picks):
+ *   home_real / initial_infected are copied to the device.
+ * keyed_prologue != 0: the DEVICE makes them from the keyed contract (include/seir_draws.h, sd_perm): per age the
+ *   first int(fraction_stay_home[a] * N_a) entries of a keyed permutation of the age group, and the first
+ *   int(initial_infected_fraction * n) entries of a keyed permutation of the agents -- the same counts and the same
+ *   uniform-subset distribution as :178-187, nothing but 101 doubles crosses PCIe (tables.prologue_keyed is the host
+ *   restatement of the same picks). */
 typedef struct {
     uint64_t seed;                      /* Philox key                                 */
     const uint8_t *home_real;           /* [n] 0/1 shelter-in-place assignment, or NULL (nobody) */
     const int64_t *initial_infected;    /* [n_initial] agent ids exposed at t=0 (:187)  */
     int64_t n_initial;
+    const double *fraction_stay_home;   /* [101] (:178-182), keyed prologue only; NULL = nobody */
+    double initial_infected_fraction;   /* (:186), keyed prologue only                */
+    int32_t keyed_prologue;
+    int32_t reserved0;
 } seir_replica;
+
+/* Optional per-replica overrides: one launch batches runs of DIFFERENT grid points of a sweep
+ * (parameter_sweep.py:54-56,120-126: p_infect_given_contact x mortality_multiplier x start date).  What the grid
+ * varies reaches the device as a set of draw tables (severity tables and the kept-contact Poisson table depend on
+ * the first two) and as day numbers (the start date moves T and the switch days); every other scalar is the
+ * handle's.  T must not exceed the handle's T. */
+typedef struct {
+    int32_t T, t_lockdown, t_stayhome_start, t_tracing_start;
+    int32_t table_set;                  /* index into the sets registered with seir_set_table_bank */
+    int32_t reserved0;
+} seir_overrides;
 
 /* per-agent output vectors, as doubles with the reference's sentinels (:200-218) */
 enum {
@@ -120,6 +145,7 @@ enum {
 /* history planes for seir_get_history, in the order of the reference's return tuple (:392) */
 enum { SEIR_H_S = 0, SEIR_H_E, SEIR_H_MILD, SEIR_H_DOCUMENTED, SEIR_H_SEVERE, SEIR_H_CRITICAL,
        SEIR_H_R, SEIR_H_D, SEIR_H_Q, SEIR_H_PACKED /* raw byte: bits0-2 compartment, bit3 Q, bit4 Documented */ };
+#define SEIR_H_PREVIOUS 16         /* OR into `which`: read the history set aside by seir_history_preserve */
 
 typedef struct seir_handle seir_handle;
 
@@ -144,6 +170,14 @@ int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables
 
 /* Run all replicas for T days.  reps[n_replicas].  Blocking. */
 int seir_run(seir_handle *h, const seir_replica *reps);
+/* The same with per-replica overrides (overrides[n_replicas], or NULL = seir_run). */
+int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *overrides);
+/* Register n_sets table sets for seir_overrides.table_set (set 0 replaces the handle's own tables);
+ * p_infect_given_contact[n_sets] is the scalar of :146 each set was built for (replay mode reads it). */
+int seir_set_table_bank(seir_handle *h, int n_sets, const seir_tables *sets, const double *p_infect_given_contact);
+/* The picks of the last run's prologue as the device holds them: home_out[n] 0/1 (all 0 when stay-home never
+ * starts within T), init_out[cap] agent ids, *n_init their number. */
+int seir_get_prologue(seir_handle *h, int replica, uint8_t *home_out, int64_t *init_out, int64_t cap, int64_t *n_init);
 
 /* Device time of the last seir_run, CUDA events on the launching stream:
  * *day_loop_ms = the day loop (persistent kernel or T launches),
@@ -167,11 +201,18 @@ int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out);
 
 /* History plane `which` for days [t0, t1), out[(t1-t0)*n] bytes (0/1, or the packed byte). */
 int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uint8_t *out);
+/* The reference returns fresh arrays from every run_model call; here the T x n history lives on the device and the next
+ * seir_run overwrites it.  seir_history_preserve sets the packed history of the LAST run aside (one device-to-device
+ * copy, 0.2 ms at n = 10 M, T = 60) so that it stays readable (which | SEIR_H_PREVIOUS) across the next run. */
+int seir_history_preserve(seir_handle *h);
 
 /* Counters of the last run: out[0]=kernels launched, out[1]=sum over days of active agents
  * A(t-1) (E/Mild/Severe/Critical), out[2]=infections I (excluding the initial ones),
  * out[3]=transmission hits (>= infections: same-day multiple hits count). */
 int seir_get_counters(seir_handle *h, int replica, int64_t *out4);
+/* List entries the day loop of the last run visited (new infectees + agents that may transmit + parked agents
+ * on their due days): the work actually done, against the A(t-1) sum of seir_get_counters. */
+int seir_get_visits(seir_handle *h, int replica, int64_t *out);
 
 /* %globaltimer (ns) stamped by CTA 0 at the start of every day pass of the last run: out[T+2],
  * out[t] = start of pass t (1 <= t <= T), out[T+1] = end of the persistent day loop (0 in per-day mode). */
@@ -193,6 +234,9 @@ const char *seir_last_error(void);
 int seir_device_count(void);
 /* library self-description (arch the kernels were compiled for, build flags) */
 const char *seir_build_info(void);
+/* sizeof of the ABI's structs as compiled: seir_params, seir_population, seir_tables, seir_replica, seir_overrides
+ * (a binding checks its own struct definitions against these) */
+void seir_abi_sizes(int64_t out5[5]);
 
 /* draw-contract probes (device evaluation of include/seir_draws.h, for parity tests) */
 int seir_probe_draws(int device, uint64_t seed, int64_t m, double mean, double mu, double sigma, double enlam,

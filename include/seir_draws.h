@@ -75,7 +75,9 @@ enum {
     SD_SITE_NPICK = 10, /* native community: sub=k, lane0 -> contact age (alias table), words2,3 -> member index */
     SD_SITE_TR_HH = 11, /* tracing, household edge (:72)  agent=tracer sub=slot j lane0                 */
     SD_SITE_TR_OUT = 12,/* tracing, outside edge (:83)    agent=tracer sub=log slot j lane0             */
-    SD_SITE_INIT = 13   /* prologue (:227) activation time of an initially infected agent, polar calls  */
+    SD_SITE_INIT = 13,  /* prologue (:227) activation time of an initially infected agent, polar calls  */
+    SD_SITE_HOME = 14,  /* keyed prologue: Home_real of one age group (:178-182), agent = age, round keys of sd_perm */
+    SD_SITE_CASES = 15  /* keyed prologue: initial_infected (:187), agent = 0, round keys of sd_perm             */
 };
 
 /* event ordinal of an infection inside its infector's day, monotone in the
@@ -126,6 +128,49 @@ SD_FN uint64_t sd_index(sd_block b, uint64_t n)
 {
     uint64_t r = ((uint64_t)b.w[2] << 32) | (uint64_t)b.w[3];
     return SD_MULHI64(r, n);
+}
+
+/* ---- keyed permutation of [0, n): the prologue's `choice(..., replace=False)` (:181, :187) -----------------------
+ * The reference draws a k-subset as the first k entries of a random permutation.  Here the permutation is a keyed
+ * bijection: a 6-round Feistel network over the smallest even number of bits that holds n, with cycle walking (apply
+ * again while the image is >= n), its round keys one pair of Philox blocks per (seed, site, group).  The k-subset is
+ * { sd_perm_at(P, r) : r < k }: exactly k distinct members, any of them computable on its own -- O(k) work, no scan
+ * over the n candidates, no atomics on a counter, the same on the host and on the device.                         */
+typedef struct { uint32_t k[6]; uint32_t half, mask, n; } sd_perm;
+SD_FN uint32_t sd_fmix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+SD_FN sd_perm sd_perm_make(uint64_t seed, uint32_t site, uint32_t group, uint32_t n)
+{
+    sd_perm P;
+    const sd_block a = sd_draw(seed, group, 0u, site, 0u), b = sd_draw(seed, group, 0u, site, 1u);
+    P.k[0] = a.w[0]; P.k[1] = a.w[1]; P.k[2] = a.w[2]; P.k[3] = a.w[3]; P.k[4] = b.w[0]; P.k[5] = b.w[1];
+    uint32_t bits = 0;
+    while (bits < 32u && ((uint64_t)1 << bits) < (uint64_t)n) ++bits;   /* 2^bits >= n */
+    P.half = bits < 2u ? 1u : (bits + 1u) / 2u;
+    P.mask = (1u << P.half) - 1u;
+    P.n = n;
+    return P;
+}
+SD_FN uint32_t sd_perm_at(const sd_perm *P, uint32_t rank)            /* rank < n */
+{
+    uint32_t x = rank;
+    do {
+        uint32_t L = x >> P->half, R = x & P->mask;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < 6; ++r) {
+            const uint32_t f = sd_fmix32(R ^ P->k[r]) & P->mask;
+            const uint32_t nl = R;
+            R = L ^ f;
+            L = nl;
+        }
+        x = (L << P->half) | R;
+    } while (x >= P->n);
+    return x;
 }
 
 /* ---- bit moves -------------------------------------------------------- */

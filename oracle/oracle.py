@@ -187,3 +187,14 @@ OUTPUT_NAMES = ("S", "E", "Mild", "Documented", "Severe", "Critical", "R", "D", 
                 "time_documented", "time_to_activation", "time_to_death", "time_to_recovery",
                 "time_critical", "time_exposed", "num_infected_asympt", "age", "time_infected",
                 "time_to_severe")
+
+
+def perm_picks(seed, site, group, n, k):
+    """First k entries of the keyed permutation of [0, n) (include/seir_draws.h, sd_perm) from the C header."""
+    out = np.zeros(k, dtype=np.int64)
+    L = lib()
+    L.oracle_perm_picks.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]
+    L.oracle_perm_picks.restype = None
+    L.oracle_perm_picks(int(seed) & 0xFFFFFFFFFFFFFFFF, site, group, n, k, out.ctypes.data)
+    return out
+

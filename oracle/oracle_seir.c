@@ -668,3 +668,12 @@ void oracle_mt_doubles(uint32_t seed, double *y, int64_t m)
     mt_state s; mt_init(&s, seed);
     for (int64_t i = 0; i < m; i++) y[i] = mt_double(&s);
 }
+
+/* keyed prologue (include/seir_draws.h, sd_perm): the first k entries of the keyed permutation of [0, n) -- the picks
+ * the device makes for Home_real (site SD_SITE_HOME, group = age) and initial_infected (site SD_SITE_CASES, group 0) */
+void oracle_perm_picks(uint64_t seed, uint32_t site, uint32_t group, uint32_t n, int64_t k, int64_t *out)
+{
+    sd_perm P = sd_perm_make(seed, site, group, n);
+    for (int64_t r = 0; r < k; r++) out[r] = (int64_t)sd_perm_at(&P, (uint32_t)r);
+}
+

@@ -35,7 +35,7 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = _run(["--n", "200000", "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-tracing-leg"], 600)
+    d = _run(["--n", "200000", "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--c3-n", "300000"], 900)
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d) and "impl" not in d
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
     assert d["value"] > 0 and d["gpu_launches"] >= 2 * 3
@@ -44,3 +44,13 @@ def test_gpu_arm_line():
     assert d["e2e"]["value"] > 0 and d["e2e"]["value"] != d["value"] and d["e2e"]["d2h_bytes_per_step"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # every BASELINE.json config is a leg of the line, with its own numbers
+    cfg = d["config"]
+    for leg in ("c1", "c4_like", "c5_like", "c3_single_gpu", "stress_variant", "as_reference_tracing", "dropin_run_model"):
+        assert leg in cfg and "error" not in cfg[leg], (leg, cfg.get(leg))
+    for leg in ("c1", "c4_like", "c5_like", "c3_single_gpu"):
+        assert cfg[leg]["agent_days_per_sec"] > 0 and cfg[leg]["sim_runs_per_hour_e2e"] > 0 and 0 < cfg[leg]["roofline_frac"] < 1.5
+    assert cfg["dropin_run_model"]["warm_call_ms"] < cfg["dropin_run_model"]["first_call_ms"]
+    k = r["kernels"]
+    assert abs(k["seir_persistent_kernel"]["algorithmic_bytes"] + k["seir_materialize_kernel"]["algorithmic_bytes"]
+               - r["algorithmic_bytes_per_launch"]) < 1e-6 * r["algorithmic_bytes_per_launch"]

@@ -109,3 +109,30 @@ def test_run_complete_simulation_keeps_the_population_pickle(gpu_engine_module, 
     for x, y in zip(a, b):
         assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True)
     assert np.asarray(a[0]).shape == (20, 2000)
+
+
+@pytest.mark.gpu
+def test_histories_of_earlier_calls_stay_valid_and_the_engine_is_reused(gpu_engine_module):
+    """The drivers call run_model once per seed with the same population arrays (run_simulation.py:437-444): the
+    device-resident population is reused (no second engine), and the lazy histories of EARLIER calls -- the
+    reference hands out fresh arrays every time -- keep their own run's content while later runs overwrite the
+    device buffer: one run back on the device (seir_history_preserve), older ones from a host copy."""
+    m = _module()
+    m.clear_engine_cache()
+    c = util.Case("italy_seeded")
+    params = c.no_tracing_params()
+    outs, oracles = [], []
+    for seed in (1, 2, 3, 4):
+        outs.append(m.run_model(seed, *c.model_args(params)))
+        oracles.append(c.keyed_oracle("native", params, seed=seed)[0])
+    assert len(m._engine_cache) == 1 and m.last_engine.run_serial == 4
+    for out, tup in zip(outs, oracles):   # every call's nine histories and sums, read AFTER all four runs
+        for k in range(9):
+            assert np.array_equal(np.asarray(out[k]), np.asarray(tup[k])), k
+            assert np.array_equal(out[k].sum(axis=1), np.asarray(tup[k]).sum(axis=1))
+        assert np.array_equal(out[7][-1], np.asarray(tup[7])[-1]) and np.array_equal(out[15], tup[15])
+    # a different population gets its own engine; the cache keeps the two most recent
+    c2 = util.Case("china_default")
+    m.run_model(5, *c2.model_args(c2.no_tracing_params()))
+    assert len(m._engine_cache) == 2
+    m.clear_engine_cache()

