@@ -26,23 +26,43 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     // the host resets the barrier counter to 0 before each launch
     stage_tables(cx, sm);
-    unsigned int epoch = 0;  // grid barriers passed so far
+    unsigned int epoch = 0, epoch_m = 0;  // grid barriers passed so far: this GPU's own, and the ones across the GPUs of a sharded run
     const int reps_per_sweep = gridDim.x / cx.blocks_per_rep;  // >= 1
     const int my_slot = blockIdx.x / cx.blocks_per_rep, my_part = blockIdx.x % cx.blocks_per_rep;
-    if (cx.n_shards > 1) {  // no GPU touches a peer's arrays before every peer has finished (re-)initialising them
-        ++epoch;
-        grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
+    // A sharded run starts REPLICATED: while the epidemic is small every GPU steps the whole population on its own (the
+    // runs are deterministic, so the GPUs stay identical without exchanging a byte or meeting at a barrier -- a sparse
+    // day costs what it costs on one GPU).  On the first day whose lists exceed shard_threshold entries all GPUs switch,
+    // for good, to sharded passes: each keeps the agents it owns, cross-shard hits go to the owner's memory over NVLink
+    // and the GPUs meet once per day.  No state moves at the switch: everybody holds everything up to that day.
+    bool sharded_now = cx.n_shards > 1 && cx.shard_threshold == 0u;
+    if (sharded_now) {  // no GPU touches a peer's arrays before every peer has finished (re-)initialising them
+        ++epoch_m;
+        grid_barrier_multi(cx, cx.barrier, epoch_m * gridDim.x, cx.epoch_base + epoch_m);
     }
     const bool defer_counters = cx.n_rep == 1;  // this CTA serves the one replica throughout: its run counters are added once, below
     if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
     int bank_staged = -1;  // the table set whose kept-contact table sits in shared memory
     for (int t = 1; t <= cx.T_loop; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
-        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep, bank_staged, defer_counters);
+        if (cx.n_shards > 1 && !sharded_now) {  // (the day's list lengths are the same on every GPU: so is the decision)
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint32_t *c0 = cx.list_cnt + t;
+                sm.base_new = __ldcg(c0) + __ldcg(c0 + (cx.T + 2)) + __ldcg(c0 + 2 * (cx.T + 2));
+            }
+            __syncthreads();
+            if (sm.base_new > cx.shard_threshold) {
+                sharded_now = true;
+                ++epoch_m;
+                grid_barrier_multi(cx, cx.barrier, epoch_m * gridDim.x, cx.epoch_base + epoch_m);
+            }
+            __syncthreads();
+        }
+        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep, bank_staged, defer_counters, sharded_now);
         if (t < cx.T_loop) {
-            if (cx.n_shards > 1) {
-                ++epoch;
-                grid_barrier_multi(cx, cx.barrier, epoch * gridDim.x, cx.epoch_base + epoch);
+            if (sharded_now) {
+                ++epoch_m;
+                grid_barrier_multi(cx, cx.barrier, epoch_m * gridDim.x, cx.epoch_base + epoch_m);
                 continue;  // (tracing is not available in sharded runs)
             }
             grid_barrier(cx.barrier, ++epoch * gridDim.x);
@@ -167,7 +187,8 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
     const int64_t lo = init_off[rep], hi = init_off[rep + 1];
     for (int64_t k = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = init_ids[k];
-        if (cx.n_shards > 1 && (a < cx.shard_lo[cx.my_shard] || a >= cx.shard_lo[cx.my_shard + 1])) continue;  // another GPU's agent
+        const bool own = cx.n_shards <= 1 || (a >= cx.shard_lo[cx.my_shard] && a < cx.shard_lo[cx.my_shard + 1]);
+        if (!own && cx.shard_threshold == 0u) continue;  // another GPU's agent (a run that starts replicated steps it here too)
         const uint64_t seed = cx.seeds[rep];
         AgentRec r;
         r.clear();
@@ -181,7 +202,7 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
         cx.winner[(size_t)rep * cx.n_pad + a] = 1ull;  // day 0, never susceptible again
         atomicOr(cx.inbox + (size_t)rep * (cx.n_pad / 16) + (a >> 4), inbox_infected_bit((int)(a & 15)));
         cx.list_old[((size_t)rep * 2 + 1) * cx.n_pad + atomicAdd(cx.list_cnt + (size_t)rep * 3 * (cx.T + 2) + 1, 1u)] = (uint32_t)a;
-        atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat() & 127), 1u);
+        if (own) atomicAdd(cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges + TAL_NEW_E * kAges + (r.stat() & 127), 1u);
     }
 }
 
@@ -369,6 +390,7 @@ __global__ void seir_cohort_kernel(DevCtx cx, int rep, unsigned long long *out)
     const AgentRec *rec = cx.rec + (size_t)rep * cx.n_pad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cx.n; i += (int64_t)gridDim.x * blockDim.x) {
         if (!(inbox[i >> 4] & inbox_infected_bit((int)(i & 15)))) continue;
+        if (cx.n_shards > 1 && (i < cx.shard_lo[cx.my_shard] || i >= cx.shard_lo[cx.my_shard + 1])) continue;  // (its owner counts it)
         const AgentRec r = load_rec(rec + i);
         const int d = r.t_exposed(), age = r.stat() & 127, comp = r.state() & 7;
         if (d >= cx.T) continue;
@@ -479,10 +501,12 @@ struct seir_handle {
     DevBuf<unsigned int> barrier;
     // sharded run: one population across the GPUs of a box
     int n_shards = 0, my_shard = 0;
+    uint32_t shard_threshold = 131072;   // list entries of a day from which a sharded run leaves its replicated phase
     int64_t shard_lo[kMaxShards + 1] = {0};
     void *peer_ptr[kMaxShards][5] = {{nullptr}};   // opened IPC mappings: winner, inbox, list_new, list_cnt, flags
     DevBuf<unsigned int> flags;
     unsigned int run_count = 0;
+    unsigned int epoch_base = 0, epoch_next = 0;   // day-barrier epochs of the sharded runs: a running counter (monotone whatever T does)
     std::vector<uint8_t> age8;         // ages, for the per-shard group sizes
     std::vector<int64_t> shard_group_sizes;
     // contact tracing (allocated when the run can switch tracing on)
@@ -670,7 +694,7 @@ static void fill_ctx(seir_handle *h)
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
     c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
     { const char *dp = getenv("SEIR_DEBUG_PASS"); c.dbg_pass = dp ? atoi(dp) : -1; }
-    c.n_shards = h->n_shards; c.my_shard = h->my_shard;
+    c.n_shards = h->n_shards; c.my_shard = h->my_shard; c.shard_threshold = h->shard_threshold;
     for (int g = 0; g <= kMaxShards; ++g) c.shard_lo[g] = (uint32_t)h->shard_lo[g < h->n_shards ? g : (h->n_shards > 0 ? h->n_shards : 0)];
     for (int g = 0; g < kMaxShards; ++g) {
         const bool mine = g == h->my_shard || h->n_shards <= 1 || g >= h->n_shards;
@@ -680,7 +704,7 @@ static void fill_ctx(seir_handle *h)
         c.peer_list_cnt[g] = mine ? h->list_cnt.p : (uint32_t *)h->peer_ptr[g][3];
         c.peer_flags[g] = mine ? h->flags.p : (unsigned int *)h->peer_ptr[g][4];
     }
-    c.epoch_base = h->run_count * (unsigned int)(p.T + 2);
+    c.epoch_base = h->epoch_base;
     const bool tr = tracing_can_start(p) && h->trace_alloc;
     c.trace_from = tr ? p.t_tracing_start : 0;
     c.p_trace_hh = p.p_trace_household; c.p_trace_out = p.p_trace_outside;
@@ -913,6 +937,15 @@ int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_ha
     return 0;
 }
 
+int seir_shard_set_threshold(seir_handle *h, int64_t entries)
+{
+    if (!h) return fail("handle is NULL");
+    if (entries < 0 || entries > 0xFFFFFFFFll) return fail("seir_shard_set_threshold: entries must be in [0, 2^32)");
+    h->shard_threshold = (uint32_t)entries;
+    fill_ctx(h);
+    return 0;
+}
+
 int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables *tables)
 {
     if (!h) return fail("handle is NULL");
@@ -973,7 +1006,12 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
         if (q.t_stayhome >= 1 && q.t_stayhome < q.T && q.t_stayhome < t_home_min) t_home_min = q.t_stayhome;
         if (q.trace_from && (!trace_min || q.trace_from < trace_min)) trace_min = q.trace_from;
     }
-    if (h->n_shards > 1) ++h->run_count;  // every rank runs the same sequence of seir_run calls: the barrier epochs stay in step
+    if (h->n_shards > 1) {  // every rank runs the same sequence of seir_run calls: the barrier epochs stay in step
+        ++h->run_count;
+        h->epoch_base = h->epoch_next;
+        h->epoch_next += (unsigned int)(h->prm.T + 2);
+        CK(cudaMemsetAsync(h->flags.p + kMaxShards + 1, 0, sizeof(unsigned int), h->stream));  // (the error word of an earlier time-out)
+    }
     // ---- per-run host inputs -> device
     // the run's small inputs (seeds, offsets, the ids of the initial cases as int32, the pick counts of the keyed
     // prologue, the overrides) are assembled in ONE pinned host buffer and copied from there: truly asynchronous

@@ -202,6 +202,8 @@ struct DevCtx {
     unsigned long long *ttotal;    // nodes ever appended to a frontier (grows monotonically: the BFS loop's stop test)
     // one population across the GPUs of a box (household-aligned shards, peer memory over NVLink)
     int n_shards, my_shard;        // n_shards <= 1: not sharded
+    uint32_t shard_threshold;      // a sharded run steps the WHOLE population on every GPU (replicated, no exchange, no
+                                   // cross-GPU barrier) until a day's lists exceed this many entries; 0: sharded from day 1
     uint32_t shard_lo[kMaxShards + 1];             // shard g owns agents [shard_lo[g], shard_lo[g+1])
     unsigned long long *peer_winner[kMaxShards];   // every GPU keeps full-size arrays in GLOBAL agent indexing;
     uint32_t *peer_inbox[kMaxShards];              // an agent's winner / inbox / list entries live on its owner
@@ -364,6 +366,8 @@ struct RepView {
     int rep;
     bool tracing;                           // contact_tracing is True today (:241-242)
     int T;                                  // the replica's horizon (seir_overrides.T)
+    bool sharded;                           // this pass exchanges with the peer GPUs (each steps the agents it owns)
+    bool replicated;                        // a sharded run before its switch: every GPU steps everybody, counts its own
     const double *p_ms, *p_sc, *p_cd;       // the replica's severity tables (its table set)
     const double *p_contact;                // -> p_infect_given_contact of the set (:146; read by the replay mode only)
 };
@@ -454,10 +458,11 @@ static __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, 
     const uint32_t i = sm.slot_agent[slot];
     const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
     if (age_c == 127) age_c = __ldg(cx.stat + c) & 127;  // (independent of the atomic below: one round trip)
-    const int g = cx.n_shards > 1 ? owner_of(cx, c) : 0;
-    const bool remote = cx.n_shards > 1 && g != cx.my_shard;
+    const bool sh = v.sharded;
+    const int g = sh ? owner_of(cx, c) : 0;
+    const bool remote = sh && g != cx.my_shard;
     // (sharded: every atomic on an infectee is system-scope -- it is performed at the owner's L2 over NVLink)
-    const unsigned long long old = cx.n_shards > 1 ? atomicMax_system(cx.peer_winner[g] + c, key) : atomicMax(v.winner + c, key);
+    const unsigned long long old = sh ? atomicMax_system(cx.peer_winner[g] + c, key) : atomicMax(v.winner + c, key);
     const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
     uint32_t bits = 0;
     if (wday(old) != t) {  // first hit of c today: announce it, queue it for tomorrow
@@ -474,7 +479,7 @@ static __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, 
     }
     if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
     if (bits) {
-        if (cx.n_shards > 1) atomicOr_system(cx.peer_inbox[g] + (c >> 4), bits);
+        if (sh) atomicOr_system(cx.peer_inbox[g] + (c >> 4), bits);
         else atomicOr(v.inbox + (c >> 4), bits);
     }
     atomicAdd(&sm.hit_n[slot], ord >= 16u ? 0x10001u : 1u);  // ord >= 16: community (:386-388)
@@ -536,7 +541,7 @@ static __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &
     if (glen == 0) return;
     const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
     if (!SEIR_CHECK((int64_t)c < cx.n && sd_index(b, (uint64_t)glen) < (uint64_t)glen, cx, v.rep)) return;
-    const unsigned long long w = __ldcg((cx.n_shards > 1 ? cx.peer_winner[owner_of(cx, c)] : v.winner) + c);
+    const unsigned long long w = __ldcg((v.sharded ? cx.peer_winner[owner_of(cx, c)] : v.winner) + c);
     if ((w == 0ull || wday(w) == t) && !at_home(v, c))  // :375
         push_hit(cx, sm, c, (slot << 16) | ord, a, t);
 }
@@ -598,7 +603,9 @@ static __device__ __forceinline__ void push_draw(const DevCtx &cx, PassSmem &sm,
 #endif
 }
 
-static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm, uint32_t i, int t, AgentRec &r)
+// (tw: 1, or 0 for an agent another GPU owns while a sharded run is still replicated -- it is stepped here too, but
+// counted by its owner only)
+static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSmem &sm, uint32_t i, int t, AgentRec &r, uint32_t tw)
 {
     const RepView &v = sm.v;
     // infected on day t-1 by the winner of that day's hits (:347-356)
@@ -621,13 +628,13 @@ static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSm
     if (ib & inbox_q_bit((int)(i & 15))) {
         r.set_state(r.state() | ST_Q);
         r.set_t_q_on((uint16_t)tx);
-        atomicAdd(&sm.tally[TAL_NEW_QE * kAges + (stt & 127)], 1u);
+        atomicAdd(&sm.tally[TAL_NEW_QE * kAges + (stt & 127)], tw);
     }
     if (w & W_TRACED) {  // a tracer reached the agent on the day it was infected (:83-87): Documented, Q (inbox bit), traced
         r.set_state(r.state() | ST_DOC);
         r.set_t_documented((uint16_t)tx);
     }
-    atomicAdd(&sm.tally[TAL_NEW_E * kAges + (stt & 127)], 1u);
+    atomicAdd(&sm.tally[TAL_NEW_E * kAges + (stt & 127)], tw);
 }
 
 // the progression events of the agent's own day (:256-272, :291-311, :312-321)
@@ -725,7 +732,7 @@ static __device__ __noinline__ int next_wake_day(const DevCtx &cx, uint64_t seed
 // (DAY_KEEP_Q carries the wake day's offset: DAY_KEEP_Q | (wake - t - 1) << 2)
 enum { DAY_DROP = 0, DAY_KEEP = 1, DAY_KEEP_Q = 3 };
 static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i, AgentRec &r,
-                                         bool dirty, int t)
+                                         bool dirty, int t, uint32_t tw)
 {
     const RepView &v = sm.v;
     const uint16_t stt = r.stat();
@@ -753,7 +760,7 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
         ncomp = C_R;
         nq = false;
         transmit = false;
-        atomicAdd(&sm.tally[TAL_NEW_R * kAges + age], 1u);
+        atomicAdd(&sm.tally[TAL_NEW_R * kAges + age], tw);
     } else {
         const bool ev = (Ep && due(t, r.t_exposed(), r.tt_activation())) || (Mp && due(t, t_inf, r.tt_severe())) ||
                         (Sevp && due(t, t_severe_of(r), r.tt_critical()));
@@ -771,9 +778,9 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
         } else if (Cp && due(t, t_critical_of(r), r.tt_death())) {  // :323-327
             ncomp = C_D;
             nq = false;
-            atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], 1u);
+            atomicAdd(&sm.tally[TAL_NEW_D * kAges + age], tw);
         }
-        if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], 1u);
+        if (ndoc && !Dp) atomicAdd(&sm.tally[TAL_NEW_DOC * kAges + age], tw);
         if (TR && root && v.tracing) {
             atomicOr(cx.rootbits + (size_t)v.rep * (cx.n_pad / 32) + (i >> 5), 1u << (i & 31));
             atomicOr(cx.rootsum + (size_t)v.rep * (cx.n_pad / 1024) + (i >> 10), 1u << ((i >> 5) & 31));
@@ -789,10 +796,10 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
     // the day's changes of the head counts (every tally row is a change: nobody recounts the agents that were not visited)
     const bool active = ncomp <= C_CRIT;  // (ncomp >= C_E always)
     if (ncomp != comp) {
-        atomicAdd(&sm.tally[(TAL_D_E + comp - C_E) * kAges + age], 0xFFFFFFFFu);
-        if (active) atomicAdd(&sm.tally[(TAL_D_E + ncomp - C_E) * kAges + age], 1u);
+        atomicAdd(&sm.tally[(TAL_D_E + comp - C_E) * kAges + age], 0u - tw);
+        if (active) atomicAdd(&sm.tally[(TAL_D_E + ncomp - C_E) * kAges + age], tw);
     }
-    if ((nq && active) != Qp) atomicAdd(&sm.tally[TAL_D_Q * kAges + age], Qp ? 0xFFFFFFFFu : 1u);
+    if ((nq && active) != Qp) atomicAdd(&sm.tally[TAL_D_Q * kAges + age], Qp ? 0u - tw : tw);
     // the agent's own record is final for today except for the infector counters (stage W)
     const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
     if (nst != st) {
@@ -842,13 +849,14 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
 
 // ---- stage A: one list entry -----------------------------------------------------------------------------
 static __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &sm, uint32_t slot, uint32_t i,
-                                             bool is_new, int t, bool finalize)
+                                             bool is_new, int t, bool finalize, bool own)
 {
     const RepView &v = sm.v;
     AgentRec r;
     bool dirty = false;
+    const uint32_t tw = own ? 1u : 0u;
     if (is_new) {
-        build_new_record(cx, sm, i, t, r);
+        build_new_record(cx, sm, i, t, r, tw);
         dirty = true;
     } else {
         r = load_rec(v.rec + i);
@@ -858,12 +866,12 @@ static __device__ __forceinline__ int stage_a_entry(const DevCtx &cx, PassSmem &
     const int age = stt & 127;
     const int comp = r.state() & 7;
     sm.slot_agent[slot] = i;
-    sm.slot_info[slot] = (uint16_t)(age | (comp == C_E ? 128 : 0) | (((stt >> 9) & 7) << 8));
+    sm.slot_info[slot] = (uint16_t)(age | (comp == C_E ? 128 : 0) | (((stt >> 9) & 7) << 8) | (own ? 0 : 0x8000));
     if (finalize) {  // pass T: nothing moves (only the agents infected on the last day are listed: their records)
         if (dirty) store_rec(v.rec + i, r);
         return DAY_DROP;
     }
-    return agent_day(cx, sm, slot, i, r, dirty, t);
+    return agent_day(cx, sm, slot, i, r, dirty, t, tw);
 }
 
 // Survivors: the ones that may transmit tomorrow re-append themselves to tomorrow's list (one shared-memory atomic
@@ -979,7 +987,7 @@ static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSme
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
 #endif
 static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep,
-                                int &bank_staged, bool defer_counters = false)
+                                int &bank_staged, bool defer_counters = false, bool sharded_now = false)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
@@ -1055,6 +1063,8 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             sm.v.phase = (rp.t_lockdown >= 1 && t >= rp.t_lockdown) ? 1 : 0;  // :234-240
             sm.v.rep = rep;
             sm.v.tracing = rp.trace_from >= 1 && t >= rp.trace_from;          // :241-242
+            sm.v.sharded = sharded_now;
+            sm.v.replicated = cx.n_shards > 1 && !sharded_now;
         }
 
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
@@ -1124,6 +1134,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 const uint32_t slot = (k - g_lo) * 32u + lane;
                 int keep = DAY_DROP;
                 uint32_t i = 0;
+                bool own = true;
 #if SEIR_PREFETCH
                 // the group one of this CTA's warps takes kWarps grabs from now: ask the L2 for its agents' records and
                 // household words now (the loads of a group are dependent DRAM round trips: entry -> record -> household)
@@ -1152,13 +1163,16 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                     }
 #endif
                     SEIR_FINE(1);
-                    if (SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_pk) <= cx.n, cx, rep))
-                        keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize);
+                    // (a sharded run after its switch: the lists still hold what the replicated days left; each GPU keeps its own agents)
+                    own = cx.n_shards <= 1 || (i >= cx.shard_lo[cx.my_shard] && i < cx.shard_lo[cx.my_shard + 1]);
+                    if ((own || !sharded_now) && SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_pk) <= cx.n, cx, rep))
+                        keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize, own);
                     SEIR_FINE(8);
                 }
                 append_survivors(sm, keep, i);
                 SEIR_FINE(9);
-                const unsigned hm = __ballot_sync(0xFFFFFFFFu, has), nm = __ballot_sync(0xFFFFFFFFu, has && is_new);
+                // (run counters: every agent is counted by its owner -- a replicated day steps the others' agents too)
+                const unsigned hm = __ballot_sync(0xFFFFFFFFu, has && own), nm = __ballot_sync(0xFFFFFFFFu, has && own && is_new);
                 if (lane == 0 && hm) {
                     atomicAdd(&sm.cnt[0], (uint32_t)__popc(hm));
                     if (nm) atomicAdd(&sm.cnt[1], (uint32_t)__popc(nm));
@@ -1212,7 +1226,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                             u.x = by | (as << 16);
                             u.y = (u.y & 0xFFFF0000u) | inc_sat16((uint16_t)(u.y & 0xFFFFu), hits_out);
                             __stcg(q, u);
-                            atomicAdd(&sm.cnt[2], hits);
+                            if (!(sm.slot_info[sl] & 0x8000u)) atomicAdd(&sm.cnt[2], hits);
                         }
                     }
                 }

@@ -30,7 +30,8 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_last_error", "seir_device_count", "seir_build_info", "seir_probe_draws",
            "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
            "seir_get_stage_times", "seir_get_cohorts", "seir_shard_export", "seir_shard_attach", "seir_get_visits",
-           "seir_history_preserve", "seir_run_ex", "seir_set_table_bank", "seir_get_prologue")
+           "seir_history_preserve", "seir_run_ex", "seir_set_table_bank", "seir_get_prologue", "seir_abi_sizes",
+           "seir_shard_set_threshold")
 
 
 class SeirParams(C.Structure):
@@ -97,6 +98,7 @@ def load_library():
     lib.seir_history_preserve.argtypes = [H]
     lib.seir_shard_export.argtypes = [H, C.c_void_p]
     lib.seir_shard_attach.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.seir_shard_set_threshold.argtypes = [H, C.c_int64]
     lib.seir_get_day_times.argtypes = [H, C.c_void_p]
     lib.seir_get_stage_times.argtypes = [H, C.c_void_p]
     lib.seir_destroy.argtypes = [H]
@@ -231,13 +233,16 @@ class Engine:
         _check(self.lib.seir_shard_export(self._h, _ptr(out)))
         return out
 
-    def shard_attach(self, rank, world, all_handles, bounds):
-        """all_handles uint8[world, 320] (rank-major), bounds int64[world + 1] (household starts)."""
+    def shard_attach(self, rank, world, all_handles, bounds, threshold=None):
+        """all_handles uint8[world, 320] (rank-major), bounds int64[world + 1] (household starts).  threshold: list
+        entries of a day up to which the run stays replicated (None: the library's default; 0: sharded from day 1)."""
         hd = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world, 5 * 64)
         bd = np.ascontiguousarray(bounds, dtype=np.int64)
         if bd.shape != (world + 1,):
             raise ValueError("bounds must have world + 1 entries")
         _check(self.lib.seir_shard_attach(self._h, int(rank), int(world), _ptr(hd), _ptr(bd)))
+        if threshold is not None:
+            _check(self.lib.seir_shard_set_threshold(self._h, int(threshold)))
         self.shard = (int(rank), int(world), bd.copy())
 
     def set_params(self, params=None, tables=None, mode=None, launch=None, tracing_enabled=None):

@@ -12,6 +12,11 @@ handles at set-up and the small results at the end.
 Every rank holds the full-size arrays in global agent indexing (C3: 11 GB per GPU) and steps the agents
 it owns; results are bit-identical to the single-GPU run because every draw is keyed on
 (agent, day, site) -- never on who executes it.
+
+A run starts REPLICATED: while the epidemic is small (a day's lists below `threshold` entries) every GPU steps
+the whole population on its own -- deterministic runs stay identical without exchanging a byte or meeting at a
+barrier, so a sparse day costs what it costs on one GPU -- and on the first longer day all GPUs switch, for good,
+to sharded passes.  Nothing moves at the switch: everybody holds everything up to that day.
 """
 import numpy as np
 
@@ -40,15 +45,17 @@ def shard_bounds(households, world):
     return np.asarray(bounds, dtype=np.int64)
 
 
-def attach(engine, households, dist):
-    """Exchange the IPC handles over an initialised torch.distributed group and attach the peers."""
+def attach(engine, households, dist, threshold=None):
+    """Exchange the IPC handles over an initialised torch.distributed group and attach the peers.  `threshold`: see
+    Engine.shard_attach (the run stays replicated -- every GPU steps everybody, no exchange -- while the day's lists
+    are shorter)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     bounds = shard_bounds(households, world)
     mine = engine.shard_export()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine.tobytes())
     handles = np.stack([np.frombuffer(b, dtype=np.uint8) for b in gathered])
-    engine.shard_attach(rank, world, handles, bounds)
+    engine.shard_attach(rank, world, handles, bounds, threshold=threshold)
     dist.barrier()
     return bounds
 

@@ -161,9 +161,14 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
  * Afterwards seir_run steps only the owned agents; a community contact whose target lives on another GPU is
  * resolved in that GPU's memory over NVLink (system-scope atomics), and the GPUs meet at a device-side
  * barrier once per day.  All ranks must call seir_run together, with the same seed and initial cases.
- * Outputs (tallies, vectors, history) cover the owned agents; tallies of the ranks add up. */
+ * Outputs (tallies, vectors, history) cover the owned agents; tallies of the ranks add up.
+ * A sharded run starts REPLICATED: while a day's lists hold at most `entries` agents (seir_shard_set_threshold, default
+ * 131072) every GPU steps the whole population on its own -- the runs are deterministic, so the GPUs stay identical
+ * without exchanging a byte, and a sparse day costs what it costs on one GPU -- and on the first longer day all GPUs
+ * switch for good to sharded passes.  0 = sharded from day 1.  All ranks must use the same value. */
 int seir_shard_export(seir_handle *h, uint8_t *handles_out);
 int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_handles, const int64_t *bounds);
+int seir_shard_set_threshold(seir_handle *h, int64_t entries);
 
 /* Replace the scalar parameters / tables (same population) before the next seir_run. */
 int seir_set_params(seir_handle *h, const seir_params *params, const seir_tables *tables);

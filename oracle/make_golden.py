@@ -140,11 +140,51 @@ def run_ensemble(n=20000, seeds=64, t_tracing_start=1000.0, name="ref_ensemble_i
     print("ensemble", name % n, curves[:, -1, :].mean(axis=0), "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
+def run_ensemble_large(n=20000, seeds=256, name="ref_ensemble256_italy_n%d.npz"):
+    """A larger reference ensemble on the SAME population and parameters as run_ensemble() (tracing never on), for
+    the tightened statistical tier: daily curves of 256 seeds, per-age attack counts at the end, the pooled
+    distribution of num_infected_by (the reference's per-infector offspring numbers).  Only statistics are stored;
+    the population is the one of ref_ensemble_italy_n20000.npz (checked here)."""
+    ns = ref_shim.driver_namespace(n, "Italy")
+    ref = ref_shim.load()
+    params = ns["params"]
+    params["initial_infected_fraction"] = 0.001
+    params["t_tracing_start"] = 1000.0
+    params["t_lockdown"] = 40.0
+    args = (ns["contact_matrix"], ns["p_mild_severe"], ns["p_severe_critical"], ns["p_critical_death"],
+            ns["mean_time_to_isolate_factor"], ns["lockdown_factor_age"], ns["p_infect_household"],
+            np.array(ns["fraction_stay_home"], dtype=np.float64))
+    ref.run_complete_simulation(1234, "Italy", *args, params, False)  # builds the population
+    age, households, diabetes, hypertension, age_groups = pickle.load(open("Italy_population_%d.pickle" % n, "rb"))
+    small = np.load(os.path.join(GOLDEN, "ref_ensemble_italy_n%d.npz" % n))
+    assert np.array_equal(small["age"], age) and np.array_equal(small["households"], households), "not the fixture's population"
+    T = int(params["T"])
+    curves = np.zeros((seeds, T, 9), dtype=np.int32)
+    attack_by_age = np.zeros((seeds, 101), dtype=np.int32)
+    offspring = np.zeros((seeds, 16), dtype=np.int64)   # histogram of num_infected_by over infected agents, last bin = 15+
+    r0 = np.zeros(seeds)
+    for s in range(seeds):
+        out = ref.run_model(10000 + s, households, age, age_groups, diabetes, hypertension, *args, params)
+        for k in range(9):
+            curves[s, :, k] = out[k].sum(axis=1)
+        te, nib = out[15], out[9]
+        attack_by_age[s] = np.bincount(age[te >= 0], minlength=101)
+        offspring[s] = np.bincount(np.minimum(nib[nib >= 0].astype(np.int64), 15), minlength=16)
+        m = (te > 0) & (te <= 20)
+        r0[s] = nib[m].mean() if m.any() else np.nan
+    path = os.path.join(GOLDEN, name % n)
+    np.savez_compressed(path, curves=curves, attack_by_age=attack_by_age, offspring=offspring, r0_early=r0,
+                        seeds=np.arange(10000, 10000 + seeds))
+    print("ensemble256", curves[:, -1, :].mean(axis=0), "%.0f kB" % (os.path.getsize(path) / 1e3))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     which = sys.argv[1:] or (list(CASES) + ["ensemble", "ensemble_tracing"])
     for name in which:
-        if name == "ensemble":
+        if name == "ensemble256":
+            run_ensemble_large()
+        elif name == "ensemble":
             run_ensemble()
         elif name == "ensemble_tracing":  # tracing from day 25 of 60, the drivers' p_trace_household = 1, p_trace_outside = 0.95
             run_ensemble(t_tracing_start=25.0, name="ref_ensemble_tracing_italy_n%d.npz")

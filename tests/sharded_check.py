@@ -33,8 +33,10 @@ def main():
             eng = engine.Engine(tables_mod.params_to_dict(params), c.households, c.age, c.age_groups, c.diabetes,
                                 c.hypertension, c.p_infect_household, c.tables(params), n_replicas=1, device=local,
                                 mode=mode)
-            bounds = sharding.attach(eng, c.households, dist)
+            # the first seed sharded from day 1, the second replicated until a day lists more than 40 agents
+            bounds = sharding.attach(eng, c.households, dist, threshold=0)
             for seed in (c.seed, c.seed + 7):
+                eng.lib.seir_shard_set_threshold(eng._h, 0 if seed == c.seed else 40)
                 home, init = tables_mod.prologue(seed, c.age_groups, c.n, c.fraction_stay_home,
                                                  params["initial_infected_fraction"])
                 eng.run([seed], [home], [init])

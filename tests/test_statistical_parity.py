@@ -99,3 +99,79 @@ def test_gpu_ensemble_matches_reference_ensemble(gpu_engine_module, which, mode)
         want = np.stack([np.asarray(tup[j]).sum(axis=1) for j in range(9)], axis=1)
         assert np.array_equal(got[k], want)
     eng.close()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# The tightened tier (round 2): 256 reference seeds against 256 keyed seeds on the same population, KS p > 0.01,
+# plus what the daily curves cannot show -- WHO gets infected (final attack counts per age decade) and HOW the
+# infections are distributed over the infectors (the offspring numbers num_infected_by, incl. the double counting of
+# same-day multiple hits).
+N_LARGE = 256
+KS_P_MIN_LARGE = 0.01
+
+
+def reference_ensemble_large():
+    c = util.Case(FIXTURES["no_tracing"])
+    fx = np.load(util.os.path.join(util.GOLDEN, "ref_ensemble256_italy_n20000.npz"))
+    return c, fx
+
+
+def assert_same_distribution_large(curves, attack_by_age, offspring, fx, n, label):
+    ref = fx["curves"].astype(np.int64)
+    stats = {
+        "final deaths": lambda c: c[:, -1, 7], "peak ICU": lambda c: c[:, :, 5].max(axis=1),
+        "final attack size": lambda c: n - c[:, -1, 0], "peak Mild": lambda c: c[:, :, 2].max(axis=1),
+        "final Documented": lambda c: c[:, -1, 3], "final Q": lambda c: c[:, -1, 8],
+        "day of peak Mild": lambda c: c[:, :, 2].argmax(axis=1), "infections by day 30": lambda c: n - c[:, 30, 0],
+    }
+    for name, f in stats.items():
+        p = st.ks_2samp(f(curves), f(ref)).pvalue
+        assert p > KS_P_MIN_LARGE, "%s: KS p=%.3g on %s (means %.1f vs %.1f)" % (label, p, name, f(curves).mean(), f(ref).mean())
+
+    def close(xa, xb, what):
+        se = np.sqrt(xa.var(ddof=1) / len(xa) + xb.var(ddof=1) / len(xb))
+        assert abs(xa.mean() - xb.mean()) <= CI_SIGMAS * se + 0.5, "%s: %s means %.2f vs %.2f (se %.3f)" % (label, what, xa.mean(), xb.mean(), se)
+    dec = np.minimum(np.arange(101) // 10, 9)
+    for d in range(10):   # final attack counts per age decade
+        close(attack_by_age[:, dec == d].sum(axis=1).astype(float), fx["attack_by_age"][:, dec == d].sum(axis=1).astype(float),
+              "attack count, ages %d-%d" % (10 * d, 10 * d + 9))
+    fa = offspring / offspring.sum(axis=1, keepdims=True)   # share of infected agents that infected k others, per seed
+    fb = fx["offspring"] / fx["offspring"].sum(axis=1, keepdims=True)
+    for k in range(8):
+        close(fa[:, k] * 1000, fb[:, k] * 1000, "per mille of infectors with %d offspring" % k)
+    mean_a = (offspring * np.arange(16)).sum(axis=1) / offspring.sum(axis=1)
+    mean_b = (fx["offspring"] * np.arange(16)).sum(axis=1) / fx["offspring"].sum(axis=1)
+    assert st.ks_2samp(mean_a, mean_b).pvalue > KS_P_MIN_LARGE, "%s: mean offspring number" % label
+
+
+def _summaries(tup, age):
+    te, nib = tup[15], tup[9]
+    return (np.stack([np.asarray(tup[j]).sum(axis=1) for j in range(9)], axis=1), np.bincount(age[te >= 0], minlength=101),
+            np.bincount(np.minimum(nib[nib >= 0].astype(np.int64), 15), minlength=16))
+
+
+def test_keyed_oracle_large_ensemble_matches_reference():
+    c, fx = reference_ensemble_large()
+    outs = [_summaries(c.keyed_oracle("native", c.params, seed=20000 + s)[0], c.age) for s in range(N_LARGE)]
+    assert_same_distribution_large(np.stack([o[0] for o in outs]), np.stack([o[1] for o in outs]),
+                                   np.stack([o[2] for o in outs]), fx, c.n, "oracle/native/256")
+
+
+@pytest.mark.gpu
+def test_gpu_large_ensemble_matches_reference(gpu_engine_module):
+    """256 seeds as four launches of 64 replicas, prologue picks made on the device (keyed permutation)."""
+    c, fx = reference_ensemble_large()
+    R = 64
+    eng = c.gpu_engine(gpu_engine_module, c.params, "native", n_replicas=R)
+    curves, attack, off = [], [], []
+    for b in range(N_LARGE // R):
+        seeds = [30000 + b * R + r for r in range(R)]
+        eng.run(seeds, keyed=(c.fraction_stay_home, c.params["initial_infected_fraction"]))
+        for r in range(R):
+            curves.append(eng.tallies(r).sum(axis=2))
+            te, nib = eng.agent_vector("time_exposed", replica=r), eng.agent_vector("num_infected_by", replica=r)
+            attack.append(np.bincount(c.age[te >= 0], minlength=101))
+            off.append(np.bincount(np.minimum(nib[nib >= 0].astype(np.int64), 15), minlength=16))
+    eng.close()
+    assert_same_distribution_large(np.stack(curves), np.stack(attack), np.stack(off), fx, c.n, "gpu/native/256")
+
