@@ -397,7 +397,8 @@ struct __align__(16) PassSmem {
     double nat_enlam[2 * kAges * 2];
     int32_t grp_off[kAges + 1];
     uint32_t cnt[4];
-    RepParams rp;                  // the replica's overrides, read once per CTA and pass
+    RepParams rp;                  // the replica's overrides, read once per CTA (and again only when the CTA changes replica)
+    int rp_rep;                    // the replica sm.rp belongs to (-1: none yet)
     uint32_t list_n[3];            // today's list lengths (new, transmitting, quarantined), read once per CTA
     uint32_t run_cnt[3];           // this CTA's share of the run counters (persistent kernel: flushed once, at the end)
     int dyn[3];                    // replica ensembles: the replica this CTA serves in the current pass, its part, the replica's CTAs
@@ -413,6 +414,7 @@ __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
     }
     for (int k = threadIdx.x; k <= kAges; k += kThreads) sm.grp_off[k] = cx.grp_off[k];
     // (nat_enlam belongs to the replica's table set: staged by the pass)
+    if (threadIdx.x == 0) sm.rp_rep = -1;
     __syncthreads();
 }
 
@@ -841,7 +843,12 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
     SEIR_FINE(7);
     if (!active) return DAY_DROP;
     if (!nq) return DAY_KEEP;
-    int wake = next_wake_day(cx, v.seed, i, r.w[0], r.w[1], r.w[2], ncomp, ndoc, t);
+    // An agent that turned quarantined TODAY sits in a warp of transmitting agents: it is looked at again tomorrow, among
+    // the parked agents due that day -- warps in which every lane works out its wake day (the scan of the documentation
+    // draws is the longest path of this function, and one lane taking it would hold its whole warp back).
+    // (Without documentation draws the wake day is a handful of compares: computed at once.)
+    int wake = t + 1;
+    if (Qp || !(ncomp == C_MILD && !ndoc && cx.p_doc > 0.0)) wake = next_wake_day(cx, v.seed, i, r.w[0], r.w[1], r.w[2], ncomp, ndoc, t);
     if (wake >= v.T) return DAY_DROP;  // nothing more can happen to it within the horizon: its record is final
     if (wake > t + kParkHorizon) wake = t + kParkHorizon;  // (the bucket offset travels in 5 bits: look again then)
     return DAY_KEEP_Q | ((wake - t - 1) << 2);
@@ -922,15 +929,17 @@ static __device__ __forceinline__ uint32_t reserve_survivors(PassSmem &sm)
     }
     return base;
 }
+// (the same for the round's parks: threads 128 .. 142, one wake day each)
+static __device__ __forceinline__ uint32_t reserve_parks(PassSmem &sm, int t) { return sm.n_pk ? park_reserve(sm, t) : 0u; }
 
 // The round's parks go to their day buckets.  Threads 128 .. 142 own one wake-day offset each and reserve the room
 // (one atomic per CTA and day); afterwards every staged agent is stored at its rank behind that base.
-static __device__ __forceinline__ void park_reserve(PassSmem &sm, int t)
+static __device__ __forceinline__ uint32_t park_reserve(PassSmem &sm, int t)
 {
     const int o = (int)threadIdx.x - 128;
-    if (o < 0 || o >= kParkHorizon) return;
+    if (o < 0 || o >= kParkHorizon) return 0u;
     const uint32_t cnt = sm.pk_n[o];
-    if (cnt) sm.pk_base[o] = atomicAdd(sm.v.pk_cnt + (t + 1 + o), cnt);
+    return cnt ? atomicAdd(sm.v.pk_cnt + (t + 1 + o), cnt) : 0u;
 }
 static __device__ __forceinline__ void park_store(const DevCtx &cx, PassSmem &sm, int t, uint32_t n_pk)
 {
@@ -945,7 +954,7 @@ static __device__ __forceinline__ void park_store(const DevCtx &cx, PassSmem &sm
 // the staged survivors, parks and (flush_new) new infectees to tomorrow's lists / the day buckets (the whole CTA;
 // ends with the staging counters reset)
 static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSmem &sm, int t, bool flush_new, uint32_t reserved,
-                                                       bool new_reserved = false)
+                                                       uint32_t park_reserved, bool new_reserved = false)
 {
     const RepView &v = sm.v;
     const uint32_t so = sm.n_old < (uint32_t)kOutOld ? sm.n_old : (uint32_t)kOutOld;
@@ -955,7 +964,7 @@ static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSme
     if (so | sp | sn) {
         if (threadIdx.x == 0 && so) { sm.base_old = reserved; sm.n_old = 0; }
         if (threadIdx.x == 64 && sn) { sm.base_new = new_reserved ? reserved : atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
-        if (sp) park_reserve(sm, t);
+        if (sp && threadIdx.x >= 128 && threadIdx.x < 128 + kParkHorizon) sm.pk_base[threadIdx.x - 128] = park_reserved;
         __syncthreads();
 #ifdef SEIR_CHECKS
         if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sn && sm.base_new + sn > v.n_pad_m1 + 1u)))
@@ -1041,8 +1050,11 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_pk = cnt_new + (cx.T + 2);
         const RepView &v = sm.v;
         if (tid == 0) {
-            const RepParams rp = cx.rp[rep];  // (one request per CTA: the same line asked for by every warp queues up at its L2 slice)
-            sm.rp = rp;
+            if (sm.rp_rep != rep) {  // (one request per CTA and replica: the overrides do not change during a launch)
+                sm.rp = cx.rp[rep];
+                sm.rp_rep = rep;
+            }
+            const RepParams rp = sm.rp;
             sm.v.T = rp.T;
             const double *bank = cx.bank + (size_t)rp.bank * kBankStride;
             sm.v.p_ms = bank + kBankPms; sm.v.p_sc = bank + kBankPsc; sm.v.p_cd = bank + kBankPcd;
@@ -1113,6 +1125,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         SEIR_STAMP(0);
 
         uint32_t reserved = 0;  // thread 0: offset of the round's staged survivors in tomorrow's list
+        uint32_t park_reserved = 0;  // threads 128 .. 142: offset of the round's parks in their day bucket
         for (uint32_t round = 0; round < rounds; ++round) {
             // ================= stage A: the round's groups, grabbed by the warps =================
             const uint32_t g_lo = round * kGroupsPerRound;
@@ -1182,6 +1195,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             SEIR_STAMP(1);
             SEIR_STAMP(2);
             reserved = reserve_survivors(sm);  // (nobody stages a survivor after this point of the round)
+            park_reserved = reserve_parks(sm, t);
             // ================= stage D: draw items =================
             if (sm.n_draw) {
                 const uint32_t nd = sm.n_draw < (uint32_t)kDrawCap ? sm.n_draw : (uint32_t)kDrawCap;
@@ -1234,7 +1248,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             __syncthreads();
             // more rounds follow: empty the staging buffers
             if (round + 1u < rounds) {
-                flush_survivors(cx, sm, t, sm.n_new > (uint32_t)(kOutNew - kHitCap), reserved);
+                flush_survivors(cx, sm, t, sm.n_new > (uint32_t)(kOutNew - kHitCap), reserved, park_reserved);
                 if (tid == 0) { sm.n_hit = 0; sm.n_con = 0; sm.n_draw = 0; sm.next_group = 0; }
                 __syncthreads();
             }
@@ -1242,7 +1256,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             stamped = true;
         }
         stamped = false;
-        flush_survivors(cx, sm, t, true, reserved, rounds != 0u);
+        flush_survivors(cx, sm, t, true, reserved, park_reserved, rounds != 0u);
         // ---- flush the tallies: rows [0,kTalLagRows) belong to day t-1, the rest to day t
         uint32_t *tal = cx.tally + (size_t)rep * cx.T * TAL_ROWS * kAges;
         for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) {

@@ -29,11 +29,13 @@ def batches(items, batch):
 
 
 def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fraction, want_vectors=(),
-              want_cohorts=False, fast_prologue=False, host_threads=0):
+              want_cohorts=False, fast_prologue=False, host_threads=0, keyed_prologue=False):
     """Run `seeds` on `engine` (an engine.Engine with R replica slots) in batches of R.
 
     Per seed the reference's own prologue picks are used (`tables.prologue`, seir_individual.py:176-187).
     `fast_prologue` swaps in `tables.prologue_fast` (same distributions, O(picks) instead of two O(n) permutations).
+    `keyed_prologue` lets the DEVICE make the picks (keyed permutation, include/seir_draws.h sd_perm; the host
+    restatement is tables.prologue_keyed): nothing but 101 doubles per run crosses PCIe, no host work per seed.
     `host_threads` > 0 draws the prologues of the NEXT batch on that many host threads while the device runs the
     current one (NumPy's generators and ctypes' foreign calls release the GIL), so a long ensemble is bound by
     the device, not by the host prologue (0.3 s per seed at n = 10 M for the reference's stream).
@@ -52,10 +54,12 @@ def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fr
     padded = [c + [c[-1]] * (R - len(c)) for c in chunks]
 
     def draw(batch):
+        if keyed_prologue:
+            return None
         return [pick(s, age_groups, n, fraction_stay_home, initial_infected_fraction) for s in batch]
 
     pool = None
-    if host_threads > 0 and len(chunks) > 0:
+    if host_threads > 0 and len(chunks) > 0 and not keyed_prologue:
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=host_threads)
 
@@ -72,7 +76,10 @@ def run_seeds(engine, seeds, age_groups, fraction_stay_home, initial_infected_fr
                     pending = draw_async(padded[b + 1])  # overlaps with the device run below
             else:
                 pro = draw(padded[b])
-            engine.run(padded[b], [p[0] for p in pro], [p[1] for p in pro])
+            if keyed_prologue:
+                engine.run(padded[b], keyed=(fraction_stay_home, initial_infected_fraction))
+            else:
+                engine.run(padded[b], [p[0] for p in pro], [p[1] for p in pro])
             for r in range(len(chunk)):
                 tallies[done + r] = engine.tallies(r)
                 counters.append(engine.counters(r))

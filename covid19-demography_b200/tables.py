@@ -69,8 +69,10 @@ def alias_table(weights):
 
 
 def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_factor, p_mild_severe,
-                 p_severe_critical, p_critical_death, with_replay=True):
-    """Returns a dict of C-contiguous float64 arrays keyed like the fields of `seir_tables`."""
+                 p_severe_critical, p_critical_death, with_replay=True, alias_from=None):
+    """Returns a dict of C-contiguous float64 arrays keyed like the fields of `seir_tables`.
+    alias_from: tables of an earlier call with the SAME contact matrix and group sizes -- the alias tables (the only
+    part that costs milliseconds: a Python loop per row) do not depend on anything else, a sweep builds them once."""
     p = params
     C_pre = np.ascontiguousarray(contact_matrix, dtype=np.float64)
     if C_pre.shape != (N_AGES, N_AGES):
@@ -85,12 +87,15 @@ def build_tables(contact_matrix, group_sizes, params, mean_time_to_isolate_facto
         rowsum = np.where(nonempty[None, :], C, 0.0).sum(axis=1)
         for w, weight in enumerate((1.0, p["asymptomatic_transmissibility"])):
             nat_enlam[ph, :, w] = np.exp(-(p["p_infect_given_contact"] * weight) * rowsum)
-    Cz = np.where(nonempty[None, :], C_pre, 0.0)
-    alias_prob = np.ones((N_AGES, N_AGES), dtype=np.float64)
-    alias_idx = np.tile(np.arange(N_AGES, dtype=np.int32), (N_AGES, 1))
-    for a in range(N_AGES):
-        if Cz[a].sum() > 0:
-            alias_prob[a], alias_idx[a] = alias_table(Cz[a])
+    if alias_from is not None:
+        alias_prob, alias_idx = alias_from["nat_alias_prob"], alias_from["nat_alias_idx"]
+    else:
+        Cz = np.where(nonempty[None, :], C_pre, 0.0)
+        alias_prob = np.ones((N_AGES, N_AGES), dtype=np.float64)
+        alias_idx = np.tile(np.arange(N_AGES, dtype=np.int32), (N_AGES, 1))
+        for a in range(N_AGES):
+            if Cz[a].sum() > 0:
+                alias_prob[a], alias_idx[a] = alias_table(Cz[a])
     out = {
         "p_mild_severe": np.ascontiguousarray(p_mild_severe, dtype=np.float64).reshape(N_AGES, 2, 2),
         "p_severe_critical": np.ascontiguousarray(p_severe_critical, dtype=np.float64).reshape(N_AGES, 2, 2),
