@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
             }
             __syncthreads();
         }
-        Pass<TR>::day_pass(cx, sm, t, my_slot, my_part, reps_per_sweep, bank_staged, defer_counters, sharded_now);
+        Pass<TR>::template day_pass<true>(cx, sm, t, my_slot, my_part, reps_per_sweep, bank_staged, defer_counters, sharded_now);
         if (t < cx.T_loop) {
             if (sharded_now) {
                 ++epoch_m;
@@ -92,6 +92,100 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[cx.T + 1] = global_timer_ns();
 }
 
+// The day loop of ONE replica on one GPU without contact tracing (C1, C2, C3 on one GPU: the bench's default) is run by
+// two kernels in turn.  seir_sparse_kernel takes the days whose lists fit one entry per warp (warp-cooperative passes,
+// sparse_entry): one CTA per SM, so a thread may use 128 registers -- the pass is ONE warp's dependent chain, and a spill
+// is a round trip to L2 behind the barrier's invalidated L1 -- a barrier over 148 CTAs, a code footprint of a few KB.
+// seir_dense_solo_kernel takes the others (staged passes, two CTAs per SM).  Each leaves the first day it does not take
+// in ctl[k + 1] and the host has queued the next launch already: no host round trip at a hand-over.
+__global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_constant__ DevCtx cx, int k)
+{
+    PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
+    int t = __ldcg(cx.ctl + k) + 1;
+    if (t > cx.T_loop) {  // nothing left to do: hand the word on
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.ctl[k + 1] = t - 1;
+        return;
+    }
+    stage_tables(cx, sm);
+    unsigned int *bar = cx.barrier + (size_t)(1 + k) * kBarStride;  // this launch's barrier word (zeroed by the host with the others)
+    unsigned int epoch = 0;
+    if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 4) sm.cnt[threadIdx.x] = 0;
+    int bank_staged = -1;
+    for (; t <= cx.T_loop; ++t) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();  // (a dense day: the other kernel stamps it again)
+        if (threadIdx.x == 0) {
+            Pass<false>::fill_view(cx, sm, t, 0, false);
+            Pass<false>::load_list_lengths(cx, sm, t, 0);
+        }
+        __syncthreads();
+        const int T = sm.rp.T;
+        const bool finalize = t >= T;
+        const uint32_t n_new = sm.list_n[0], n_old = finalize ? 0u : sm.list_n[1], n_pk = finalize ? 0u : sm.list_n[2];
+        if (sm.list_n[0] + sm.list_n[1] + sm.list_n[2] > cx.sparse_cap) break;  // (grid-uniform: a dense day)
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.stage_ns[(size_t)t * 8 + 0] = global_timer_ns();
+        if (bank_staged != sm.rp.bank) {
+            const double *src = cx.bank + (size_t)sm.rp.bank * kBankStride + kBankNatEn;
+            for (int q = threadIdx.x; q < 4 * kAges; q += kThreads) sm.nat_enlam[q] = src[q];
+            bank_staged = sm.rp.bank;
+            __syncthreads();
+        }
+        Pass<false>::sparse_rounds(cx, sm, t, n_new, n_old, n_pk, cx.list_new + (size_t)(t & 1) * cx.n_pad, cx.list_old + (size_t)(t & 1) * cx.n_pad,
+                                   cx.pk_pool + (size_t)(t & (kParkRing - 1)) * cx.n_pad, (int)blockIdx.x, (int)gridDim.x, finalize, false);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long now = global_timer_ns();
+            for (int q = 1; q < 8; ++q) cx.stage_ns[(size_t)t * 8 + q] = now;
+        }
+        // the grid barrier (flat form of grid_barrier); this CTA's run counters are counted between its arrival and its poll
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (t < cx.T_loop) {
+                ++epoch;
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
+            }
+            Pass<false>::flush_pass_counters(cx, sm, 0, true);
+            if (t < cx.T_loop) {
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+                } while (seen < epoch * gridDim.x);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3 && sm.run_cnt[threadIdx.x]) atomicAdd(&cx.counters[1 + threadIdx.x], (unsigned long long)sm.run_cnt[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cx.ctl[k + 1] = t - 1;
+        if (t > cx.T_loop) cx.day_ns[cx.T + 1] = global_timer_ns();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, kMinBlocks) seir_dense_solo_kernel(const __grid_constant__ DevCtx cx, int k, uint32_t yield_below)
+{
+    PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
+    int t = __ldcg(cx.ctl + k) + 1;
+    if (t > cx.T_loop) {  // nothing left to do: hand the word on
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.ctl[k + 1] = t - 1;
+        return;
+    }
+    stage_tables(cx, sm);
+    unsigned int *bar = cx.barrier + (size_t)k * kBarStride;  // (grid_barrier counts in the word one stride further)
+    unsigned int epoch = 0;
+    if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
+    int bank_staged = -1;
+    for (; t <= cx.T_loop; ++t) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
+        if (Pass<false>::day_pass<false, true>(cx, sm, t, 0, (int)blockIdx.x, 1, bank_staged, true, false, yield_below)) break;
+        if (t < cx.T_loop) grid_barrier(bar, ++epoch * gridDim.x);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && sm.run_cnt[threadIdx.x]) atomicAdd(&cx.counters[1 + threadIdx.x], (unsigned long long)sm.run_cnt[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cx.ctl[k + 1] = t - 1;
+        if (t > cx.T_loop) cx.day_ns[cx.T + 1] = global_timer_ns();
+    }
+}
+
 template <bool TR>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __grid_constant__ DevCtx cx, int t)
 {
@@ -99,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_day_kernel(const __
     if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
     stage_tables(cx, sm);
     int bank_staged = -1;
-    Pass<TR>::day_pass(cx, sm, t, blockIdx.x / cx.blocks_per_rep, blockIdx.x % cx.blocks_per_rep, gridDim.x / cx.blocks_per_rep, bank_staged);
+    Pass<TR>::template day_pass<true>(cx, sm, t, blockIdx.x / cx.blocks_per_rep, blockIdx.x % cx.blocks_per_rep, gridDim.x / cx.blocks_per_rep, bank_staged);
 }
 
 // contact tracing of day t as its own launch (per-day launch mode)
@@ -487,6 +581,7 @@ struct seir_handle {
     int prev_T = 0;   // rows of the history set aside by seir_history_preserve (0: none)
     DevBuf<uint32_t> inbox, tally, home, list_old, list_new, list_cnt;
     DevBuf<uint32_t> pk_pool;   // day buckets of the parked agents
+    DevBuf<int> ctl;            // hand-over words of the single-replica day loop's launches
     DevBuf<RepParams> rp;       // per-replica overrides of the current run
     DevBuf<double> bank;        // table sets (seir_set_table_bank); set 0 = the handle's own tables
     DevBuf<int64_t> kcum;       // keyed prologue: prefix sums of the pick counts per replica
@@ -682,6 +777,7 @@ static void fill_ctx(seir_handle *h)
     c.blocks_per_rep = bpr;
     c.list_old = h->list_old.p; c.list_new = h->list_new.p; c.list_cnt = h->list_cnt.p;
     c.pk_pool = h->pk_pool.p;
+    c.ctl = h->ctl.p;
     c.rp = h->rp.p; c.bank = h->bank.p; c.home_rw = h->home.p; c.T_loop = p.T;
     c.stat = h->stat.p; c.grp_off = h->grp_off.p; c.grp_members = h->grp_members.p;
     c.p_hh_vec = h->p_hh_uniform ? nullptr : h->p_hh.p; c.p_hh_scalar = h->p_hh_scalar;
@@ -694,6 +790,12 @@ static void fill_ctx(seir_handle *h)
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
     c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
     { const char *dp = getenv("SEIR_DEBUG_PASS"); c.dbg_pass = dp ? atoi(dp) : -1; }
+    { const char *sr = getenv("SEIR_SPARSE_ROUNDS"); c.sparse_rounds = sr ? (uint32_t)atoi(sr) : 1u; }  // 0: staged passes only
+    { const char *sx = getenv("SEIR_SPARSE_MAX"); c.sparse_max = sx ? (uint32_t)atoi(sx) : 0xFFFFFFFFu; }
+    {   // single-replica runs: the sparse-day kernel (one CTA per SM) takes the days with at most one entry per warp and round
+        const unsigned long long cap = (unsigned long long)c.sparse_rounds * (unsigned long long)(h->sms * kWarps);
+        c.sparse_cap = (uint32_t)(cap < c.sparse_max ? cap : c.sparse_max);
+    }
     c.n_shards = h->n_shards; c.my_shard = h->my_shard; c.shard_threshold = h->shard_threshold;
     for (int g = 0; g <= kMaxShards; ++g) c.shard_lo[g] = (uint32_t)h->shard_lo[g < h->n_shards ? g : (h->n_shards > 0 ? h->n_shards : 0)];
     for (int g = 0; g < kMaxShards; ++g) {
@@ -854,6 +956,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(cudaMemset(h->home.p, 0, R * np / 32 * 4));
         CKB(h->seeds.alloc(R));
         CKB(h->counters.alloc(R * 4));
+        CKB(h->ctl.alloc(kMaxLaunches + 1));
         CKB(h->barrier.alloc(kBarStride * (2 + 64)));  // flat word, global word, up to 64 group counters (1024 CTAs)
         CKB(h->init_off.alloc(R + 1));
         CKB(h->rp.alloc(R));
@@ -866,20 +969,24 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         if (upload_bank(h, 1, tables, &params->p_infect_given_contact)) break;
         // persistent grid: every CTA must be co-resident
         int occ = 0;
-        if (cudaFuncSetAttribute(seir_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+        if (cudaFuncSetAttribute(seir_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_dense_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
             cudaFuncSetAttribute(seir_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
             cudaFuncSetAttribute(seir_day_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
             cudaFuncSetAttribute(seir_day_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess) {
             fail("cannot reserve shared memory for the day-step kernels");
             break;
         }
-        int occ_t = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel<false>, kThreads, sizeof(PassSmem)) != cudaSuccess || occ < 1 ||
+        int occ_t = 0, occ_s = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, seir_dense_solo_kernel, kThreads, sizeof(PassSmem)) != cudaSuccess || occ_s < 1 ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, seir_persistent_kernel<false>, kThreads, sizeof(PassSmem)) != cudaSuccess || occ < 1 ||
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, seir_persistent_kernel<true>, kThreads, sizeof(PassSmem)) != cudaSuccess || occ_t < 1) {
             fail("occupancy query failed for seir_persistent_kernel");
             break;
         }
-        if (occ_t < occ) occ = occ_t;  // one grid size for both instantiations
+        if (occ_t < occ) occ = occ_t;  // one grid size for all instantiations
+        if (occ_s < occ) occ = occ_s;
         h->occ = occ;
         h->grid = h->sms * occ;
         fill_ctx(h);
@@ -1130,9 +1237,23 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
     CK(cudaEventRecord(h->ev1, h->stream));
     if (h->prm.launch == SEIR_LAUNCH_PERSISTENT) {
         void *args[] = {&h->cx};
+        const bool solo = !tracing && R == 1 && h->n_shards <= 1 && h->prm.mode == SEIR_MODE_NATIVE && SEIR_FLAT_BARRIER && !getenv("SEIR_NO_SOLO");
+        if (solo) {
+            // sparse-day and dense-day kernels in turn (see seir_sparse_kernel); the last launch never hands over, so
+            // four launches always finish the run, and one that finds nothing left to do exits at once
+            CK(cudaMemsetAsync(h->ctl.p, 0, (kMaxLaunches + 1) * sizeof(int), h->stream));
+            for (int k = 0; k < 4; ++k) {
+                uint32_t yield_below = k == 3 ? 0u : h->cx.sparse_cap / 2u + 1u;  // (0: this launch never hands over)
+                void *args[] = {&h->cx, &k, &yield_below};
+                if (k % 2 == 0) CK(cudaLaunchCooperativeKernel((const void *)seir_sparse_kernel, dim3(h->sms), dim3(kThreads), args, sizeof(PassSmem), h->stream));
+                else CK(cudaLaunchCooperativeKernel((const void *)seir_dense_solo_kernel, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
+                ++h->launches;
+            }
+        } else {
         const void *fn = tracing ? (const void *)seir_persistent_kernel<true> : (const void *)seir_persistent_kernel<false>;
         CK(cudaLaunchCooperativeKernel(fn, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
         ++h->launches;
+        }
     } else {
 #ifdef SEIR_SORT_PROBE
         const int sort_mask = getenv("SEIR_DEBUG_SORT") ? atoi(getenv("SEIR_DEBUG_SORT")) : 0;  // 1 transmitting, 2 new, 4 quarantined
@@ -1430,6 +1551,16 @@ int seir_get_stage_times(seir_handle *h, int64_t *out)
     return 0;
 }
 
+// (debug) the hand-over words of the last single-replica run: launch k started at day out[k] + 1
+int seir_get_handover(seir_handle *h, int32_t *out, int n)
+{
+    if (!h || !out) return fail("seir_get_handover: NULL argument");
+    CK(cudaSetDevice(h->device));
+    if (n > kMaxLaunches + 1) n = kMaxLaunches + 1;
+    CK(cudaMemcpy(out, h->ctl.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int seir_get_fine_times(seir_handle *h, int64_t *out)
 {
     if (!h || !out) return fail("seir_get_fine_times: NULL argument");
@@ -1519,7 +1650,7 @@ void seir_destroy(seir_handle *h)
     h->stat.release(); h->grp_off.release(); h->grp_members.release(); h->init_ids.release(); h->init_off.release();
     h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release();
     h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
-    h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release();
+    h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release(); h->ctl.release();
     for (int g = 0; g < kMaxShards; ++g)
         for (int k = 0; k < 5; ++k)
             if (h->peer_ptr[g][k]) cudaIpcCloseMemHandle(h->peer_ptr[g][k]);

@@ -73,7 +73,9 @@ constexpr unsigned long long W_TRACED = 1ull << 63;
 __host__ __device__ __forceinline__ int wday(unsigned long long w) { return (int)((w >> 48) & 0x7FFFu); }
 constexpr int kLogWidth = 100;  // width of the reference's infected_by log (:197)
 constexpr int kMaxShards = 8;   // GPUs of one box
+constexpr int kMaxLaunches = 64; // day-loop launches of one single-replica run (sparse-day and dense-day kernels in turn)
 constexpr uint16_t NEVER = 0xFFFFu;
+constexpr uint32_t kHole = 0xFFFFFFFFu;  // an entry of the transmitting list whose agent left it during a warp-cooperative pass
 
 // 32 B per-agent record.  Derived days: t_infected = t_exposed + tt_activation (F_MILD),
 // t_severe = t_infected + tt_severe (F_SEV), t_critical = t_severe + tt_critical (F_CRIT) -- the reference
@@ -197,6 +199,12 @@ struct DevCtx {
     uint32_t *tedge;               // [rep][tedge_cap] target | kEdgeHH | kEdgeToday, written by the frontier step, read by every root's search
     uint32_t tedge_cap;
     uint32_t *tbig;                // [rep][kBigCap] leaders (root slots) of the components that get a whole CTA
+    uint32_t sparse_rounds;        // a day whose lists hold at most this many entries PER WARP of the replica's CTAs runs as a
+                                   // warp-cooperative pass (sparse_pass: one agent per warp, its draws and gathers spread over
+                                   // the lanes); 0: never.  env SEIR_SPARSE_ROUNDS
+    uint32_t sparse_cap;           // single-replica runs: a day with at most this many list entries is run by seir_sparse_kernel ...
+    int *ctl;                      // [kMaxLaunches + 1] launch k of a run starts at day ctl[k] + 1 and leaves the next day to run in ctl[k + 1]
+    uint32_t sparse_max;           // ... and at most this many entries in all (tests: SEIR_SPARSE_MAX makes a small run switch back and forth)
     int dbg_pass;                  // (debug builds with -DSEIR_CTA_STAMPS) the pass whose per-CTA stage stamps go to fine_ns; env SEIR_DEBUG_PASS
     uint32_t tday0;                // run number << 12: the tracer's day stamps (tmark, tcomp, tlead) are tday0 + t and never need clearing
     unsigned long long *ttotal;    // nodes ever appended to a frontier (grows monotonically: the BFS loop's stop test)
@@ -296,6 +304,22 @@ __device__ __noinline__ double lognormal_days_ni(uint64_t seed, uint32_t agent, 
     return sd_lognormal_days(seed, agent, day, site, sub_base, mu, sigma);
 }
 // continuation of sd_poisson_day after the first uniform (lane 1 of the day block) did not end the product
+// (general form: the product so far, X contacts counted, the next block is `call`)
+__device__ __noinline__ uint32_t poisson_day_from(uint64_t seed, uint32_t agent, uint32_t day, double prod, double enlam, uint32_t cap,
+                                                  uint32_t X, uint32_t call)
+{
+    for (;; ++call) {
+        const sd_block b = sd_draw(seed, agent, day, SD_SITE_NCNT, call);
+        prod = SD_MUL(prod, sd_lane(b, 0));
+        if (prod <= enlam || X >= cap) return X;
+        X += 1;
+        prod = SD_MUL(prod, sd_lane(b, 1));
+        if (prod <= enlam || X >= cap) return X;
+        X += 1;
+    }
+}
+__device__ __noinline__ double log_ni(double x) { return sd_log(x); }
+__device__ __noinline__ double exp_ni(double x) { return sd_exp(x); }
 __device__ __noinline__ uint32_t poisson_day_more(uint64_t seed, uint32_t agent, uint32_t day, double prod, double enlam, uint32_t cap)
 {
     uint32_t X = 1;
@@ -985,6 +1009,451 @@ static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSme
 }
 
 // ---------------------------------------------------------------------------------------
+// The warp-cooperative pass of a SPARSE day (sparse_entry / sparse_rounds).
+// While a day's lists are shorter than the warps that serve them, the staged pass above runs at its latency floor:
+// ONE agent's chain through five stages, queues and __syncthreads(), every link a draw or a round trip issued by a
+// single lane.  Here a WARP takes one list entry through its whole day, and the 32 lanes hold everything of that day
+// that is independent by the keyed-draw contract: the agent's day block, its four household blocks, the blocks of the
+// three progression events, four more blocks of the kept-contact count and sixteen contact picks are ONE SIMD Philox
+// evaluation issued before the agent's record has arrived; the household members' words, the contacts' alias / member /
+// winner gathers and the hits' atomics run side by side on their own lanes; the tries of an infectee's log-normal
+// activation time are evaluated at once.  The agent's logic (:256-337) is executed uniformly by all lanes.
+// No queue and no CTA barrier; tallies go straight to the day's rows (fire-and-forget reductions).
+// Tomorrow's list of transmitting agents keeps the SLOT of every entry (a dropped agent leaves kHole), so a survivor
+// costs one store and no atomic; holes disappear whenever a staged pass runs (it re-appends densely).
+// Same statements, same keys, same atomics on the infectee as the staged pass: the two are interchangeable day by day
+// (tests/test_gpu_parity.py runs every fixture through both).
+static __device__ __forceinline__ void tally_add(const DevCtx &cx, const RepView &v, int t, int row, int age, uint32_t val)
+{
+    const int day = row < kTalLagRows ? t - 1 : t;
+    if (val && day < v.T) atomicAdd(cx.tally + ((size_t)v.rep * cx.T + day) * (TAL_ROWS * kAges) + row * kAges + age, val);
+}
+
+// next_wake_day with the documentation draws of the days ahead on lanes 1 .. kDocScan (every lane returns the day)
+static __device__ __forceinline__ int next_wake_day_warp(const DevCtx &cx, uint64_t seed, uint32_t i, const AgentRec &r, int comp, bool doc, int t)
+{
+    const int lane = threadIdx.x & 31;
+    const int t_exposed = (int)r.t_exposed();
+    int w = 0x7FFFFFFF;
+#define SEIR_CAND(t0, tt) do { if ((tt) != NEVER) { const int d_ = (int)(t0) + (int)(tt); if (d_ > t && d_ < w) w = d_; } } while (0)
+    if (comp == C_E) {
+        SEIR_CAND(t_exposed, r.tt_activation());
+    } else {
+        const int t_inf = t_exposed + (int)r.tt_activation();
+        SEIR_CAND(t_inf, r.tt_recovery());
+        if (comp == C_MILD) SEIR_CAND(t_inf, r.tt_severe());
+        else if (comp == C_SEV) SEIR_CAND(t_inf + (int)r.tt_severe(), r.tt_critical());
+        else SEIR_CAND(t_inf + (int)r.tt_severe() + (int)r.tt_critical(), r.tt_death());
+    }
+#undef SEIR_CAND
+    if (comp == C_MILD && !doc && cx.p_doc > 0.0) {
+        const int hi = w < t + kDocScan + 1 ? w : t + kDocScan + 1;
+        const int k = lane >= 1 && lane <= kDocScan ? lane : 1;
+        const sd_block b = draw_block(seed, i, (uint32_t)(t + k), SD_SITE_DAY, 0);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, lane >= 1 && lane <= kDocScan && t + k < hi && sd_lane(b, 0) < cx.p_doc);
+        w = m ? t + (__ffs(m) - 1) : hi;
+    }
+    return w;
+}
+
+// One list entry by one warp (all 32 lanes arrive and leave together).  kind: 0 parked agent due today, 1 infected
+// yesterday (no record yet), 2 may transmit today.  Returns DAY_DROP / DAY_KEEP / DAY_KEEP_Q | offset like agent_day.
+#ifdef SEIR_FINE_STAMPS
+#define SEIR_SFINE(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) cx.fine_ns[(size_t)t * 16 + (k)] = (unsigned long long)clock64(); } while (0)  // (SM cycles: deltas within CTA 0)
+#else
+#define SEIR_SFINE(k) do { } while (0)
+#endif
+static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, uint32_t i, int kind, int t, bool finalize, bool own,
+                                                uint32_t site, uint32_t sub)
+{
+    const RepView &v = sm.v;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tw = own ? 1u : 0u;
+    const bool is_new = kind == 1;
+    // ---- everything that only needs (i, t) is in flight before the record arrives
+    AgentRec r;
+    unsigned long long w_self = 0;
+    uint32_t ib = 0, stt_new = 0;
+    if (is_new) {
+        w_self = __ldcg(v.winner + i);
+        ib = __ldcg(v.inbox + (i >> 4));
+        stt_new = __ldg(cx.stat + i);
+    } else {
+        r = load_rec(v.rec + i);
+    }
+    SEIR_SFINE(0);
+    double p_h = cx.p_hh_vec ? __ldg(cx.p_hh_vec + i) : cx.p_hh_scalar;
+    const bool home_i = at_home(v, i);
+    const sd_block blk = finalize ? sd_block{{0u, 0u, 0u, 0u}} : draw_block(v.seed, i, (uint32_t)t, site, sub);
+    const double u0 = sd_lane(blk, 0), u1 = sd_lane(blk, 1);
+    SEIR_SFINE(1);
+    bool dirty = false;
+    if (is_new) {  // infected on day t-1 by the winner of that day's hits (:347-356); try `lane` of the polar method on lane `lane`
+        const uint32_t inf = (uint32_t)(w_self >> 16), ord = (uint32_t)(w_self & 0xFFFFu);
+        const int tx = t - 1;
+        const int age = (int)(stt_new & 127u);
+        const sd_block b = draw_block(v.seed, inf, (uint32_t)tx, SD_SITE_INF, (ord << 8) + lane);
+        const double x1 = SD_SUB(SD_MUL(2.0, sd_lane(b, 0)), 1.0), x2 = SD_SUB(SD_MUL(2.0, sd_lane(b, 1)), 1.0);
+        const double r2 = SD_ADD(SD_MUL(x1, x1), SD_MUL(x2, x2));
+        const bool ok = lane >= 1u && r2 < 1.0 && r2 != 0.0;
+        const double lg = log_ni(lane == 0u ? SD_SUB(1.0, sd_lane(b, 0)) : (ok ? r2 : 1.0));   // one log for all: lane 0 the exponential, the others their try
+        double tiso = SD_RINT(SD_MUL(-lg, sm.iso_asym[age]));
+        double z = ok ? SD_MUL(SD_SQRT(SD_DIV(SD_MUL(-2.0, lg), r2)), x2) : 0.0;
+        const unsigned acc = __ballot_sync(0xFFFFFFFFu, ok);
+        tiso = __shfl_sync(0xFFFFFFFFu, tiso, 0);
+        double tact;
+        if (acc) {
+            z = __shfl_sync(0xFFFFFFFFu, z, __ffs(acc) - 1);
+            const double x = exp_ni(SD_FMA(cx.act_sigma, z, cx.act_mu));
+            tact = x <= 0.0 ? 1.0 : SD_RINT(x);
+        } else {  // (31 rejections in a row: the plain loop goes on from there)
+            tact = lognormal_days_ni(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+        }
+        r.clear();
+        r.set_t_exposed((uint16_t)tx);
+        r.set_tt_isolate(sd_enc16(tiso));
+        r.set_tt_activation(sd_enc16(tact));
+        r.set_t_end(NEVER);
+        r.set_t_q_on(NEVER);
+        r.set_stat(stt_new);
+        r.set_state(C_E);
+        if (ib & inbox_q_bit((int)(i & 15))) {
+            r.set_state(r.state() | ST_Q);
+            r.set_t_q_on((uint16_t)tx);
+            if (lane == 0u) tally_add(cx, v, t, TAL_NEW_QE, age, tw);
+        }
+        if (w_self & W_TRACED) {
+            r.set_state(r.state() | ST_DOC);
+            r.set_t_documented((uint16_t)tx);
+        }
+        if (lane == 0u) tally_add(cx, v, t, TAL_NEW_E, age, tw);
+        dirty = true;
+    }
+    SEIR_SFINE(2);
+    if (finalize) {  // pass T: the agents infected on the last day get their records, nothing moves
+        if (dirty && lane == 0u) store_rec(v.rec + i, r);
+        return DAY_DROP;
+    }
+    // ---- the agent's own day (:256-337), uniform over the lanes; the draws come from the lanes that hold them
+    const uint16_t stt = r.stat();
+    const int age = stt & 127;
+    const uint8_t st = r.state();
+    const int comp = st & 7;
+    const bool Ep = comp == C_E, Mp = comp == C_MILD, Sevp = comp == C_SEV, Cp = comp == C_CRIT;
+    const bool Qp = (st & ST_Q) != 0, Dp = (st & ST_DOC) != 0;
+    int ncomp = comp;
+    bool nq = Qp, ndoc = Dp;
+    bool transmit = !Qp;
+    const double doc_u = __shfl_sync(0xFFFFFFFFu, u0, 0), knuth_u = __shfl_sync(0xFFFFFFFFu, u1, 0);
+    const double act0 = __shfl_sync(0xFFFFFFFFu, u0, 5), act1 = __shfl_sync(0xFFFFFFFFu, u1, 5), act2 = __shfl_sync(0xFFFFFFFFu, u0, 6);
+    const double sev0 = __shfl_sync(0xFFFFFFFFu, u0, 7), sev1 = __shfl_sync(0xFFFFFFFFu, u1, 7);
+    const double cr0 = __shfl_sync(0xFFFFFFFFu, u0, 8), cr1 = __shfl_sync(0xFFFFFFFFu, u1, 8);
+    const bool want_doc = Mp && !Dp && cx.p_doc > 0.0;
+    const int t_inf = t_infected_of(r);
+    if (!Ep && due(t, t_inf, r.tt_recovery())) {  // :276-279
+        ncomp = C_R;
+        nq = false;
+        transmit = false;
+        if (lane == 0u) tally_add(cx, v, t, TAL_NEW_R, age, tw);
+    } else {
+        const bool ev = (Ep && due(t, r.t_exposed(), r.tt_activation())) || (Mp && due(t, t_inf, r.tt_severe())) ||
+                        (Sevp && due(t, t_severe_of(r), r.tt_critical()));
+        if (want_doc && doc_u < cx.p_doc) {  // :280-289 (tracing days never run here: no Q from :287)
+            ndoc = true;
+            r.set_t_documented((uint16_t)t);
+        }
+        if (ev) {
+            const int k3 = age * 4 + ((stt >> 7) & 1) * 2 + ((stt >> 8) & 1);
+            dirty = true;
+            if (Ep) {  // :256-272 activation: both exponentials at once (lane 0 the course, lane 1 the isolation time)
+                ncomp = C_MILD;
+                r.set_flags(r.flags() | F_MILD);
+                const bool sev = act0 < __ldg(v.p_ms + k3);
+                const double val = exp_days_ni(lane == 1u ? act2 : act1, lane == 1u ? sm.iso_mean[age] : (sev ? cx.m_sev : cx.m_mild_rec));
+                const double tcourse = __shfl_sync(0xFFFFFFFFu, val, 0), tiso = __shfl_sync(0xFFFFFFFFu, val, 1);
+                if (sev) { r.set_tt_severe(sd_enc16(tcourse)); r.set_tt_recovery(NEVER); }
+                else { r.set_tt_recovery(sd_enc16(tcourse)); r.set_tt_severe(NEVER); }
+                r.set_tt_isolate(sd_enc16(tiso));
+                if (tiso == 0.0) nq = true;
+            } else if (Mp) {  // :291-311 Mild -> Severe
+                ncomp = C_SEV;
+                r.set_flags(r.flags() | F_SEV);
+                if (!ndoc) { ndoc = true; r.set_t_documented((uint16_t)t); }
+                nq = true;
+                const bool crit = sev0 < __ldg(v.p_sc + k3);
+                const double val = exp_days_ni(sev1, crit ? cx.m_crit : cx.m_sev_rec);
+                if (crit) { r.set_tt_critical(sd_enc16(val)); r.set_tt_recovery(NEVER); }
+                else { r.set_tt_recovery(add_sat16(sd_enc16(val), r.tt_severe())); r.set_tt_critical(NEVER); }
+            } else {  // :312-321 Severe -> Critical
+                ncomp = C_CRIT;
+                r.set_flags(r.flags() | F_CRIT);
+                const bool dies = cr0 < __ldg(v.p_cd + k3);
+                const double val = exp_days_ni(cr1, dies ? cx.m_death : cx.m_crit_rec);
+                if (dies) { r.set_tt_death(sd_enc16(val)); r.set_tt_recovery(NEVER); }
+                else { r.set_tt_recovery(add_sat16(add_sat16(sd_enc16(val), r.tt_severe()), r.tt_critical())); r.set_tt_death(NEVER); }
+            }
+        } else if (Cp && due(t, t_critical_of(r), r.tt_death())) {  // :323-327
+            ncomp = C_D;
+            nq = false;
+            if (lane == 0u) tally_add(cx, v, t, TAL_NEW_D, age, tw);
+        }
+        if (ndoc && !Dp && lane == 0u) tally_add(cx, v, t, TAL_NEW_DOC, age, tw);
+    }
+    SEIR_SFINE(3);
+    if (transmit) {  // :328-337 isolation entry
+        if (!Ep && due(t, t_infected_of(r), r.tt_isolate())) { nq = true; transmit = false; }
+        else if (Ep && due(t, r.t_exposed(), r.tt_isolate())) { nq = true; transmit = false; }
+    }
+    const bool active = ncomp <= C_CRIT;
+    if (lane == 0u) {
+        if (ncomp != comp) {
+            tally_add(cx, v, t, TAL_D_E + comp - C_E, age, 0u - tw);
+            if (active) tally_add(cx, v, t, TAL_D_E + ncomp - C_E, age, tw);
+        }
+        if ((nq && active) != Qp) tally_add(cx, v, t, TAL_D_Q, age, Qp ? 0u - tw : tw);
+    }
+    const uint8_t nst = (uint8_t)(ncomp | (nq ? ST_Q : 0) | (ndoc ? ST_DOC : 0));
+    if (nst != st) {
+        r.set_state(nst);
+        if (nq && !Qp && r.t_q_on() == NEVER) r.set_t_q_on((uint16_t)t);
+        if (ncomp == C_R || ncomp == C_D) r.set_t_end((uint16_t)t);
+        dirty = true;
+    }
+    if (transmit) {
+        // ---- household push :339-359 on lanes 0..6 (member j), community push :361-390 on lanes 16..31 (contact k)
+        const int pos = (stt >> 9) & 7, size = ((stt >> 12) & 7) + 1;
+        const uint32_t base = i - (uint32_t)pos;
+        if (Ep) p_h = SD_MUL(p_h, cx.asym);
+        const bool hh_lane = (int)lane < size - 1;
+        const uint32_t member = base + lane + ((int)lane >= pos ? 1u : 0u);
+        unsigned long long w_m = 1ull;
+        uint32_t stat_m = 0;
+        if (hh_lane) { w_m = __ldcg(v.winner + member); stat_m = __ldg(cx.stat + member); }
+        // member j draws lane j&1 of household block j>>1, which lane 1 + (j>>1) holds
+        const int src = 1 + (int)((lane >> 1) & 3u);
+        const double h0 = __shfl_sync(0xFFFFFFFFu, u0, src), h1 = __shfl_sync(0xFFFFFFFFu, u1, src);
+        // the kept-contact count: Knuth's product over lane 1 of the day block and the NCNT blocks of lanes 9..12
+        // (every branch below is warp-uniform: the shuffles are executed by all lanes)
+        uint32_t kept = 0;
+        if (!home_i) {
+            const double en = sm.nat_enlam[(v.phase * kAges + age) * 2 + (Ep ? 1 : 0)];
+            double prod = knuth_u;
+            if (prod > en) {
+                kept = 1;
+                bool done = false;
+#pragma unroll 1
+                for (int c = 0; c < 4 && !done; ++c) {
+                    prod = SD_MUL(prod, __shfl_sync(0xFFFFFFFFu, u0, 9 + c));
+                    if (prod <= en || kept >= SD_MAX_CONTACTS_NATIVE) done = true;
+                    else {
+                        kept += 1;
+                        prod = SD_MUL(prod, __shfl_sync(0xFFFFFFFFu, u1, 9 + c));
+                        if (prod <= en || kept >= SD_MAX_CONTACTS_NATIVE) done = true;
+                        else kept += 1;
+                    }
+                }
+                if (!done) kept = poisson_day_from(v.seed, i, (uint32_t)t, prod, en, SD_MAX_CONTACTS_NATIVE, kept, 4u);
+            }
+        }
+    SEIR_SFINE(4);
+        uint32_t hits = 0, hits_out = 0;
+        const bool first_batch_hh = hh_lane && (w_m == 0ull || wday(w_m) == t) && ((lane & 1u) ? h1 : h0) < p_h;  // :346
+        for (uint32_t k0 = 0; k0 == 0u || k0 < kept; k0 += 16u) {
+            // this lane's candidate of the batch
+            bool cand = false, is_hit = false;
+            uint32_t c = 0, ord = 0;
+            int age_c = 0;
+            unsigned long long w_c = 1ull;
+            const uint32_t k = k0 + lane - 16u;
+            if (lane >= 16u && k < kept) {  // :373-375, native: contact age from the alias table of the sender's row, a uniform member
+                const sd_block b = k0 == 0u ? blk : draw_block(v.seed, i, (uint32_t)t, SD_SITE_NPICK, k);
+                const double x = SD_MUL(sd_lane(b, 0), (double)kAges);
+                int col = (int)x;
+                if (col > kAges - 1) col = kAges - 1;
+                const int row = age * kAges + col;
+                const double pr = __ldg(cx.nat_alias_prob + row);
+                const int al = __ldg(cx.nat_alias_idx + row);
+                age_c = (SD_SUB(x, (double)col) < pr) ? col : al;
+                const int g0 = sm.grp_off[age_c], glen = sm.grp_off[age_c + 1] - g0;
+                if (glen != 0) {
+                    c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));
+                    if (SEIR_CHECK((int64_t)c < cx.n, cx, v.rep)) {
+                        w_c = __ldcg(v.winner + c);
+                        cand = true;
+                        ord = SD_ORD_COMM_NATIVE(k);
+                    }
+                }
+            } else if (k0 == 0u && first_batch_hh) {
+                cand = true;
+                c = member;
+                ord = SD_ORD_HH(lane);
+                age_c = (int)(stat_m & 127u);
+                w_c = 0ull;
+            }
+            if (__any_sync(0xFFFFFFFFu, cand)) {
+                // the infectee's isolation draw (:352, :381) does not depend on the target's state: it overlaps the gathers
+    SEIR_SFINE(5);
+                const bool home_c = cand && lane >= 16u && at_home(v, c);  // (:375; the household push has no Home test, :346)
+                double tiso = 1.0;
+                if (cand) tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
+    SEIR_SFINE(6);
+                is_hit = cand && (w_c == 0ull || wday(w_c) == t) && !home_c;
+                if (is_hit) {
+                    const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
+                    const unsigned long long old = atomicMax(v.winner + c, key);
+                    uint32_t bits = 0;
+                    if (wday(old) != t) {  // first hit of c today
+                        bits = inbox_infected_bit((int)(c & 15));
+                        const uint32_t p = atomicAdd_system(v.next_new_cnt, 1u);
+                        if (SEIR_CHECK((int64_t)p < cx.n_pad, cx, v.rep)) __stcg(v.next_new + p, c);
+                    }
+                    if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
+                    if (bits) atomicOr(v.inbox + (c >> 4), bits);
+                    if (TR && cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387)
+                        const uint32_t e = atomicAdd(cx.log_cnt + v.rep, 1u);
+                        if (e < cx.log_cap) {
+                            const uint32_t prev = atomicExch(cx.log_head + (size_t)v.rep * cx.n_pad + i, e + 1u);
+                            __stcg(cx.log_ent + (size_t)v.rep * cx.log_cap + e, make_uint4(c, prev, ((uint32_t)t << 16) | ord, 0u));
+                        } else {
+                            atomicOr(&cx.counters[v.rep * 4 + 0], 1ull);
+                        }
+                    }
+                }
+    SEIR_SFINE(7);
+                const unsigned hm = __ballot_sync(0xFFFFFFFFu, is_hit);
+                hits += (uint32_t)__popc(hm);
+                hits_out += (uint32_t)__popc(hm & 0xFFFF0000u);
+            }
+        }
+        if (hits) {  // :357-359, :386-390
+            r.set_n_inf_by(inc_sat16(r.n_inf_by(), hits));
+            if (Ep) r.set_n_inf_asympt(inc_sat16(r.n_inf_asympt(), hits));
+            r.set_n_inf_outside(inc_sat16(r.n_inf_outside(), hits_out));
+            dirty = true;
+            if (own && lane == 0u) atomicAdd(&sm.cnt[2], hits);
+        }
+    }
+    SEIR_SFINE(8);
+    if (dirty && lane == 0u) store_rec(v.rec + i, r);
+    if (!active) return DAY_DROP;
+    if (!nq) return DAY_KEEP;
+    int wake = t + 1;
+    if (Qp || !(ncomp == C_MILD && !ndoc && cx.p_doc > 0.0)) wake = next_wake_day_warp(cx, v.seed, i, r, ncomp, ndoc, t);
+    if (wake >= v.T) return DAY_DROP;
+    if (wake > t + kParkHorizon) wake = t + kParkHorizon;
+    return DAY_KEEP_Q | ((wake - t - 1) << 2);
+}
+
+// the lane's block of the agent's day: (site, sub) of lane l
+static __device__ __forceinline__ void sparse_lane_role(uint32_t lane, uint32_t &site, uint32_t &sub)
+{
+    site = SD_SITE_DAY; sub = 0u;                                                 // lane 0 (and the spare lanes 13..15)
+    if (lane >= 16u) { site = SD_SITE_NPICK; sub = lane - 16u; }                  // contact picks 0..15
+    else if (lane >= 1u && lane <= 4u) { site = SD_SITE_HH; sub = lane - 1u; }    // household blocks 0..3
+    else if (lane == 5u) { site = SD_SITE_ACT; sub = 0u; }
+    else if (lane == 6u) { site = SD_SITE_ACT; sub = 1u; }
+    else if (lane == 7u) { site = SD_SITE_SEV; sub = 0u; }
+    else if (lane == 8u) { site = SD_SITE_CRIT; sub = 0u; }
+    else if (lane >= 9u && lane <= 12u) { site = SD_SITE_NCNT; sub = lane - 9u; } // Knuth uniforms 2..9
+}
+
+// The replica's lists of day t by the warps of its CTAs: entry e goes to warp e / bpr of CTA part e mod bpr.
+// (entries: [0, n_pk) parked agents due today, [n_pk, n_pk + n_new) infected yesterday, then the transmitting list)
+static __device__ __noinline__ void sparse_rounds(const DevCtx &cx, PassSmem &sm, int t, uint32_t n_new, uint32_t n_old, uint32_t n_pk,
+                                                     const uint32_t *cur_new, const uint32_t *cur_old, const uint32_t *cur_pk,
+                                                     int my_part, int bpr, bool finalize, bool sharded_now)
+{
+    const RepView &v = sm.v;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t site, sub;
+    sparse_lane_role(lane, site, sub);
+    const uint32_t count = n_pk + n_new + n_old;
+    for (uint32_t e = warp * (uint32_t)bpr + (uint32_t)my_part; e < count; e += (uint32_t)(kWarps * bpr)) {
+        const int kind = e < n_pk ? 0 : e < n_pk + n_new ? 1 : 2;
+        const uint32_t idx = kind == 0 ? e : kind == 1 ? e - n_pk : e - n_pk - n_new;
+        const uint32_t i = __ldcg((kind == 0 ? cur_pk : kind == 1 ? cur_new : cur_old) + idx);
+        int keep = DAY_DROP;
+        SEIR_SFINE(11);
+        if (i != kHole && SEIR_CHECK((int64_t)i < cx.n, cx, v.rep)) {
+            const bool own = cx.n_shards <= 1 || (i >= cx.shard_lo[cx.my_shard] && i < cx.shard_lo[cx.my_shard + 1]);
+            keep = sparse_entry(cx, sm, i, kind, t, finalize, own, site, sub);
+            if (lane == 0u && own) {
+                atomicAdd(&sm.cnt[0], 1u);
+                if (kind == 1) atomicAdd(&sm.cnt[1], 1u);
+            }
+        }
+        if (lane == 0u && !finalize) {
+            // tomorrow's transmitting list keeps today's slots: the list's entries first, then the new infectees
+            if (kind != 0) v.next_old[kind == 2 ? idx : n_old + idx] = keep == DAY_KEEP ? i : kHole;
+            if ((keep & 3) == DAY_KEEP_Q) {
+                const int wake = t + 1 + (keep >> 2);
+                const uint32_t p = atomicAdd(v.pk_cnt + wake, 1u);
+                if (SEIR_CHECK((int64_t)p < cx.n_pad, cx, v.rep)) __stcg(v.pk_pool + (size_t)(wake & (kParkRing - 1)) * cx.n_pad + p, i);
+            }
+        }
+    }
+    SEIR_SFINE(13);
+    if (my_part == 0 && threadIdx.x == 0 && !finalize) *v.next_old_cnt = n_old + n_new;  // (nobody else touches this counter today)
+    (void)sharded_now;
+}
+
+// the replica's view of pass t (thread 0 of the CTA)
+static __device__ __noinline__ void fill_view(const DevCtx &cx, PassSmem &sm, int t, int rep, bool sharded_now)
+{
+    const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad;
+    uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_pk = cnt_new + (cx.T + 2);
+    if (sm.rp_rep != rep) {  // (one request per CTA and replica: the overrides do not change during a launch)
+        sm.rp = cx.rp[rep];
+        sm.rp_rep = rep;
+    }
+    const RepParams rp = sm.rp;
+    sm.v.T = rp.T;
+    const double *bank = cx.bank + (size_t)rp.bank * kBankStride;
+    sm.v.p_ms = bank + kBankPms; sm.v.p_sc = bank + kBankPsc; sm.v.p_cd = bank + kBankPcd;
+    sm.v.p_contact = bank + kBankPcontact;
+    sm.v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
+    sm.v.winner = cx.winner + (size_t)rep * cx.n_pad;
+    sm.v.rec = cx.rec + (size_t)rep * cx.n_pad;
+    sm.v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
+    sm.v.next_old = cx.list_old + lrow;
+    sm.v.next_new = cx.list_new + lrow;
+    sm.v.next_old_cnt = cnt_old + (t + 1);
+    sm.v.next_new_cnt = cnt_new + (t + 1);
+    sm.v.pk_cnt = cnt_pk;
+    sm.v.pk_pool = cx.pk_pool + (size_t)rep * kParkRing * cx.n_pad;
+    sm.v.n_pad_m1 = (uint32_t)(cx.n_pad - 1);
+    sm.v.seed = cx.seeds[rep];
+    sm.v.home_on = rp.t_stayhome >= 1 && t >= rp.t_stayhome;          // :243-244
+    sm.v.phase = (rp.t_lockdown >= 1 && t >= rp.t_lockdown) ? 1 : 0;  // :234-240
+    sm.v.rep = rep;
+    sm.v.tracing = rp.trace_from >= 1 && t >= rp.trace_from;          // :241-242
+    sm.v.sharded = sharded_now;
+    sm.v.replicated = cx.n_shards > 1 && !sharded_now;
+}
+// today's list lengths of the replica (new, transmitting, parked due), by ONE thread of the CTA
+static __device__ __forceinline__ void load_list_lengths(const DevCtx &cx, PassSmem &sm, int t, int rep)
+{
+    const uint32_t *c = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2) + t;
+    const uint32_t a = __ldcg(c + (cx.T + 2)), b = __ldcg(c), d = __ldcg(c + 2 * (cx.T + 2));
+    sm.list_n[0] = a; sm.list_n[1] = b; sm.list_n[2] = d;
+}
+// this CTA's run counters of the pass (thread 0; the CTA has met since the last of them was counted)
+static __device__ __noinline__ void flush_pass_counters(const DevCtx &cx, PassSmem &sm, int rep, bool defer_counters)
+{
+    if (defer_counters) {
+        sm.run_cnt[0] += sm.cnt[0]; sm.run_cnt[1] += sm.cnt[1]; sm.run_cnt[2] += sm.cnt[2];
+    } else {
+        if (sm.cnt[0]) atomicAdd(&cx.counters[rep * 4 + 1], (unsigned long long)sm.cnt[0]);
+        if (sm.cnt[1]) atomicAdd(&cx.counters[rep * 4 + 2], (unsigned long long)sm.cnt[1]);
+        if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
+    }
+#ifdef SEIR_CHECKS
+    if (sm.cnt[3]) atomicOr(&cx.counters[rep * 4 + 0], 4ull);
+#endif
+    sm.cnt[0] = 0; sm.cnt[1] = 0; sm.cnt[2] = 0; sm.cnt[3] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // Pass t over all replicas.  CTA b serves replica (b / blocks_per_rep) [+ k * reps_per_sweep]; the CTAs of a
 // replica split its list: a list shorter than the replica's threads is dealt S threads apart (one entry
 // per warp while it fits), a longer one in equal contiguous chunks, kPerThread entries per thread and round.
@@ -995,8 +1464,13 @@ static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSme
 #else
 #define SEIR_STAMP(k) do { if (blockIdx.x == 0 && tid == 0 && !stamped) cx.stage_ns[(size_t)t * 8 + (k)] = global_timer_ns(); } while (0)
 #endif
-static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep,
-                                int &bank_staged, bool defer_counters = false, bool sharded_now = false)
+// (inline_sparse: a sparse day runs as a warp-cooperative pass inside this kernel -- replica ensembles, tracing builds and
+// sharded runs; the single-replica day loop hands its sparse days to seir_sparse_kernel instead and keeps this code out)
+// (can_yield: the single-replica dense-day kernel; returns true WITHOUT touching the day when its lists have shrunk to
+// fewer than yield_below entries (0: never) -- the sparse-day kernel takes over)
+template <bool inline_sparse, bool can_yield = false>
+static __device__ bool day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep,
+                                int &bank_staged, bool defer_counters = false, bool sharded_now = false, uint32_t yield_below = 0u)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
@@ -1049,45 +1523,14 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad, lcur = ((size_t)rep * 2 + (t & 1)) * cx.n_pad;
         uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_pk = cnt_new + (cx.T + 2);
         const RepView &v = sm.v;
-        if (tid == 0) {
-            if (sm.rp_rep != rep) {  // (one request per CTA and replica: the overrides do not change during a launch)
-                sm.rp = cx.rp[rep];
-                sm.rp_rep = rep;
-            }
-            const RepParams rp = sm.rp;
-            sm.v.T = rp.T;
-            const double *bank = cx.bank + (size_t)rp.bank * kBankStride;
-            sm.v.p_ms = bank + kBankPms; sm.v.p_sc = bank + kBankPsc; sm.v.p_cd = bank + kBankPcd;
-            sm.v.p_contact = bank + kBankPcontact;
-            sm.v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
-            sm.v.winner = cx.winner + (size_t)rep * cx.n_pad;
-            sm.v.rec = cx.rec + (size_t)rep * cx.n_pad;
-            sm.v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
-            sm.v.next_old = cx.list_old + lrow;
-            sm.v.next_new = cx.list_new + lrow;
-            sm.v.next_old_cnt = cnt_old + (t + 1);
-            sm.v.next_new_cnt = cnt_new + (t + 1);
-            sm.v.pk_cnt = cnt_pk;
-            sm.v.pk_pool = cx.pk_pool + (size_t)rep * kParkRing * cx.n_pad;
-            sm.v.n_pad_m1 = (uint32_t)(cx.n_pad - 1);
-            sm.v.seed = cx.seeds[rep];
-            sm.v.home_on = rp.t_stayhome >= 1 && t >= rp.t_stayhome;          // :243-244
-            sm.v.phase = (rp.t_lockdown >= 1 && t >= rp.t_lockdown) ? 1 : 0;  // :234-240
-            sm.v.rep = rep;
-            sm.v.tracing = rp.trace_from >= 1 && t >= rp.trace_from;          // :241-242
-            sm.v.sharded = sharded_now;
-            sm.v.replicated = cx.n_shards > 1 && !sharded_now;
-        }
+        if (tid == 0) fill_view(cx, sm, t, rep, sharded_now);
 
         const uint32_t *cur_old = cx.list_old + lcur, *cur_new = cx.list_new + lcur;
         const uint32_t *cur_pk = cx.pk_pool + ((size_t)rep * kParkRing + (size_t)(t & (kParkRing - 1))) * cx.n_pad;  // today's bucket
         // today's list lengths: ONE request per CTA and counter (a load by every warp of the grid is 4 736 requests
         // for the same L2 line, which its slice serves one at a time: 2 us at the start of every pass)
         if (tid < 3) sm.list_n[tid] = __ldcg((tid == 0 ? cnt_new : tid == 1 ? cnt_old : cnt_pk) + t);
-        for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
         if (tid >= 32 && tid < 36) sm.cnt[tid - 32] = 0;
-        if (tid == 64) { sm.n_old = 0; sm.n_pk = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_draw = 0; sm.next_group = 0; }
-        if (tid >= 96 && tid < 128) sm.pk_n[tid - 96] = 0;
         __syncthreads();
         const RepParams rp = sm.rp;
         if (t > rp.T) {  // (a replica with a shorter horizon than the launch's: finished)
@@ -1099,11 +1542,27 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             const double *src = cx.bank + (size_t)rp.bank * kBankStride + kBankNatEn;
             for (int k = tid; k < 4 * kAges; k += kThreads) sm.nat_enlam[k] = src[k];
             bank_staged = rp.bank;
+            __syncthreads();  // (once per CTA and table set)
         }
         // yesterday's bucket has been consumed: its chunks go back to the free ring (one warp of the replica's first CTA;
         // today's allocations cannot reach these ring slots: the ring holds twice the chunks that can be in use)
         // (pass T only finalises: the agents infected on the last day get their records, nobody else is visited)
+        if (can_yield && sm.list_n[0] + sm.list_n[1] + sm.list_n[2] < yield_below) return true;  // (grid-uniform)
         const uint32_t n_new = sm.list_n[0], n_old = finalize ? 0u : sm.list_n[1], n_pk = finalize ? 0u : sm.list_n[2];
+        // a SPARSE day: one warp per entry (sparse_rounds); the staged rounds below serve the days whose lists outgrow the warps
+        const bool sparse = inline_sparse && cx.sparse_rounds != 0u && cx.mode == SEIR_MODE_NATIVE && !sharded_now && !(TR && v.tracing) &&
+                            n_pk + n_new + n_old <= cx.sparse_rounds * (uint32_t)(kWarps * bpr) && n_pk + n_new + n_old <= cx.sparse_max;
+        if (sparse) {
+            SEIR_STAMP(0);
+            SEIR_SFINE(10);
+            sparse_rounds(cx, sm, t, n_new, n_old, n_pk, cur_new, cur_old, cur_pk, my_part, bpr, finalize, sharded_now);
+            SEIR_STAMP(1); SEIR_STAMP(2); SEIR_STAMP(3); SEIR_STAMP(4); SEIR_STAMP(5); SEIR_STAMP(6);
+            __syncthreads();
+        } else {
+        for (int k = tid; k < TAL_ROWS * kAges; k += kThreads) sm.tally[k] = 0;
+        if (tid == 64) { sm.n_old = 0; sm.n_pk = 0; sm.n_new = 0; sm.n_hit = 0; sm.n_con = 0; sm.n_draw = 0; sm.next_group = 0; }
+        if (tid >= 96 && tid < 128) sm.pk_n[tid - 96] = 0;
+        __syncthreads();
         // three segments, each starting on a multiple of 32 -- a warp of a dense day serves one kind -- the heaviest
         // first (the warps grab the groups in this order, and the pass lasts as long as its last group): parked
         // agents due today (every one of them has an event, most of them draws), new infectees (record build),
@@ -1165,6 +1624,9 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
 #endif
                 if (has) {
                     i = is_q ? __ldcg(cur_pk + e) : is_new ? __ldcg(cur_new + (e - o_n)) : __ldcg(cur_old + (e - o_t));
+                }
+                const bool hole = has && i == kHole;  // (left behind by a warp-cooperative pass)
+                if (has && !hole) {
 #if SEIR_PREFETCH
                     if (!is_new && (int64_t)i < cx.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(v.rec + i));  // (its own record: in flight while i2 arrives)
 #endif
@@ -1185,7 +1647,7 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 append_survivors(sm, keep, i);
                 SEIR_FINE(9);
                 // (run counters: every agent is counted by its owner -- a replicated day steps the others' agents too)
-                const unsigned hm = __ballot_sync(0xFFFFFFFFu, has && own), nm = __ballot_sync(0xFFFFFFFFu, has && own && is_new);
+                const unsigned hm = __ballot_sync(0xFFFFFFFFu, has && !hole && own), nm = __ballot_sync(0xFFFFFFFFu, has && !hole && own && is_new);
                 if (lane == 0 && hm) {
                     atomicAdd(&sm.cnt[0], (uint32_t)__popc(hm));
                     if (nm) atomicAdd(&sm.cnt[1], (uint32_t)__popc(nm));
@@ -1267,24 +1729,15 @@ static __device__ void day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                 if (day < rp.T) atomicAdd(&tal[(size_t)day * TAL_ROWS * kAges + k], val);
             }
         }
-        if (tid == 0) {
-            // run counters (list entries visited, infections, hits): 296 CTAs adding to the same three words every pass
-            // queue up at one L2 slice in front of the grid barrier's fence; a CTA that serves ONE replica for the
-            // whole kernel keeps its share in shared memory and adds it once, at the end (flush_run_counters)
-            if (defer_counters) {
-                sm.run_cnt[0] += sm.cnt[0]; sm.run_cnt[1] += sm.cnt[1]; sm.run_cnt[2] += sm.cnt[2];
-            } else {
-                if (sm.cnt[0]) atomicAdd(&cx.counters[rep * 4 + 1], (unsigned long long)sm.cnt[0]);
-                if (sm.cnt[1]) atomicAdd(&cx.counters[rep * 4 + 2], (unsigned long long)sm.cnt[1]);
-                if (sm.cnt[2]) atomicAdd(&cx.counters[rep * 4 + 3], (unsigned long long)sm.cnt[2]);
-            }
-#ifdef SEIR_CHECKS
-            if (sm.cnt[3]) atomicOr(&cx.counters[rep * 4 + 0], 4ull);
-#endif
-        }
+        }  // (staged pass)
+        // run counters (list entries visited, infections, hits): 296 CTAs adding to the same three words every pass
+        // queue up at one L2 slice in front of the grid barrier's fence; a CTA that serves ONE replica for the
+        // whole kernel keeps its share in shared memory and adds it once, at the end
+        if (tid == 0) flush_pass_counters(cx, sm, rep, defer_counters);
         __syncthreads();
         SEIR_STAMP(7);
     }
+    return false;
 }
 
 };  // struct Pass

@@ -38,6 +38,15 @@ if os.environ.get("FINE"):
     day = np.zeros(eng.T + 2, dtype=np.int64)
     eng.lib.seir_get_day_times(eng._h, day.ctypes.data)
     names = "grab entry rec tallies dayblk progr+store hhloads pushes ret append".split()
-    for t in range(1, eng.T):
-        rel = [(f[t, k] - day[t]) / 1e3 if f[t, k] > 0 else float("nan") for k in range(10)]
-        print("pass %2d fine: " % t + " ".join("%s=%.2f" % (n, x) for n, x in zip(names, rel)))
+    if os.environ.get("FINE") == "sparse":  # the stamps of sparse_entry (warp 0 of CTA 0)
+        names = "entry+loads dayblk newrec progress hh+knuth gathers tiso hits store dayblk_again".split()
+    if os.environ.get("FINE") == "sparse":  # SM cycle counter of CTA 0 / warp 0, relative to the call of sparse_rounds
+        order = [10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 8, 13]
+        names = "call entry loads-issued dayblk newrec progress hh+knuth gathers tiso hits store end".split()
+        for t in range(1, eng.T):
+            base = f[t, 10]
+            print("pass %2d cycles: " % t + " ".join("%s=%d" % (nm, f[t, k] - base) for nm, k in zip(names, order) if f[t, k] >= base))
+    else:
+        for t in range(1, eng.T):
+            rel = [(f[t, k] - day[t]) / 1e3 if f[t, k] > 0 else float("nan") for k in range(10)]
+            print("pass %2d fine: " % t + " ".join("%s=%.2f" % (n, x) for n, x in zip(names, rel)))

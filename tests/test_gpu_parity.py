@@ -53,6 +53,27 @@ def test_gpu_equals_keyed_oracle(gpu_engine_module, name, mode):
     eng.close()
 
 
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("sparse", ["never", "mixed"])
+def test_staged_and_warp_cooperative_passes_agree(gpu_engine_module, monkeypatch, name, sparse):
+    """The fixtures are small: by default every day of a native run is a warp-cooperative pass (sparse_entry).  The same
+    runs through the staged pass only, and switching between the two from day to day (lists above 40 entries are staged;
+    the holes a warp-cooperative day leaves in the transmitting list are then skipped and squeezed out)."""
+    if sparse == "never":
+        monkeypatch.setenv("SEIR_SPARSE_ROUNDS", "0")
+    else:
+        monkeypatch.setenv("SEIR_SPARSE_MAX", "40")
+    c = util.Case(name)
+    params = c.no_tracing_params()
+    tup, ex, home, init = c.keyed_oracle("native", params)
+    for launch in ("persistent", "per_day"):
+        eng = c.gpu_engine(gpu_engine_module, params, "native", launch=launch)
+        eng.run([c.seed], [home], [init])
+        _compare(eng, tup, ex, c, int(params["T"]))
+        assert eng.counters()["infections"] == int((tup[15] > 0).sum())
+        eng.close()
+
+
 @pytest.mark.parametrize("mode", ["native", "replay"])
 def test_per_day_launch_equals_persistent(gpu_engine_module, mode):
     c = util.Case("italy_seeded")
