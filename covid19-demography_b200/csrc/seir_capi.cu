@@ -112,13 +112,17 @@ __global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_c
     if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
     if (threadIdx.x < 4) sm.cnt[threadIdx.x] = 0;
     int bank_staged = -1;
+    if (threadIdx.x == 0) {
+        Pass<false>::fill_view(cx, sm, t, 0, false);
+        Pass<false>::load_list_lengths(cx, sm, t, 0);
+    }
+    __syncthreads();
     for (; t <= cx.T_loop; ++t) {
+        // (the view and the list lengths of day t are in shared memory: set up before the loop, or in the shadow of the barrier below)
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();  // (a dense day: the other kernel stamps it again)
-        if (threadIdx.x == 0) {
-            Pass<false>::fill_view(cx, sm, t, 0, false);
-            Pass<false>::load_list_lengths(cx, sm, t, 0);
-        }
-        __syncthreads();
+#ifdef SEIR_FINE_STAMPS
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.fine_ns[(size_t)t * 16 + 14] = (unsigned long long)clock64();
+#endif
         const int T = sm.rp.T;
         const bool finalize = t >= T;
         const uint32_t n_new = sm.list_n[0], n_old = finalize ? 0u : sm.list_n[1], n_pk = finalize ? 0u : sm.list_n[2];
@@ -130,13 +134,18 @@ __global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_c
             bank_staged = sm.rp.bank;
             __syncthreads();
         }
+#ifdef SEIR_FINE_STAMPS
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.fine_ns[(size_t)t * 16 + 10] = (unsigned long long)clock64();
+#endif
         Pass<false>::sparse_rounds(cx, sm, t, n_new, n_old, n_pk, cx.list_new + (size_t)(t & 1) * cx.n_pad, cx.list_old + (size_t)(t & 1) * cx.n_pad,
                                    cx.pk_pool + (size_t)(t & (kParkRing - 1)) * cx.n_pad, (int)blockIdx.x, (int)gridDim.x, finalize, false);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             const unsigned long long now = global_timer_ns();
             for (int q = 1; q < 8; ++q) cx.stage_ns[(size_t)t * 8 + q] = now;
         }
-        // the grid barrier (flat form of grid_barrier); this CTA's run counters are counted between its arrival and its poll
+        // The grid barrier (flat form of grid_barrier) with the next pass's set-up in its shadow: between its arrival and
+        // its poll thread 0 does what needs nothing from the other CTAs (this CTA's run counters, tomorrow's view), and as
+        // soon as the poll succeeds it fetches tomorrow's list lengths -- the closing __syncthreads() hands both on.
         __syncthreads();
         if (threadIdx.x == 0) {
             if (t < cx.T_loop) {
@@ -145,13 +154,18 @@ __global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_c
             }
             Pass<false>::flush_pass_counters(cx, sm, 0, true);
             if (t < cx.T_loop) {
+                Pass<false>::fill_view(cx, sm, t + 1, 0, false);
                 unsigned int seen;
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
                 } while (seen < epoch * gridDim.x);
+                Pass<false>::load_list_lengths(cx, sm, t + 1, 0);
             }
         }
         __syncthreads();
+#ifdef SEIR_FINE_STAMPS
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.fine_ns[(size_t)t * 16 + 15] = (unsigned long long)clock64();
+#endif
     }
     if (threadIdx.x < 3 && sm.run_cnt[threadIdx.x]) atomicAdd(&cx.counters[1 + threadIdx.x], (unsigned long long)sm.run_cnt[threadIdx.x]);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -581,6 +595,7 @@ struct seir_handle {
     int prev_T = 0;   // rows of the history set aside by seir_history_preserve (0: none)
     DevBuf<uint32_t> inbox, tally, home, list_old, list_new, list_cnt;
     DevBuf<uint32_t> pk_pool;   // day buckets of the parked agents
+    uint32_t run_serial = 0;    // runs of this handle (DevCtx.run_nonce)
     DevBuf<int> ctl;            // hand-over words of the single-replica day loop's launches
     DevBuf<RepParams> rp;       // per-replica overrides of the current run
     DevBuf<double> bank;        // table sets (seir_set_table_bank); set 0 = the handle's own tables
@@ -1198,6 +1213,8 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
     h->home_valid = home_used;
     fill_ctx(h);
     h->cx.T_loop = T_loop;
+    h->run_serial = (h->run_serial + 1u) & 0x7FFFFFFFu;
+    h->cx.run_nonce = h->run_serial | 0x80000000u;
     h->cx.trace_from = trace_min;  // the first day on which ANY replica traces (each replica records roots from its own day on)
     h->launches = 0;
     // ---- init + day loop, timed on the launching stream

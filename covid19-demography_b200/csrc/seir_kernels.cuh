@@ -203,6 +203,7 @@ struct DevCtx {
                                    // warp-cooperative pass (sparse_pass: one agent per warp, its draws and gathers spread over
                                    // the lanes); 0: never.  env SEIR_SPARSE_ROUNDS
     uint32_t sparse_cap;           // single-replica runs: a day with at most this many list entries is run by seir_sparse_kernel ...
+    uint32_t run_nonce;            // tags the timers a hitter leaves in its infectee's record-to-be (never 0, new for every run)
     int *ctl;                      // [kMaxLaunches + 1] launch k of a run starts at day ctl[k] + 1 and leaves the next day to run in ctl[k + 1]
     uint32_t sparse_max;           // ... and at most this many entries in all (tests: SEIR_SPARSE_MAX makes a small run switch back and forth)
     int dbg_pass;                  // (debug builds with -DSEIR_CTA_STAMPS) the pass whose per-CTA stage stamps go to fine_ns; env SEIR_DEBUG_PASS
@@ -638,15 +639,21 @@ static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSm
     const unsigned long long w = __ldcg(v.winner + i);
     const uint32_t ib = __ldcg(v.inbox + (i >> 4));
     const uint16_t stt = __ldg(cx.stat + i);
+    const uint4 hint = __ldcg(reinterpret_cast<const uint4 *>(v.rec + i));  // the timers a hitter of a warp-cooperative pass left (sparse_entry)
     const uint32_t inf = (uint32_t)(w >> 16), ord = (uint32_t)(w & 0xFFFFu);
     const int tx = t - 1;
-    const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8), 0),
-                                    sm.iso_asym[stt & 127]);
-    const double tact = lognormal_days_ni(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+    uint32_t tiso16, tact16;
+    if (hint.x == (uint32_t)w && hint.y == (uint32_t)((w & ~W_TRACED) >> 32) && hint.w == cx.run_nonce) {
+        tiso16 = hint.z & 0xFFFFu;
+        tact16 = hint.z >> 16;
+    } else {
+        tiso16 = sd_enc16(exp_days_ni(sd_lane(draw_block(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8), 0), sm.iso_asym[stt & 127]));
+        tact16 = sd_enc16(lognormal_days_ni(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma));
+    }
     r.clear();
     r.set_t_exposed((uint16_t)tx);
-    r.set_tt_isolate(sd_enc16(tiso));
-    r.set_tt_activation(sd_enc16(tact));
+    r.set_tt_isolate(tiso16);
+    r.set_tt_activation(tact16);
     r.set_t_end(NEVER);
     r.set_t_q_on(NEVER);
     r.set_stat(stt);
@@ -1074,10 +1081,12 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
     AgentRec r;
     unsigned long long w_self = 0;
     uint32_t ib = 0, stt_new = 0;
+    uint4 hint = make_uint4(0u, 0u, 0u, 0u);
     if (is_new) {
         w_self = __ldcg(v.winner + i);
         ib = __ldcg(v.inbox + (i >> 4));
         stt_new = __ldg(cx.stat + i);
+        hint = __ldcg(reinterpret_cast<const uint4 *>(v.rec + i));  // the timers its infector may have left (see the hits below)
     } else {
         r = load_rec(v.rec + i);
     }
@@ -1092,27 +1101,38 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
         const uint32_t inf = (uint32_t)(w_self >> 16), ord = (uint32_t)(w_self & 0xFFFFu);
         const int tx = t - 1;
         const int age = (int)(stt_new & 127u);
-        const sd_block b = draw_block(v.seed, inf, (uint32_t)tx, SD_SITE_INF, (ord << 8) + lane);
-        const double x1 = SD_SUB(SD_MUL(2.0, sd_lane(b, 0)), 1.0), x2 = SD_SUB(SD_MUL(2.0, sd_lane(b, 1)), 1.0);
-        const double r2 = SD_ADD(SD_MUL(x1, x1), SD_MUL(x2, x2));
-        const bool ok = lane >= 1u && r2 < 1.0 && r2 != 0.0;
-        const double lg = log_ni(lane == 0u ? SD_SUB(1.0, sd_lane(b, 0)) : (ok ? r2 : 1.0));   // one log for all: lane 0 the exponential, the others their try
-        double tiso = SD_RINT(SD_MUL(-lg, sm.iso_asym[age]));
-        double z = ok ? SD_MUL(SD_SQRT(SD_DIV(SD_MUL(-2.0, lg), r2)), x2) : 0.0;
-        const unsigned acc = __ballot_sync(0xFFFFFFFFu, ok);
-        tiso = __shfl_sync(0xFFFFFFFFu, tiso, 0);
-        double tact;
-        if (acc) {
-            z = __shfl_sync(0xFFFFFFFFu, z, __ffs(acc) - 1);
-            const double x = exp_ni(SD_FMA(cx.act_sigma, z, cx.act_mu));
-            tact = x <= 0.0 ? 1.0 : SD_RINT(x);
-        } else {  // (31 rejections in a row: the plain loop goes on from there)
-            tact = lognormal_days_ni(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+        // the winner of the day's hits left the timers in the record's first words (tagged with its key and the run's
+        // nonce): nothing to draw.  Otherwise (a hit by a staged pass, or a later store of an earlier hitter won the race
+        // for the words) they are drawn here, the tries of the polar method side by side on the lanes.
+        uint32_t tiso16, tact16;
+        if (hint.x == (uint32_t)w_self && hint.y == (uint32_t)((w_self & ~W_TRACED) >> 32) && hint.w == cx.run_nonce) {
+            tiso16 = hint.z & 0xFFFFu;
+            tact16 = hint.z >> 16;
+        } else {
+            const sd_block b = draw_block(v.seed, inf, (uint32_t)tx, SD_SITE_INF, (ord << 8) + lane);
+            const double x1 = SD_SUB(SD_MUL(2.0, sd_lane(b, 0)), 1.0), x2 = SD_SUB(SD_MUL(2.0, sd_lane(b, 1)), 1.0);
+            const double r2 = SD_ADD(SD_MUL(x1, x1), SD_MUL(x2, x2));
+            const bool ok = lane >= 1u && r2 < 1.0 && r2 != 0.0;
+            const double lg = log_ni(lane == 0u ? SD_SUB(1.0, sd_lane(b, 0)) : (ok ? r2 : 1.0));   // one log for all: lane 0 the exponential, the others their try
+            double tiso = SD_RINT(SD_MUL(-lg, sm.iso_asym[age]));
+            double z = ok ? SD_MUL(SD_SQRT(SD_DIV(SD_MUL(-2.0, lg), r2)), x2) : 0.0;
+            const unsigned acc = __ballot_sync(0xFFFFFFFFu, ok);
+            tiso = __shfl_sync(0xFFFFFFFFu, tiso, 0);
+            double tact;
+            if (acc) {
+                z = __shfl_sync(0xFFFFFFFFu, z, __ffs(acc) - 1);
+                const double x = exp_ni(SD_FMA(cx.act_sigma, z, cx.act_mu));
+                tact = x <= 0.0 ? 1.0 : SD_RINT(x);
+            } else {  // (31 rejections in a row: the plain loop goes on from there)
+                tact = lognormal_days_ni(v.seed, inf, (uint32_t)tx, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+            }
+            tiso16 = sd_enc16(tiso);
+            tact16 = sd_enc16(tact);
         }
         r.clear();
         r.set_t_exposed((uint16_t)tx);
-        r.set_tt_isolate(sd_enc16(tiso));
-        r.set_tt_activation(sd_enc16(tact));
+        r.set_tt_isolate(tiso16);
+        r.set_tt_activation(tact16);
         r.set_t_end(NEVER);
         r.set_t_q_on(NEVER);
         r.set_stat(stt_new);
@@ -1259,71 +1279,88 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
         uint32_t hits = 0, hits_out = 0;
         const bool first_batch_hh = hh_lane && (w_m == 0ull || wday(w_m) == t) && ((lane & 1u) ? h1 : h0) < p_h;  // :346
         for (uint32_t k0 = 0; k0 == 0u || k0 < kept; k0 += 16u) {
-            // this lane's candidate of the batch
+            // This lane's candidate of the batch.  The gathers of a contact are three dependent round trips (alias row ->
+            // member -> the member's winner word); the infectee's timers (:352-356, :381-385) depend on (i, t, ordinal)
+            // only, so their draws are evaluated BETWEEN the gathers: the warp computes while the loads fly.
             bool cand = false, is_hit = false;
             uint32_t c = 0, ord = 0;
-            int age_c = 0;
-            unsigned long long w_c = 1ull;
+            int age_c = 0, col = 0, al = 0;
+            double x = 0.0, pr = 0.0;
+            unsigned long long w_c = 0ull;
+            sd_block b = blk;
             const uint32_t k = k0 + lane - 16u;
-            if (lane >= 16u && k < kept) {  // :373-375, native: contact age from the alias table of the sender's row, a uniform member
-                const sd_block b = k0 == 0u ? blk : draw_block(v.seed, i, (uint32_t)t, SD_SITE_NPICK, k);
-                const double x = SD_MUL(sd_lane(b, 0), (double)kAges);
-                int col = (int)x;
+            const bool contact = lane >= 16u && k < kept;
+            if (contact) {  // :373-375, native: contact age from the alias table of the sender's row, a uniform member
+                if (k0 != 0u) b = draw_block(v.seed, i, (uint32_t)t, SD_SITE_NPICK, k);
+                x = SD_MUL(sd_lane(b, 0), (double)kAges);
+                col = (int)x;
                 if (col > kAges - 1) col = kAges - 1;
-                const int row = age * kAges + col;
-                const double pr = __ldg(cx.nat_alias_prob + row);
-                const int al = __ldg(cx.nat_alias_idx + row);
-                age_c = (SD_SUB(x, (double)col) < pr) ? col : al;
-                const int g0 = sm.grp_off[age_c], glen = sm.grp_off[age_c + 1] - g0;
-                if (glen != 0) {
-                    c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));
-                    if (SEIR_CHECK((int64_t)c < cx.n, cx, v.rep)) {
-                        w_c = __ldcg(v.winner + c);
-                        cand = true;
-                        ord = SD_ORD_COMM_NATIVE(k);
-                    }
-                }
+                pr = __ldg(cx.nat_alias_prob + age * kAges + col);
+                al = __ldg(cx.nat_alias_idx + age * kAges + col);
+                cand = true;
+                ord = SD_ORD_COMM_NATIVE(k);
             } else if (k0 == 0u && first_batch_hh) {
                 cand = true;
                 c = member;
                 ord = SD_ORD_HH(lane);
                 age_c = (int)(stat_m & 127u);
-                w_c = 0ull;
             }
-            if (__any_sync(0xFFFFFFFFu, cand)) {
-                // the infectee's isolation draw (:352, :381) does not depend on the target's state: it overlaps the gathers
+            if (!__any_sync(0xFFFFFFFFu, cand)) continue;
     SEIR_SFINE(5);
-                const bool home_c = cand && lane >= 16u && at_home(v, c);  // (:375; the household push has no Home test, :346)
-                double tiso = 1.0;
-                if (cand) tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
+            // the isolation draw's logarithm (in the shadow of the alias loads)
+            double lg = 0.0;
+            if (cand) lg = log_ni(SD_SUB(1.0, sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0)));
+            if (contact) {
+                age_c = (SD_SUB(x, (double)col) < pr) ? col : al;
+                const int g0 = sm.grp_off[age_c], glen = sm.grp_off[age_c + 1] - g0;
+                if (glen != 0) c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));
+                else cand = false;
+            }
+            // the activation time the infectee would get from this hit (in the shadow of the member load)
+            double tact = 0.0;
+            if (cand) tact = lognormal_days_ni(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8, cx.act_mu, cx.act_sigma);
+            bool home_c = false;
+            if (contact && cand) {
+                if (SEIR_CHECK((int64_t)c < cx.n, cx, v.rep)) {
+                    w_c = __ldcg(v.winner + c);
+                    home_c = at_home(v, c);  // (:375; the household push has no Home test, :346)
+                } else {
+                    cand = false;
+                }
+            }
+            const double tiso = SD_RINT(SD_MUL(-lg, sm.iso_asym[age_c]));
     SEIR_SFINE(6);
-                is_hit = cand && (w_c == 0ull || wday(w_c) == t) && !home_c;
-                if (is_hit) {
-                    const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
-                    const unsigned long long old = atomicMax(v.winner + c, key);
-                    uint32_t bits = 0;
-                    if (wday(old) != t) {  // first hit of c today
-                        bits = inbox_infected_bit((int)(c & 15));
-                        const uint32_t p = atomicAdd_system(v.next_new_cnt, 1u);
-                        if (SEIR_CHECK((int64_t)p < cx.n_pad, cx, v.rep)) __stcg(v.next_new + p, c);
-                    }
-                    if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
-                    if (bits) atomicOr(v.inbox + (c >> 4), bits);
-                    if (TR && cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387)
-                        const uint32_t e = atomicAdd(cx.log_cnt + v.rep, 1u);
-                        if (e < cx.log_cap) {
-                            const uint32_t prev = atomicExch(cx.log_head + (size_t)v.rep * cx.n_pad + i, e + 1u);
-                            __stcg(cx.log_ent + (size_t)v.rep * cx.log_cap + e, make_uint4(c, prev, ((uint32_t)t << 16) | ord, 0u));
-                        } else {
-                            atomicOr(&cx.counters[v.rep * 4 + 0], 1ull);
-                        }
+            is_hit = cand && (w_c == 0ull || wday(w_c) == t) && !home_c;
+            if (is_hit) {
+                const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
+                // the hit and a slot of tomorrow's list of new infectees are requested together: the slot of a hit that
+                // turns out not to be the first one on c today is left as a hole
+                const unsigned long long old = atomicMax(v.winner + c, key);
+                const uint32_t p = atomicAdd_system(v.next_new_cnt, 1u);
+                const bool first = wday(old) != t;
+                if (SEIR_CHECK((int64_t)p < cx.n_pad, cx, v.rep)) __stcg(v.next_new + p, first ? c : kHole);
+                uint32_t bits = first ? inbox_infected_bit((int)(c & 15)) : 0u;
+                if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
+                if (bits) atomicOr(v.inbox + (c >> 4), bits);
+                // the winner so far leaves the infectee's timers where its record will be built tomorrow (rec[c] is not
+                // in use yet): the builder takes them if the tag is the day's final winner, and draws them itself otherwise
+                if ((old & ~W_TRACED) < key)
+                    __stcg(reinterpret_cast<uint4 *>(v.rec + c),
+                           make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sd_enc16(tiso) | ((uint32_t)sd_enc16(tact) << 16), cx.run_nonce));
+                if (TR && cx.log_ent && ord >= 16u) {  // infected_by[i, k] = c (:387)
+                    const uint32_t e = atomicAdd(cx.log_cnt + v.rep, 1u);
+                    if (e < cx.log_cap) {
+                        const uint32_t prev = atomicExch(cx.log_head + (size_t)v.rep * cx.n_pad + i, e + 1u);
+                        __stcg(cx.log_ent + (size_t)v.rep * cx.log_cap + e, make_uint4(c, prev, ((uint32_t)t << 16) | ord, 0u));
+                    } else {
+                        atomicOr(&cx.counters[v.rep * 4 + 0], 1ull);
                     }
                 }
-    SEIR_SFINE(7);
-                const unsigned hm = __ballot_sync(0xFFFFFFFFu, is_hit);
-                hits += (uint32_t)__popc(hm);
-                hits_out += (uint32_t)__popc(hm & 0xFFFF0000u);
             }
+    SEIR_SFINE(7);
+            const unsigned hm = __ballot_sync(0xFFFFFFFFu, is_hit);
+            hits += (uint32_t)__popc(hm);
+            hits_out += (uint32_t)__popc(hm & 0xFFFF0000u);
         }
         if (hits) {  // :357-359, :386-390
             r.set_n_inf_by(inc_sat16(r.n_inf_by(), hits));

@@ -41,10 +41,10 @@ if os.environ.get("FINE"):
     if os.environ.get("FINE") == "sparse":  # the stamps of sparse_entry (warp 0 of CTA 0)
         names = "entry+loads dayblk newrec progress hh+knuth gathers tiso hits store dayblk_again".split()
     if os.environ.get("FINE") == "sparse":  # SM cycle counter of CTA 0 / warp 0, relative to the call of sparse_rounds
-        order = [10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 8, 13]
-        names = "call entry loads-issued dayblk newrec progress hh+knuth gathers tiso hits store end".split()
+        order = [14, 10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15]
+        names = "top call entry loads-issued dayblk newrec progress hh+knuth gathers tiso hits store end barrier".split()
         for t in range(1, eng.T):
-            base = f[t, 10]
+            base = f[t, 14]
             print("pass %2d cycles: " % t + " ".join("%s=%d" % (nm, f[t, k] - base) for nm, k in zip(names, order) if f[t, k] >= base))
     else:
         for t in range(1, eng.T):
