@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include <vector>
 
 #include "seir_kernels.cuh"
@@ -42,7 +43,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
     const bool defer_counters = cx.n_rep == 1;  // this CTA serves the one replica throughout: its run counters are added once, below
     if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
     int bank_staged = -1;  // the table set whose kept-contact table sits in shared memory
-    for (int t = 1; t <= cx.T_loop; ++t) {
+    // (a sharded run's replicated sparse / dense days may have been run by the single-replica kernels: go on from their day)
+    const int t_first = cx.start_word >= 0 ? __ldcg(cx.ctl + cx.start_word) + 1 : 1;
+    for (int t = t_first; t <= cx.T_loop; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
         if (cx.n_shards > 1 && !sharded_now) {  // (the day's list lengths are the same on every GPU: so is the decision)
             __syncthreads();
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_c
     }
 }
 
-__global__ void __launch_bounds__(kThreads, kMinBlocks) seir_dense_solo_kernel(const __grid_constant__ DevCtx cx, int k, uint32_t yield_below)
+__global__ void __launch_bounds__(kThreads, kMinBlocks) seir_dense_solo_kernel(const __grid_constant__ DevCtx cx, int k, uint32_t yield_below, uint32_t yield_above)
 {
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     int t = __ldcg(cx.ctl + k) + 1;
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_dense_solo_kernel(c
     int bank_staged = -1;
     for (; t <= cx.T_loop; ++t) {
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
-        if (Pass<false>::day_pass<false, true>(cx, sm, t, 0, (int)blockIdx.x, 1, bank_staged, true, false, yield_below)) break;
+        if (Pass<false>::day_pass<false, true>(cx, sm, t, 0, (int)blockIdx.x, 1, bank_staged, true, false, yield_below, yield_above)) break;
         if (t < cx.T_loop) grid_barrier(bar, ++epoch * gridDim.x);
     }
     __syncthreads();
@@ -283,7 +286,7 @@ __global__ void seir_rows_kernel(DevCtx cx, int rep, int t0, int t1, uint8_t *ou
             continue;
         }
         const AgentRec r = load_rec(rec + i);
-        const int t_q2 = (r.flags() & F_TRX) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
+        const int t_q2 = ((r.flags() & F_TRX) && cx.trc) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
         for (int t = t0; t < t1; ++t) out[(size_t)(t - t0) * cx.n_pad + i] = state_on_day(r, t, t_q2);
     }
 }
@@ -337,7 +340,7 @@ __device__ __forceinline__ MatAgent mat_pack(const AgentRec &r, int local, const
     m.b = t_sev | (t_cri << 16);
     m.c = (uint32_t)r.t_end() | ((uint32_t)r.t_q_on() << 16);
     m.d = t_doc | ((uint32_t)(r.state() & 7) << 16) | ((uint32_t)local << 20);
-    m.e = (fl & F_TRX) ? (__ldcg(trc_of_agent) & 0xFFFFu) : 0xFFFFu;  // first day of a traced Q after the end (:72-73)
+    m.e = ((fl & F_TRX) && trc_of_agent) ? (__ldcg(trc_of_agent) & 0xFFFFu) : 0xFFFFu;  // first day of a traced Q after the end (:72-73)
     return m;
 }
 // packed state byte on day t (same function as state_on_day, on the packed thresholds)
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
             if (e < n_inf) {
                 const int local = list[e];
                 const AgentRec r = load_rec(rec + local);
-                ag[k] = mat_pack(r, local, cx.trc + (size_t)rep * cx.n_pad + (g % groups_per_rep) * 512 + local);
+                ag[k] = mat_pack(r, local, cx.trc ? cx.trc + (size_t)rep * cx.n_pad + (g % groups_per_rep) * 512 + local : nullptr);
                 t_first = min(t_first, (int)r.t_exposed());
             }
         }
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
             const int local = list[e];
             const AgentRec r = load_rec(rec + local);
             const int64_t i = (g % groups_per_rep) * 512 + local;
-            const int t_q2 = (r.flags() & F_TRX) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
+            const int t_q2 = ((r.flags() & F_TRX) && cx.trc) ? (int)(__ldcg(cx.trc + (size_t)rep * cx.n_pad + i) & 0xFFFFu) : 0xFFFF;
             for (int t = r.t_exposed(); t < Tr; ++t) hist[(size_t)t * cx.n_pad + i] = state_on_day(r, t, t_q2);
         }
         __syncwarp();
@@ -464,7 +467,7 @@ __global__ void seir_agent_vector_kernel(DevCtx cx, int rep, int which, double *
                 case SEIR_VEC_NUM_INFECTED_BY: v = r.n_inf_by(); break;
                 case SEIR_VEC_TIME_DOCUMENTED: {  // :76, :85: every tracer visit rewrites time_documented
                     uint32_t td = r.t_documented();
-                    if (r.flags() & F_TRX) {
+                    if ((r.flags() & F_TRX) && cx.trc) {
                         const uint32_t last = cx.trc[(size_t)rep * cx.n_pad + i] >> 16;
                         if (last > td) td = last;
                     }
@@ -611,7 +614,7 @@ struct seir_handle {
     DevBuf<unsigned int> barrier;
     // sharded run: one population across the GPUs of a box
     int n_shards = 0, my_shard = 0;
-    uint32_t shard_threshold = 131072;   // list entries of a day from which a sharded run leaves its replicated phase
+    uint32_t shard_threshold = 393216;   // list entries of a day from which a sharded run leaves its replicated phase
     int64_t shard_lo[kMaxShards + 1] = {0};
     void *peer_ptr[kMaxShards][5] = {{nullptr}};   // opened IPC mappings: winner, inbox, list_new, list_cnt, flags
     DevBuf<unsigned int> flags;
@@ -810,6 +813,7 @@ static void fill_ctx(seir_handle *h)
     {   // single-replica runs: the sparse-day kernel (one CTA per SM) takes the days with at most one entry per warp and round
         const unsigned long long cap = (unsigned long long)c.sparse_rounds * (unsigned long long)(h->sms * kWarps);
         c.sparse_cap = (uint32_t)(cap < c.sparse_max ? cap : c.sparse_max);
+        if (h->n_shards > 1 && c.sparse_cap > h->shard_threshold) c.sparse_cap = h->shard_threshold;  // (a sharded run's replicated phase ends there)
     }
     c.n_shards = h->n_shards; c.my_shard = h->my_shard; c.shard_threshold = h->shard_threshold;
     for (int g = 0; g <= kMaxShards; ++g) c.shard_lo[g] = (uint32_t)h->shard_lo[g < h->n_shards ? g : (h->n_shards > 0 ? h->n_shards : 0)];
@@ -1213,8 +1217,11 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
     h->home_valid = home_used;
     fill_ctx(h);
     h->cx.T_loop = T_loop;
-    h->run_serial = (h->run_serial + 1u) & 0x7FFFFFFFu;
-    h->cx.run_nonce = h->run_serial | 0x80000000u;
+    {   // a nonce no other run of this process has used (record memory is recycled between handles, and it is not cleared)
+        static std::atomic<uint32_t> g_serial{0};
+        h->run_serial = (g_serial.fetch_add(1u) + 1u) & 0x7FFFFFFFu;
+        h->cx.run_nonce = h->run_serial | 0x80000000u;
+    }
     h->cx.trace_from = trace_min;  // the first day on which ANY replica traces (each replica records roots from its own day on)
     h->launches = 0;
     // ---- init + day loop, timed on the launching stream
@@ -1254,16 +1261,33 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
     CK(cudaEventRecord(h->ev1, h->stream));
     if (h->prm.launch == SEIR_LAUNCH_PERSISTENT) {
         void *args[] = {&h->cx};
-        const bool solo = !tracing && R == 1 && h->n_shards <= 1 && h->prm.mode == SEIR_MODE_NATIVE && SEIR_FLAT_BARRIER && !getenv("SEIR_NO_SOLO");
+        // single-replica runs without tracing: sparse-day and dense-day kernels in turn (see seir_sparse_kernel); the last
+        // dense launch never hands a day back, so four launches finish the run, and one that finds nothing left to do exits
+        // at once.  A sharded run's REPLICATED phase is such a run on every GPU; its dense launches also stop at the first
+        // day whose lists exceed the shard threshold, and the generic kernel (sharded passes, cross-GPU barrier) goes on.
+        const bool solo = !tracing && R == 1 && h->prm.mode == SEIR_MODE_NATIVE && SEIR_FLAT_BARRIER && !getenv("SEIR_NO_SOLO") &&
+                          !(h->n_shards > 1 && h->shard_threshold == 0u);
+        h->cx.start_word = -1;
         if (solo) {
-            // sparse-day and dense-day kernels in turn (see seir_sparse_kernel); the last launch never hands over, so
-            // four launches always finish the run, and one that finds nothing left to do exits at once
             CK(cudaMemsetAsync(h->ctl.p, 0, (kMaxLaunches + 1) * sizeof(int), h->stream));
             for (int k = 0; k < 4; ++k) {
                 uint32_t yield_below = k == 3 ? 0u : h->cx.sparse_cap / 2u + 1u;  // (0: this launch never hands over)
-                void *args[] = {&h->cx, &k, &yield_below};
+                uint32_t yield_above = h->n_shards > 1 ? h->shard_threshold : 0xFFFFFFFFu;
+                void *args[] = {&h->cx, &k, &yield_below, &yield_above};
                 if (k % 2 == 0) CK(cudaLaunchCooperativeKernel((const void *)seir_sparse_kernel, dim3(h->sms), dim3(kThreads), args, sizeof(PassSmem), h->stream));
                 else CK(cudaLaunchCooperativeKernel((const void *)seir_dense_solo_kernel, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
+                ++h->launches;
+                if (getenv("SEIR_DEBUG_SYNC")) {  // (debugging: which launch faults)
+                    const cudaError_t e = cudaStreamSynchronize(h->stream);
+                    if (e != cudaSuccess) { char b[128]; snprintf(b, sizeof b, "day-loop launch %d failed: %s", k, cudaGetErrorString(e)); return fail(b); }
+                }
+            }
+            if (h->n_shards > 1) {
+                h->cx.start_word = 4;
+                h->cx.barrier = h->barrier.p + 5 * kBarStride;  // (its own barrier words: launches 0..3 counted in words 1..4)
+                void *args[] = {&h->cx};
+                CK(cudaLaunchCooperativeKernel((const void *)seir_persistent_kernel<false>, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
+                h->cx.barrier = h->barrier.p;
                 ++h->launches;
             }
         } else {

@@ -203,6 +203,7 @@ struct DevCtx {
                                    // warp-cooperative pass (sparse_pass: one agent per warp, its draws and gathers spread over
                                    // the lanes); 0: never.  env SEIR_SPARSE_ROUNDS
     uint32_t sparse_cap;           // single-replica runs: a day with at most this many list entries is run by seir_sparse_kernel ...
+    int start_word;                // the generic persistent kernel starts at day ctl[start_word] + 1 (-1: day 1)
     uint32_t run_nonce;            // tags the timers a hitter leaves in its infectee's record-to-be (never 0, new for every run)
     int *ctl;                      // [kMaxLaunches + 1] launch k of a run starts at day ctl[k] + 1 and leaves the next day to run in ctl[k + 1]
     uint32_t sparse_max;           // ... and at most this many entries in all (tests: SEIR_SPARSE_MAX makes a small run switch back and forth)
@@ -1504,10 +1505,12 @@ static __device__ __noinline__ void flush_pass_counters(const DevCtx &cx, PassSm
 // (inline_sparse: a sparse day runs as a warp-cooperative pass inside this kernel -- replica ensembles, tracing builds and
 // sharded runs; the single-replica day loop hands its sparse days to seir_sparse_kernel instead and keeps this code out)
 // (can_yield: the single-replica dense-day kernel; returns true WITHOUT touching the day when its lists have shrunk to
-// fewer than yield_below entries (0: never) -- the sparse-day kernel takes over)
+// fewer than yield_below entries (0: never) or, in a sharded run's replicated phase, more than yield_above (the generic
+// kernel takes over: sharded passes) -- the sparse-day kernel takes over)
 template <bool inline_sparse, bool can_yield = false>
 static __device__ bool day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_slot, int my_part, int reps_per_sweep,
-                                int &bank_staged, bool defer_counters = false, bool sharded_now = false, uint32_t yield_below = 0u)
+                                int &bank_staged, bool defer_counters = false, bool sharded_now = false, uint32_t yield_below = 0u,
+                                uint32_t yield_above = 0xFFFFFFFFu)
 {
     const int tid = threadIdx.x;
     bool stamped = false;
@@ -1584,7 +1587,10 @@ static __device__ bool day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         // yesterday's bucket has been consumed: its chunks go back to the free ring (one warp of the replica's first CTA;
         // today's allocations cannot reach these ring slots: the ring holds twice the chunks that can be in use)
         // (pass T only finalises: the agents infected on the last day get their records, nobody else is visited)
-        if (can_yield && sm.list_n[0] + sm.list_n[1] + sm.list_n[2] < yield_below) return true;  // (grid-uniform)
+        if (can_yield) {
+            const uint32_t total = sm.list_n[0] + sm.list_n[1] + sm.list_n[2];
+            if (total < yield_below || total > yield_above) return true;
+        }  // (grid-uniform)
         const uint32_t n_new = sm.list_n[0], n_old = finalize ? 0u : sm.list_n[1], n_pk = finalize ? 0u : sm.list_n[2];
         // a SPARSE day: one warp per entry (sparse_rounds); the staged rounds below serve the days whose lists outgrow the warps
         const bool sparse = inline_sparse && cx.sparse_rounds != 0u && cx.mode == SEIR_MODE_NATIVE && !sharded_now && !(TR && v.tracing) &&
@@ -1679,6 +1685,11 @@ static __device__ bool day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
                     own = cx.n_shards <= 1 || (i >= cx.shard_lo[cx.my_shard] && i < cx.shard_lo[cx.my_shard + 1]);
                     if ((own || !sharded_now) && SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots && (int64_t)(n_new + n_old + n_pk) <= cx.n, cx, rep))
                         keep = stage_a_entry(cx, sm, slot, i, is_new, t, finalize, own);
+                    // (the first sharded day: an agent of another GPU that was infected on the last replicated day is in
+                    // everybody's list; its owner steps it, the others complete its record -- their inbox bit says "infected",
+                    // and the output kernels read the record of every such agent)
+                    else if (is_new && !own && SEIR_CHECK((int64_t)i < cx.n && slot < (uint32_t)kSlots, cx, rep))
+                        stage_a_entry(cx, sm, slot, i, true, t, true, false);
                     SEIR_FINE(8);
                 }
                 append_survivors(sm, keep, i);

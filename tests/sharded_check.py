@@ -24,8 +24,10 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("gloo")
     failures = 0
-    for name, modes in (("italy_seeded", ("native", "replay")), ("ensemble_italy_n20000", ("native",)),
-                        ("china_default", ("native",))):
+    cases = (("italy_seeded", ("native", "replay")), ("ensemble_italy_n20000", ("native",)), ("china_default", ("native",)))
+    if len(sys.argv) > 1:  # (debugging: only the named cases)
+        cases = tuple(c_ for c_ in cases if c_[0] in sys.argv[1:])
+    for name, modes in cases:
         c = util.Case(name)
         params = c.no_tracing_params()
         T = int(params["T"])
