@@ -150,20 +150,18 @@ __global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_c
         // its poll thread 0 does what needs nothing from the other CTAs (this CTA's run counters, tomorrow's view), and as
         // soon as the poll succeeds it fetches tomorrow's list lengths -- the closing __syncthreads() hands both on.
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (t < cx.T_loop) {
-                ++epoch;
-                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
-            }
+        if (t < cx.T_loop) ++epoch;
+        if (threadIdx.x == 0 && t < cx.T_loop) {
+            unsigned int seen;
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(bar), "r"(1u) : "memory");
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+            } while (seen < epoch * gridDim.x);
+            Pass<false>::load_list_lengths(cx, sm, t + 1, 0);
+        }
+        if (threadIdx.x == 32) {  // (another warp: in the shadow of thread 0's round trips even in the last CTA to arrive)
             Pass<false>::flush_pass_counters(cx, sm, 0, true);
-            if (t < cx.T_loop) {
-                Pass<false>::fill_view(cx, sm, t + 1, 0, false);
-                unsigned int seen;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-                } while (seen < epoch * gridDim.x);
-                Pass<false>::load_list_lengths(cx, sm, t + 1, 0);
-            }
+            if (t < cx.T_loop) Pass<false>::fill_view(cx, sm, t + 1, 0, false);
         }
         __syncthreads();
 #ifdef SEIR_FINE_STAMPS

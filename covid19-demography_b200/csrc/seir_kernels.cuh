@@ -1440,8 +1440,9 @@ static __device__ __noinline__ void fill_view(const DevCtx &cx, PassSmem &sm, in
 {
     const size_t lrow = ((size_t)rep * 2 + ((t + 1) & 1)) * cx.n_pad;
     uint32_t *cnt_old = cx.list_cnt + (size_t)rep * 3 * (cx.T + 2), *cnt_new = cnt_old + (cx.T + 2), *cnt_pk = cnt_new + (cx.T + 2);
-    if (sm.rp_rep != rep) {  // (one request per CTA and replica: the overrides do not change during a launch)
+    if (sm.rp_rep != rep) {  // (one request per CTA and replica: the overrides and the seed do not change during a launch)
         sm.rp = cx.rp[rep];
+        sm.v.seed = cx.seeds[rep];
         sm.rp_rep = rep;
     }
     const RepParams rp = sm.rp;
@@ -1460,7 +1461,6 @@ static __device__ __noinline__ void fill_view(const DevCtx &cx, PassSmem &sm, in
     sm.v.pk_cnt = cnt_pk;
     sm.v.pk_pool = cx.pk_pool + (size_t)rep * kParkRing * cx.n_pad;
     sm.v.n_pad_m1 = (uint32_t)(cx.n_pad - 1);
-    sm.v.seed = cx.seeds[rep];
     sm.v.home_on = rp.t_stayhome >= 1 && t >= rp.t_stayhome;          // :243-244
     sm.v.phase = (rp.t_lockdown >= 1 && t >= rp.t_lockdown) ? 1 : 0;  // :234-240
     sm.v.rep = rep;
@@ -1569,7 +1569,8 @@ static __device__ bool day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
         const uint32_t *cur_pk = cx.pk_pool + ((size_t)rep * kParkRing + (size_t)(t & (kParkRing - 1))) * cx.n_pad;  // today's bucket
         // today's list lengths: ONE request per CTA and counter (a load by every warp of the grid is 4 736 requests
         // for the same L2 line, which its slice serves one at a time: 2 us at the start of every pass)
-        if (tid < 3) sm.list_n[tid] = __ldcg((tid == 0 ? cnt_new : tid == 1 ? cnt_old : cnt_pk) + t);
+        // (by another warp than thread 0's: its requests fly while the view is being filled)
+        if (tid >= 64 && tid < 67) sm.list_n[tid - 64] = __ldcg((tid == 64 ? cnt_new : tid == 65 ? cnt_old : cnt_pk) + t);
         if (tid >= 32 && tid < 36) sm.cnt[tid - 32] = 0;
         __syncthreads();
         const RepParams rp = sm.rp;
