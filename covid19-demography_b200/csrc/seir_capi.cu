@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
 // is a round trip to L2 behind the barrier's invalidated L1 -- a barrier over 148 CTAs, a code footprint of a few KB.
 // seir_dense_solo_kernel takes the others (staged passes, two CTAs per SM).  Each leaves the first day it does not take
 // in ctl[k + 1] and the host has queued the next launch already: no host round trip at a hand-over.
-__global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_constant__ DevCtx cx, int k)
+__global__ void __launch_bounds__(kSparseThreads, 1) seir_sparse_kernel(const __grid_constant__ DevCtx cx, int k)
 {
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
     int t = __ldcg(cx.ctl + k) + 1;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) seir_sparse_kernel(const __grid_c
         if (blockIdx.x == 0 && threadIdx.x == 0) cx.stage_ns[(size_t)t * 8 + 0] = global_timer_ns();
         if (bank_staged != sm.rp.bank) {
             const double *src = cx.bank + (size_t)sm.rp.bank * kBankStride + kBankNatEn;
-            for (int q = threadIdx.x; q < 4 * kAges; q += kThreads) sm.nat_enlam[q] = src[q];
+            for (int q = threadIdx.x; q < 4 * kAges; q += kSparseThreads) sm.nat_enlam[q] = src[q];
             bank_staged = sm.rp.bank;
             __syncthreads();
         }
@@ -218,8 +218,19 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_trace_kernel(const 
 }
 
 // winner := 0, inbox := 0 (the only per-run state that must be cleared; records are built on infection)
-__global__ void seir_init_state_kernel(DevCtx cx)
+// (and the run's small words -- tallies, run counters, list lengths, barrier and hand-over words: one launch instead of
+// five memsets in front of it)
+__global__ void seir_init_state_kernel(DevCtx cx, uint32_t *barrier_words, int n_barrier_words)
 {
+    {
+        const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+        const int64_t n_tal = (int64_t)cx.n_rep * cx.T * TAL_ROWS * kAges, n_cnt = (int64_t)cx.n_rep * 3 * (cx.T + 2);
+        for (int64_t k = tid; k < n_tal; k += nth) cx.tally[k] = 0u;
+        for (int64_t k = tid; k < n_cnt; k += nth) cx.list_cnt[k] = 0u;
+        for (int64_t k = tid; k < (int64_t)cx.n_rep * 4; k += nth) cx.counters[k] = 0ull;
+        for (int64_t k = tid; k < n_barrier_words; k += nth) barrier_words[k] = 0u;
+        for (int64_t k = tid; k <= kMaxLaunches; k += nth) cx.ctl[k] = 0;
+    }
     const int64_t nvec = cx.n_pad / kVec;
     const int64_t total = nvec * cx.n_rep;
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -809,7 +820,7 @@ static void fill_ctx(seir_handle *h)
     { const char *sr = getenv("SEIR_SPARSE_ROUNDS"); c.sparse_rounds = sr ? (uint32_t)atoi(sr) : 1u; }  // 0: staged passes only
     { const char *sx = getenv("SEIR_SPARSE_MAX"); c.sparse_max = sx ? (uint32_t)atoi(sx) : 0xFFFFFFFFu; }
     {   // single-replica runs: the sparse-day kernel (one CTA per SM) takes the days with at most one entry per warp and round
-        const unsigned long long cap = (unsigned long long)c.sparse_rounds * (unsigned long long)(h->sms * kWarps);
+        const unsigned long long cap = (unsigned long long)c.sparse_rounds * (unsigned long long)(h->sms * (kSparseThreads / 32));
         c.sparse_cap = (uint32_t)(cap < c.sparse_max ? cap : c.sparse_max);
         if (h->n_shards > 1 && c.sparse_cap > h->shard_threshold) c.sparse_cap = h->shard_threshold;  // (a sharded run's replicated phase ends there)
     }
@@ -1224,10 +1235,6 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
     h->launches = 0;
     // ---- init + day loop, timed on the launching stream
     CK(cudaEventRecord(h->ev0, h->stream));
-    CK(cudaMemsetAsync(h->tally.p, 0, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, h->stream));
-    CK(cudaMemsetAsync(h->counters.p, 0, (size_t)R * 4 * 8, h->stream));
-    CK(cudaMemsetAsync(h->barrier.p, 0, kBarStride * (2 + 64) * 4, h->stream));
-    CK(cudaMemsetAsync(h->list_cnt.p, 0, (size_t)R * 3 * (h->prm.T + 2) * 4, h->stream));
     const bool tracing = h->cx.trace_from >= 1;
     if (tracing) {
         CK(cudaMemsetAsync(h->log_cnt.p, 0, (size_t)R * 4, h->stream));
@@ -1243,7 +1250,7 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
         }
         h->cx.tday0 = (h->trace_runs & 0xFFFFFu) << 12;
     }
-    seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx);
+    seir_init_state_kernel<<<h->sms * 8, 256, 0, h->stream>>>(h->cx, h->barrier.p, (int)(kBarStride * (2 + 64)));
     ++h->launches;
     if (any_keyed) {  // the prologue's picks (:176-187), made on the device
         dim3 g(h->sms * 2 > 64 ? 64 : h->sms * 2, R);
@@ -1267,12 +1274,11 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
                           !(h->n_shards > 1 && h->shard_threshold == 0u);
         h->cx.start_word = -1;
         if (solo) {
-            CK(cudaMemsetAsync(h->ctl.p, 0, (kMaxLaunches + 1) * sizeof(int), h->stream));
             for (int k = 0; k < 4; ++k) {
                 uint32_t yield_below = k == 3 ? 0u : h->cx.sparse_cap / 2u + 1u;  // (0: this launch never hands over)
                 uint32_t yield_above = h->n_shards > 1 ? h->shard_threshold : 0xFFFFFFFFu;
                 void *args[] = {&h->cx, &k, &yield_below, &yield_above};
-                if (k % 2 == 0) CK(cudaLaunchCooperativeKernel((const void *)seir_sparse_kernel, dim3(h->sms), dim3(kThreads), args, sizeof(PassSmem), h->stream));
+                if (k % 2 == 0) CK(cudaLaunchCooperativeKernel((const void *)seir_sparse_kernel, dim3(h->sms), dim3(kSparseThreads), args, sizeof(PassSmem), h->stream));
                 else CK(cudaLaunchCooperativeKernel((const void *)seir_dense_solo_kernel, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
                 ++h->launches;
                 if (getenv("SEIR_DEBUG_SYNC")) {  // (debugging: which launch faults)

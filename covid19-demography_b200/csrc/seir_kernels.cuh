@@ -373,6 +373,10 @@ constexpr int kDrawCap = 2 * kSlots / SEIR_QUEUE_DIV;                 // draw-it
 #define SEIR_QUEUE_DRAWS 1    // 1: household draw blocks / kept-contact counts run in stage D; 0: in place in stage A
 #endif
 constexpr int kWarps = kThreads / 32;
+#ifndef SEIR_SPARSE_THREADS
+#define SEIR_SPARSE_THREADS 512
+#endif
+constexpr int kSparseThreads = SEIR_SPARSE_THREADS;  // threads per CTA of seir_sparse_kernel (one CTA per SM: 128 registers per thread)
 constexpr int kOutOld = kSlots;                      // staged survivors that may transmit tomorrow
 constexpr int kOutNew = kSlots;                      // staged new infectees
 static_assert(kSlots <= 65536, "slot ids travel in 16 bits");
@@ -1406,7 +1410,7 @@ static __device__ __noinline__ void sparse_rounds(const DevCtx &cx, PassSmem &sm
     uint32_t site, sub;
     sparse_lane_role(lane, site, sub);
     const uint32_t count = n_pk + n_new + n_old;
-    for (uint32_t e = warp * (uint32_t)bpr + (uint32_t)my_part; e < count; e += (uint32_t)(kWarps * bpr)) {
+    for (uint32_t e = warp * (uint32_t)bpr + (uint32_t)my_part; e < count; e += (blockDim.x >> 5) * (uint32_t)bpr) {
         const int kind = e < n_pk ? 0 : e < n_pk + n_new ? 1 : 2;
         const uint32_t idx = kind == 0 ? e : kind == 1 ? e - n_pk : e - n_pk - n_new;
         const uint32_t i = __ldcg((kind == 0 ? cur_pk : kind == 1 ? cur_new : cur_old) + idx);
