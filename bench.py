@@ -15,7 +15,7 @@ value      device time of the whole run (state init + day loop + history), CUDA 
 e2e        the same through the C ABI with HOST buffers: per-run inputs (Home_real, initial cases,
            seed) copied from pinned host memory, the [T,9,101] tallies and counters read back, wall clock.
 roofline   the algorithmic bytes of SURVEY.md section 8d (sum_t 2n + 16 A(t-1) + 64 I(t)) against the measured HBM
-           peak over the WHOLE device step (init + seir_persistent_kernel + seir_materialize_kernel): the 2n term is
+           peak over the WHOLE device step (init + day-loop kernels + seir_materialize_kernel): the 2n term is
            paid by the materialise kernel, the 16 A + 64 I terms by the day loop, so neither kernel alone owns the
            figure; the per-kernel split is in roofline.kernels.
 config     further legs, each with its own numbers: c1, c4_like, c5_like (replica ensembles), c3_single_gpu, the
@@ -389,7 +389,7 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic if args.traffic is not None else measured_traffic("step"),
-                         "kernel": "device step = seir_init_* + seir_persistent_kernel + seir_materialize_kernel"
+                         "kernel": "device step = seir_init_* + day loop (seir_sparse_kernel + seir_dense_solo_kernel in turn) + seir_materialize_kernel"
                                    if args.launch == "persistent" else "seir_day_kernel x T + seir_materialize_kernel",
                          "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": balg / K, "active_agent_days": a_sum / K, "infections": i_sum / K,
@@ -397,9 +397,9 @@ def run_gpu_arm(args):
                                  "paid once by seir_materialize_kernel as a streaming T x n byte write, the 16 A + 64 I terms "
                                  "by the event-driven day loop, which is latency-bound (L2-resident working set)",
                          "kernels": {
-                             "seir_persistent_kernel": {"ms": local_ms["loop"] / K, "algorithmic_bytes": day_bytes,
+                             "day_loop": {"kernels": "seir_sparse_kernel + seir_dense_solo_kernel in turn (single replica); seir_persistent_kernel for replica ensembles, tracing and sharded runs", "ms": local_ms["loop"] / K, "algorithmic_bytes": day_bytes,
                                                         "GBps": day_bytes / (local_ms["loop"] / K / 1e3) / 1e9,
-                                                        "bound": "latency (dependent L2 round trips per day, one grid barrier per day)",
+                                                        "bound": "latency (one warp's dependent chain per sparse day, five staged CTA phases per dense day, one grid barrier per day)",
                                                         "frac_if_charged_all_bytes": balg / K / (local_ms["loop"] / K / 1e3) / 1e9 / peak,
                                                         "dram_bytes_per_launch_ncu": measured_traffic("seir_persistent_kernel")},
                              "seir_materialize_kernel": {"ms": local_ms["mat"] / K, "algorithmic_bytes": row_bytes,

@@ -1,6 +1,7 @@
-for v in "" "-DSEIR_THREADS=1024 -DSEIR_MIN_BLOCKS=1" "-DSEIR_THREADS=256 -DSEIR_MIN_BLOCKS=4" "-DSEIR_THREADS=384 -DSEIR_MIN_BLOCKS=2" "-DSEIR_THREADS=768 -DSEIR_MIN_BLOCKS=1"; do
+# usage: bash profiles/geometry_variants.sh "<nvcc flags>" ...   (each variant: C2 x4 runs + stress)
+for v in "$@"; do
   echo "=== variant: $v"
-  SEIR_NVCC_EXTRA="$v" python covid19-demography_b200/build.py --force > /dev/null 2>&1
+  SEIR_NVCC_EXTRA="$v" python covid19-demography_b200/build.py --force > /dev/null 2>&1 || echo "BUILD FAILED"
   python profiles/run_case.py c2 4 2>&1 | tail -3
   python profiles/run_case.py stress 3 2>&1 | tail -1
 done

@@ -52,5 +52,5 @@ def test_gpu_arm_line():
         assert cfg[leg]["agent_days_per_sec"] > 0 and cfg[leg]["sim_runs_per_hour_e2e"] > 0 and 0 < cfg[leg]["roofline_frac"] < 1.5
     assert cfg["dropin_run_model"]["warm_call_ms"] < cfg["dropin_run_model"]["first_call_ms"]
     k = r["kernels"]
-    assert abs(k["seir_persistent_kernel"]["algorithmic_bytes"] + k["seir_materialize_kernel"]["algorithmic_bytes"]
+    assert abs(k["day_loop"]["algorithmic_bytes"] + k["seir_materialize_kernel"]["algorithmic_bytes"]
                - r["algorithmic_bytes_per_launch"]) < 1e-6 * r["algorithmic_bytes_per_launch"]
