@@ -27,7 +27,12 @@ def build(case, n=10_000_000, replicas=1):
         p["p_documented_in_mild"] = 0.0
         p["t_lockdown"] = 1.0e6
         n_init = 500
-    hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
+    # POP=census: the census-driven population bench.py runs on (default here: the census-free generator of round 1,
+    # so that the numbers compare with profiles/r01/)
+    if os.environ.get("POP", "synthetic") == "census":
+        hh, age, diab, hyp, groups = bench.make_population(n)
+    else:
+        hh, age, diab, hyp, groups = population.synthetic_population(n, seed=1)
     tb = tables.build_tables(tabs["contact_matrix"], np.array([len(g) for g in groups]), tables.params_to_dict(p),
                              tabs["mean_time_to_isolate_factor"], tabs["p_mild_severe"], tabs["p_severe_critical"],
                              tabs["p_critical_death"], with_replay=False)
