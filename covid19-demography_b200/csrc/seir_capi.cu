@@ -61,6 +61,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_persistent_kernel(c
             }
             __syncthreads();
         }
+        if (sharded_now) {  // every GPU's copy of the infection days, from the owners' lists of today's new infectees
+            if (xday_refresh(cx, sm, t)) grid_barrier(cx.barrier, ++epoch * gridDim.x);
+        }
         Pass<TR>::template day_pass<true>(cx, sm, t, my_slot, my_part, reps_per_sweep, bank_staged, defer_counters, sharded_now);
         if (t < cx.T_loop) {
             if (sharded_now) {
@@ -239,6 +242,11 @@ __global__ void seir_init_state_kernel(DevCtx cx, uint32_t *barrier_words, int n
         uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + g * kVec);
 #pragma unroll
         for (int k = 0; k < 8; ++k) __stcs(wz + k, z);
+        if (cx.n_shards > 1) {  // (the infection days every GPU of a sharded run keeps)
+            uint4 *xz = reinterpret_cast<uint4 *>(cx.xday + g * kVec);
+            __stcs(xz, z);
+            __stcs(xz + 1, z);
+        }
         if (cx.log_head) {  // tracing state: log heads (the tracer's marks are stamped with the run number)
             uint4 *hz = reinterpret_cast<uint4 *>(cx.log_head + g * kVec);
 #pragma unroll
@@ -308,6 +316,7 @@ __global__ void seir_init_infected_kernel(DevCtx cx, const int32_t *init_ids, co
     for (int64_t k = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = init_ids[k];
         const bool own = cx.n_shards <= 1 || (a >= cx.shard_lo[cx.my_shard] && a < cx.shard_lo[cx.my_shard + 1]);
+        if (cx.n_shards > 1) cx.xday[(size_t)rep * cx.n_pad + a] = 1;  // infected on day 0 (every GPU of a sharded run keeps the whole array)
         if (!own && cx.shard_threshold == 0u) continue;  // another GPU's agent (a run that starts replicated steps it here too)
         const uint64_t seed = cx.seeds[rep];
         AgentRec r;
@@ -618,6 +627,7 @@ struct seir_handle {
     bool home_valid = false;           // the home bitmaps hold the last run's picks
     int history_mode = SEIR_HISTORY_EAGER;
     DevBuf<unsigned long long> winner, counters, day_ns, stage_ns, fine_ns;
+    DevBuf<uint16_t> xday;
     DevBuf<AgentRec> rec;
     DevBuf<uint64_t> seeds;
     DevBuf<unsigned int> barrier;
@@ -625,7 +635,7 @@ struct seir_handle {
     int n_shards = 0, my_shard = 0;
     uint32_t shard_threshold = 393216;   // list entries of a day from which a sharded run leaves its replicated phase
     int64_t shard_lo[kMaxShards + 1] = {0};
-    void *peer_ptr[kMaxShards][5] = {{nullptr}};   // opened IPC mappings: winner, inbox, list_new, list_cnt, flags
+    void *peer_ptr[kMaxShards][SEIR_SHARD_HANDLES] = {{nullptr}};   // opened IPC mappings: winner, inbox, list_new, list_cnt, flags, xday
     DevBuf<unsigned int> flags;
     unsigned int run_count = 0;
     unsigned int epoch_base = 0, epoch_next = 0;   // day-barrier epochs of the sharded runs: a running counter (monotone whatever T does)
@@ -813,11 +823,13 @@ static void fill_ctx(seir_handle *h)
     c.nat_enlam = h->tables.p + kTabNatEn; c.nat_alias_prob = h->tables.p + kTabAliasP;
     c.nat_alias_idx = h->alias_idx.p;
     c.enlam = h->replay_tables ? h->enlam.p : nullptr;
-    c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.rec = h->rec.p; c.tally = h->tally.p;
+    c.hist = h->hist.p; c.inbox = h->inbox.p; c.winner = h->winner.p; c.xday = h->xday.p; c.rec = h->rec.p; c.tally = h->tally.p;
     c.home = h->home.p; c.seeds = h->seeds.p; c.counters = h->counters.p; c.barrier = h->barrier.p;
     c.day_ns = h->day_ns.p; c.stage_ns = h->stage_ns.p; c.fine_ns = h->fine_ns.p;
     { const char *dp = getenv("SEIR_DEBUG_PASS"); c.dbg_pass = dp ? atoi(dp) : -1; }
-    { const char *sr = getenv("SEIR_SPARSE_ROUNDS"); c.sparse_rounds = sr ? (uint32_t)atoi(sr) : 1u; }  // 0: staged passes only
+    { const char *sr = getenv("SEIR_SPARSE_ROUNDS"); c.sparse_rounds = sr ? (uint32_t)atoi(sr) : 2u; }  // 0: staged passes only
+    // (2: a day with up to two entries per warp is still cheaper as two warp-cooperative rounds, 14 us, than as a staged pass, 18 us:
+    //  profiles/r02/experiments.md)
     { const char *sx = getenv("SEIR_SPARSE_MAX"); c.sparse_max = sx ? (uint32_t)atoi(sx) : 0xFFFFFFFFu; }
     {   // single-replica runs: the sparse-day kernel (one CTA per SM) takes the days with at most one entry per warp and round
         const unsigned long long cap = (unsigned long long)c.sparse_rounds * (unsigned long long)(h->sms * (kSparseThreads / 32));
@@ -833,6 +845,7 @@ static void fill_ctx(seir_handle *h)
         c.peer_list_new[g] = mine ? h->list_new.p : (uint32_t *)h->peer_ptr[g][2];
         c.peer_list_cnt[g] = mine ? h->list_cnt.p : (uint32_t *)h->peer_ptr[g][3];
         c.peer_flags[g] = mine ? h->flags.p : (unsigned int *)h->peer_ptr[g][4];
+        c.peer_xday[g] = mine ? h->xday.p : (uint16_t *)h->peer_ptr[g][5];
     }
     c.epoch_base = h->epoch_base;
     const bool tr = tracing_can_start(p) && h->trace_alloc;
@@ -1029,9 +1042,10 @@ int seir_shard_export(seir_handle *h, uint8_t *handles_out)
 {
     if (!h || !handles_out) return fail("seir_shard_export: NULL argument");
     CK(cudaSetDevice(h->device));
-    void *ptrs[5] = {h->winner.p, h->inbox.p, h->list_new.p, h->list_cnt.p, h->flags.p};
+    CK(h->xday.alloc((size_t)h->n_rep * h->n_pad));  // (only a sharded run keeps the infection days: 2 B per agent)
+    void *ptrs[SEIR_SHARD_HANDLES] = {h->winner.p, h->inbox.p, h->list_new.p, h->list_cnt.p, h->flags.p, h->xday.p};
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
-    for (int k = 0; k < 5; ++k) {
+    for (int k = 0; k < SEIR_SHARD_HANDLES; ++k) {
         cudaIpcMemHandle_t mh;
         CK(cudaIpcGetMemHandle(&mh, ptrs[k]));
         memcpy(handles_out + 64 * k, &mh, 64);
@@ -1058,9 +1072,9 @@ int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_ha
     }
     for (int g = 0; g < world; ++g) {
         if (g == rank) continue;
-        for (int k = 0; k < 5; ++k) {
+        for (int k = 0; k < SEIR_SHARD_HANDLES; ++k) {
             cudaIpcMemHandle_t mh;
-            memcpy(&mh, all_handles + ((size_t)g * 5 + k) * 64, 64);
+            memcpy(&mh, all_handles + ((size_t)g * SEIR_SHARD_HANDLES + k) * 64, 64);
             CK(cudaIpcOpenMemHandle(&h->peer_ptr[g][k], mh, cudaIpcMemLazyEnablePeerAccess));
         }
     }
@@ -1694,10 +1708,10 @@ void seir_destroy(seir_handle *h)
     cudaSetDevice(h->device);
     h->stat.release(); h->grp_off.release(); h->grp_members.release(); h->init_ids.release(); h->init_off.release();
     h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release();
-    h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release();
+    h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release(); h->xday.release();
     h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release(); h->ctl.release();
     for (int g = 0; g < kMaxShards; ++g)
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < SEIR_SHARD_HANDLES; ++k)
             if (h->peer_ptr[g][k]) cudaIpcCloseMemHandle(h->peer_ptr[g][k]);
     h->flags.release();
     h->list_old.release(); h->list_new.release(); h->list_cnt.release(); h->day_ns.release();

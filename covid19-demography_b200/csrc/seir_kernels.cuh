@@ -6,6 +6,10 @@
 //   winner[n]      u64           0 = never hit; else day<<48 | infector<<16 | event ordinal of the LAST hit
 //                                in the reference's agent order (atomicMax).  winner is also the
 //                                susceptibility oracle: S[t-1,c]  <=>  winner[c]==0 || day(winner[c])==t.
+//   xday[n]        u16           sharded runs only: day of infection + 1 (0 = never).  EVERY GPU holds a full copy, so the susceptibility
+//                                test of a community contact, S[t-1,c] <=> xday[c]==0 || xday[c]==t+1, never leaves the GPU: a first
+//                                hitter writes its own copy, and every morning each GPU completes its copy from the owners' lists of
+//                                the day's new infectees (xday_refresh)
 //   inbox[n/16]    u32           2 bits per agent: "ever infected", "an isolation draw of a hit was 0 => Q" (:353-354)
 //   rec[n]         32 B          one sector per EVER-INFECTED agent: state byte, static word, every event day and
 //                                drawn time-to-event; the whole T-day history of the agent is a function of it.
@@ -162,6 +166,7 @@ struct DevCtx {
     uint8_t *hist;                 // [rep][T][n_pad]
     uint32_t *inbox;               // [rep][n_pad/16]
     unsigned long long *winner;    // [rep][n_pad]
+    uint16_t *xday;                // [rep][n_pad] day of infection + 1 (0: never infected)
     AgentRec *rec;                 // [rep][n_pad]
     uint32_t *list_old;            // [rep][2][n_pad]  agents that transmitted yesterday and may transmit today
     uint32_t *list_new;            // [rep][2][n_pad]  agents infected yesterday (record not built yet)
@@ -219,6 +224,7 @@ struct DevCtx {
     uint32_t *peer_inbox[kMaxShards];              // an agent's winner / inbox / list entries live on its owner
     uint32_t *peer_list_new[kMaxShards];
     uint32_t *peer_list_cnt[kMaxShards];
+    uint16_t *peer_xday[kMaxShards];               // every GPU's copy of xday: the first hitter of an agent stores into all of them
     unsigned int *peer_flags[kMaxShards];          // [kMaxShards + 2] per GPU: day epochs of the peers, release word, error word
     unsigned int epoch_base;                       // run number * (T + 2): epochs never repeat, flags need no reset
     // scalars
@@ -383,6 +389,7 @@ static_assert(kSlots <= 65536, "slot ids travel in 16 bits");
 struct RepView {
     uint32_t *inbox;
     unsigned long long *winner;
+    uint16_t *xday;
     AgentRec *rec;
     const uint32_t *home;
     uint32_t *next_old, *next_new;          // tomorrow's lists
@@ -434,6 +441,7 @@ struct __align__(16) PassSmem {
     int dyn[3];                    // replica ensembles: the replica this CTA serves in the current pass, its part, the replica's CTAs
     uint32_t pk_n[32], pk_base[32]; // parks of the round per wake-day offset; their first slot in the day's bucket
     uint32_t n_old, n_pk, n_new, n_hit, n_con, n_draw, base_old, base_new, next_group;
+    uint32_t own_n[kMaxShards], own_base[kMaxShards];  // a sharded flush: staged new infectees per owner, their first slot in the owner's list
 };
 
 __device__ __forceinline__ void stage_tables(const DevCtx &cx, PassSmem &sm)
@@ -498,15 +506,22 @@ static __device__ __noinline__ void process_hit(const DevCtx &cx, PassSmem &sm, 
     const double tiso = exp_days_ni(sd_lane(draw_block(v.seed, i, (uint32_t)t, SD_SITE_INF, ord << 8), 0), sm.iso_asym[age_c]);
     uint32_t bits = 0;
     if (wday(old) != t) {  // first hit of c today: announce it, queue it for tomorrow
-        bits = inbox_infected_bit((int)(c & 15));
-        if (remote) {  // append to the OWNER's list of tomorrow, in its memory
+        // (a remote infectee's "infected" bit is set by its owner when it builds the record: one NVLink atomic less per hit)
+        if (!remote) bits = inbox_infected_bit((int)(c & 15));
+        // c is susceptible for the last day: from tomorrow on nobody's contact test sees it as S (this GPU's copy; a sharded
+        // run brings every GPU's copy up to date from the owners' lists of new infectees in the morning, xday_refresh)
+        if (cx.n_shards > 1) __stcg(v.xday + c, (uint16_t)(t + 1));
+        // staged in shared memory whoever owns c: a sharded run's flush reserves the room in each owner's list of tomorrow
+        // with ONE system-scope atomic per CTA and owner (flush_new_sharded)
+        const uint32_t pos = atomicAdd(&sm.n_new, 1u);
+        if (pos < (uint32_t)kOutNew) {
+            sm.out_new[pos] = c;
+        } else if (remote) {  // staging full: append to the OWNER's list of tomorrow, in its memory
             const size_t lrow = (size_t)((t + 1) & 1) * cx.n_pad;
-            const uint32_t pos = atomicAdd_system(cx.peer_list_cnt[g] + (cx.T + 2) + (t + 1), 1u);
-            if (SEIR_CHECK((int64_t)pos < cx.n_pad, cx, v.rep)) __stcg(cx.peer_list_new[g] + lrow + pos, c);
+            const uint32_t p2 = atomicAdd_system(cx.peer_list_cnt[g] + (cx.T + 2) + (t + 1), 1u);
+            if (SEIR_CHECK((int64_t)p2 < cx.n_pad, cx, v.rep)) __stcg(cx.peer_list_new[g] + lrow + p2, c);
         } else {
-            const uint32_t pos = atomicAdd(&sm.n_new, 1u);
-            if (pos < (uint32_t)kOutNew) sm.out_new[pos] = c;
-            else v.next_new[atomicAdd_system(v.next_new_cnt, 1u)] = c;
+            v.next_new[atomicAdd_system(v.next_new_cnt, 1u)] = c;
         }
     }
     if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
@@ -573,8 +588,15 @@ static __device__ __noinline__ void process_contact(const DevCtx &cx, PassSmem &
     if (glen == 0) return;
     const uint32_t c = (uint32_t)__ldg(cx.grp_members + g0 + (int64_t)sd_index(b, (uint64_t)glen));  // :374
     if (!SEIR_CHECK((int64_t)c < cx.n && sd_index(b, (uint64_t)glen) < (uint64_t)glen, cx, v.rep)) return;
-    const unsigned long long w = __ldcg((v.sharded ? cx.peer_winner[owner_of(cx, c)] : v.winner) + c);
-    if ((w == 0ull || wday(w) == t) && !at_home(v, c))  // :375
+    bool s_c;  // S[t-1, c]
+    if (cx.n_shards > 1) {  // a sharded run (replicated days included): this GPU's copy of the infection days
+        const uint32_t xd = __ldcg(v.xday + c);
+        s_c = xd == 0u || xd == (uint32_t)t + 1u;
+    } else {
+        const unsigned long long w = __ldcg(v.winner + c);
+        s_c = w == 0ull || wday(w) == t;
+    }
+    if (s_c && !at_home(v, c))  // :375
         push_hit(cx, sm, c, (slot << 16) | ord, a, t);
 }
 
@@ -644,6 +666,7 @@ static __device__ __forceinline__ void build_new_record(const DevCtx &cx, PassSm
     const unsigned long long w = __ldcg(v.winner + i);
     const uint32_t ib = __ldcg(v.inbox + (i >> 4));
     const uint16_t stt = __ldg(cx.stat + i);
+    if (v.sharded) atomicOr(v.inbox + (i >> 4), inbox_infected_bit((int)(i & 15)));  // (a hitter on another GPU left it to the owner)
     const uint4 hint = __ldcg(reinterpret_cast<const uint4 *>(v.rec + i));  // the timers a hitter of a warp-cooperative pass left (sparse_entry)
     const uint32_t inf = (uint32_t)(w >> 16), ord = (uint32_t)(w & 0xFFFFu);
     const int tx = t - 1;
@@ -999,17 +1022,40 @@ static __device__ __forceinline__ void flush_survivors(const DevCtx &cx, PassSme
     __syncthreads();
     if (so | sp | sn) {
         if (threadIdx.x == 0 && so) { sm.base_old = reserved; sm.n_old = 0; }
-        if (threadIdx.x == 64 && sn) { sm.base_new = new_reserved ? reserved : atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
+        if (threadIdx.x == 64 && sn && !v.sharded) { sm.base_new = new_reserved ? reserved : atomicAdd_system(v.next_new_cnt, sn); sm.n_new = 0; }
+        if (v.sharded && sn) {  // (CTA-uniform) the staged infectees belong to different GPUs: count them per owner, ...
+            if (threadIdx.x < kMaxShards) sm.own_n[threadIdx.x] = 0;
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < sn; k += kThreads) atomicAdd(&sm.own_n[owner_of(cx, sm.out_new[k])], 1u);
+            __syncthreads();
+            // ... reserve the room in every owner's list of tomorrow (one system-scope atomic per CTA and owner), ...
+            if (threadIdx.x < (unsigned)cx.n_shards) {
+                const uint32_t cnt = sm.own_n[threadIdx.x];
+                sm.own_base[threadIdx.x] = cnt ? atomicAdd_system(cx.peer_list_cnt[threadIdx.x] + (cx.T + 2) + (t + 1), cnt) : 0u;
+                sm.own_n[threadIdx.x] = 0;
+            }
+            if (threadIdx.x == 64) sm.n_new = 0;
+        }
         if (sp && threadIdx.x >= 128 && threadIdx.x < 128 + kParkHorizon) sm.pk_base[threadIdx.x - 128] = park_reserved;
         __syncthreads();
 #ifdef SEIR_CHECKS
-        if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sn && sm.base_new + sn > v.n_pad_m1 + 1u)))
+        if (threadIdx.x == 0 && ((so && sm.base_old + so > v.n_pad_m1 + 1u) || (sn && !v.sharded && sm.base_new + sn > v.n_pad_m1 + 1u)))
             atomicOr(&sm.cnt[3], 1u);
         __syncthreads();
         if (sm.cnt[3]) return;
 #endif
         for (uint32_t k = threadIdx.x; k < so; k += kThreads) v.next_old[sm.base_old + k] = sm.out_old[k];
-        for (uint32_t k = threadIdx.x; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
+        if (!v.sharded) {
+            for (uint32_t k = threadIdx.x; k < sn; k += kThreads) v.next_new[sm.base_new + k] = sm.out_new[k];
+        } else {  // ... and store each infectee behind its owner's base, in the owner's memory
+            const size_t lrow = (size_t)((t + 1) & 1) * cx.n_pad;
+            for (uint32_t k = threadIdx.x; k < sn; k += kThreads) {
+                const uint32_t c = sm.out_new[k];
+                const int g = owner_of(cx, c);
+                const uint32_t pos = sm.own_base[g] + atomicAdd(&sm.own_n[g], 1u);
+                if (SEIR_CHECK((int64_t)pos < cx.n_pad, cx, v.rep)) __stcg(cx.peer_list_new[g] + lrow + pos, c);
+            }
+        }
         if (sp) park_store(cx, sm, t, sp);
         __syncthreads();
         if (sp) {
@@ -1291,7 +1337,7 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
             uint32_t c = 0, ord = 0;
             int age_c = 0, col = 0, al = 0;
             double x = 0.0, pr = 0.0;
-            unsigned long long w_c = 0ull;
+            bool s_c = true;  // S[t-1, c] (a household candidate passed the test above)
             sd_block b = blk;
             const uint32_t k = k0 + lane - 16u;
             const bool contact = lane >= 16u && k < kept;
@@ -1327,7 +1373,13 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
             bool home_c = false;
             if (contact && cand) {
                 if (SEIR_CHECK((int64_t)c < cx.n, cx, v.rep)) {
-                    w_c = __ldcg(v.winner + c);
+                    if (cx.n_shards > 1) {
+                        const uint32_t xd = __ldcg(v.xday + c);
+                        s_c = xd == 0u || xd == (uint32_t)t + 1u;
+                    } else {
+                        const unsigned long long w_c = __ldcg(v.winner + c);
+                        s_c = w_c == 0ull || wday(w_c) == t;
+                    }
                     home_c = at_home(v, c);  // (:375; the household push has no Home test, :346)
                 } else {
                     cand = false;
@@ -1335,7 +1387,7 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
             }
             const double tiso = SD_RINT(SD_MUL(-lg, sm.iso_asym[age_c]));
     SEIR_SFINE(6);
-            is_hit = cand && (w_c == 0ull || wday(w_c) == t) && !home_c;
+            is_hit = cand && s_c && !home_c;
             if (is_hit) {
                 const unsigned long long key = ((unsigned long long)t << 48) | ((unsigned long long)i << 16) | ord;
                 // the hit and a slot of tomorrow's list of new infectees are requested together: the slot of a hit that
@@ -1343,6 +1395,7 @@ static __device__ __noinline__ int sparse_entry(const DevCtx &cx, PassSmem &sm, 
                 const unsigned long long old = atomicMax(v.winner + c, key);
                 const uint32_t p = atomicAdd_system(v.next_new_cnt, 1u);
                 const bool first = wday(old) != t;
+                if (first && cx.n_shards > 1) __stcg(v.xday + c, (uint16_t)(t + 1));  // (a replicated day of a sharded run)
                 if (SEIR_CHECK((int64_t)p < cx.n_pad, cx, v.rep)) __stcg(v.next_new + p, first ? c : kHole);
                 uint32_t bits = first ? inbox_infected_bit((int)(c & 15)) : 0u;
                 if (tiso == 0.0) bits |= inbox_q_bit((int)(c & 15));
@@ -1456,6 +1509,7 @@ static __device__ __noinline__ void fill_view(const DevCtx &cx, PassSmem &sm, in
     sm.v.p_contact = bank + kBankPcontact;
     sm.v.inbox = cx.inbox + (size_t)rep * (cx.n_pad / 16);
     sm.v.winner = cx.winner + (size_t)rep * cx.n_pad;
+    sm.v.xday = cx.xday + (size_t)rep * cx.n_pad;
     sm.v.rec = cx.rec + (size_t)rep * cx.n_pad;
     sm.v.home = cx.home + (size_t)rep * (cx.n_pad / 32);
     sm.v.next_old = cx.list_old + lrow;
@@ -1735,7 +1789,8 @@ static __device__ bool day_pass(const DevCtx &cx, PassSmem &sm, int t, int my_sl
             SEIR_STAMP(5);
             // (last round: the day's new infectees of this CTA are all staged -- thread 64 reserves their room in tomorrow's
             // list now, and the round trip overlaps stage W instead of standing in front of the grid barrier)
-            if (round + 1u == rounds && tid == 64) {
+            // (a sharded pass reserves per owner, inside the flush)
+            if (round + 1u == rounds && tid == 64 && !v.sharded) {
                 const uint32_t sn = sm.n_new < (uint32_t)kOutNew ? sm.n_new : (uint32_t)kOutNew;
                 if (sn) reserved = atomicAdd_system(v.next_new_cnt, sn);
             }
@@ -2161,6 +2216,34 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 #endif
     }
     __syncthreads();
+}
+
+// The morning of a sharded day t: every GPU brings ITS copy of xday up to date from the owners' lists of today's new
+// infectees (the agents of owner g that anybody infected yesterday; complete since last night's cross-GPU barrier): bulk,
+// coalesced reads over NVLink instead of a remote read per candidate contact.  The caller meets at a grid barrier
+// afterwards: no contact test of day t may run before the copy is complete.
+// Returns false when nobody was infected yesterday (grid-uniform: every CTA reads the same counts): nothing to wait for.
+__device__ __forceinline__ bool xday_refresh(const DevCtx &cx, PassSmem &sm, int t)
+{
+    if (threadIdx.x < (unsigned)cx.n_shards) sm.own_n[threadIdx.x] = __ldcg(cx.peer_list_cnt[threadIdx.x] + (cx.T + 2) + t);
+    __syncthreads();
+    uint32_t any = 0;
+    for (int g = 0; g < cx.n_shards; ++g) any |= sm.own_n[g];
+    if (!any) {
+        __syncthreads();
+        return false;
+    }
+    const size_t lcur = (size_t)(t & 1) * cx.n_pad;
+    for (int g = 0; g < cx.n_shards; ++g) {
+        const uint32_t cnt = sm.own_n[g];
+        const uint32_t *row = cx.peer_list_new[g] + lcur;
+        for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < cnt; k += gridDim.x * kThreads) {
+            const uint32_t c = __ldcg(row + k);
+            if (c != kHole && (int64_t)c < cx.n) __stcg(cx.xday + c, (uint16_t)t);  // infected on day t-1
+        }
+    }
+    __syncthreads();
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2701,37 +2784,40 @@ __device__ __forceinline__ void grid_barrier_multi(const DevCtx &cx, unsigned in
     unsigned int *flags = cx.peer_flags[cx.my_shard];
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        asm volatile("fence.acq_rel.sys;" ::: "memory");  // (this CTA's stores into the peers' memory are performed before it arrives)
         atomicAdd(counter, 1u);
         unsigned int seen;
         if (blockIdx.x == 0) {
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
             } while (seen < target);
-            __threadfence_system();
+            // release pattern = ONE system-scope fence, then relaxed stores: the flag stores to the peers travel side by side
+            // (a st.release.sys per peer fences again each time and waits for the previous peer's store to be acknowledged:
+            // seven NVLink round trips in a row on an 8-GPU box)
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (int g = 0; g < cx.n_shards; ++g)
                 if (g != cx.my_shard)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(cx.peer_flags[g] + cx.my_shard), "r"(epoch) : "memory");
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(cx.peer_flags[g] + cx.my_shard), "r"(epoch) : "memory");
             const unsigned long long t0 = global_timer_ns();
             for (int g = 0; g < cx.n_shards; ++g) {
                 if (g == cx.my_shard) continue;
                 if (*(volatile unsigned int *)(flags + kMaxShards + 1)) break;  // a peer is gone: do not wait again
                 do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + g) : "memory");
+                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + g) : "memory");  // (acquire = the fence below)
                     if (seen < epoch && global_timer_ns() - t0 > kPeerTimeoutNs) {
                         atomicExch(flags + kMaxShards + 1, 1u);  // error word
                         break;
                     }
                 } while (seen < epoch);
             }
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + kMaxShards), "r"(epoch) : "memory");
         } else {
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + kMaxShards) : "memory");
             } while (seen < epoch);
         }
-        __threadfence_system();
+        // (the acquire load above orders this CTA behind CTA 0, which is ordered behind the peers: no further fence)
     }
     __syncthreads();
 }

@@ -34,6 +34,9 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_shard_set_threshold")
 
 
+SHARD_HANDLES = 6   # include/seir_b200.h SEIR_SHARD_HANDLES
+
+
 class SeirParams(C.Structure):
     _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("t_lockdown", C.c_int32),
                 ("t_stayhome_start", C.c_int32), ("t_tracing_start", C.c_int32),
@@ -228,15 +231,15 @@ class Engine:
         return tb
 
     def shard_export(self):
-        """320 bytes: the CUDA IPC handles of this rank's arrays (include/seir_b200.h, seir_shard_export)."""
-        out = np.zeros(5 * 64, dtype=np.uint8)
+        """SHARD_HANDLES x 64 bytes: the CUDA IPC handles of this rank's arrays (include/seir_b200.h, seir_shard_export)."""
+        out = np.zeros(SHARD_HANDLES * 64, dtype=np.uint8)
         _check(self.lib.seir_shard_export(self._h, _ptr(out)))
         return out
 
     def shard_attach(self, rank, world, all_handles, bounds, threshold=None):
-        """all_handles uint8[world, 320] (rank-major), bounds int64[world + 1] (household starts).  threshold: list
+        """all_handles uint8[world, SHARD_HANDLES * 64] (rank-major), bounds int64[world + 1] (household starts).  threshold: list
         entries of a day up to which the run stays replicated (None: the library's default; 0: sharded from day 1)."""
-        hd = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world, 5 * 64)
+        hd = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world, SHARD_HANDLES * 64)
         bd = np.ascontiguousarray(bounds, dtype=np.int64)
         if bd.shape != (world + 1,):
             raise ValueError("bounds must have world + 1 entries")

@@ -6,7 +6,7 @@ keeps household transmission (seir_individual.py:339-359) inside a shard.  Commu
 GPU the sender's kernel reads the target's `winner` word, applies the `atomicMax`, sets the inbox bits
 and appends the target to the owner's list of tomorrow directly in the owner's memory over NVLink
 (CUDA IPC mappings, system-scope atomics); the GPUs meet at a device-side barrier once per day.  No
-host round trip and no NCCL call inside the day loop: torch.distributed only carries the 320-byte IPC
+host round trip and no NCCL call inside the day loop: torch.distributed only carries the 384-byte IPC
 handles at set-up and the small results at the end.
 
 Every rank holds the full-size arrays in global agent indexing (C3: 11 GB per GPU) and steps the agents

@@ -155,7 +155,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
 
 /* One population across the GPUs of a box (shards of whole households; every rank creates
  * its handle on its own device with the FULL population and n_replicas = 1).
- * seir_shard_export: 5 x 64 bytes of CUDA IPC handles of this rank's winner / inbox / list / flag arrays.
+ * seir_shard_export: SEIR_SHARD_HANDLES x 64 bytes of CUDA IPC handles of this rank's winner / inbox / list / flag / infection-day arrays.
  * seir_shard_attach: all ranks' handles (world x 5 x 64 bytes, rank-major) and the shard bounds
  *   (bounds[world + 1], bounds[g] a household start): rank `rank` owns agents [bounds[rank], bounds[rank+1]).
  * Afterwards seir_run steps only the owned agents; a community contact whose target lives on another GPU is
@@ -163,9 +163,10 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
  * barrier once per day.  All ranks must call seir_run together, with the same seed and initial cases.
  * Outputs (tallies, vectors, history) cover the owned agents; tallies of the ranks add up.
  * A sharded run starts REPLICATED: while a day's lists hold at most `entries` agents (seir_shard_set_threshold, default
- * 131072) every GPU steps the whole population on its own -- the runs are deterministic, so the GPUs stay identical
+ * 393216) every GPU steps the whole population on its own -- the runs are deterministic, so the GPUs stay identical
  * without exchanging a byte, and a sparse day costs what it costs on one GPU -- and on the first longer day all GPUs
  * switch for good to sharded passes.  0 = sharded from day 1.  All ranks must use the same value. */
+#define SEIR_SHARD_HANDLES 6
 int seir_shard_export(seir_handle *h, uint8_t *handles_out);
 int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_handles, const int64_t *bounds);
 int seir_shard_set_threshold(seir_handle *h, int64_t entries);
