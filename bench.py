@@ -729,12 +729,22 @@ def sharded_c3_leg(args, dist, rank, world, local):
         eng.close()
         if rank == 0:
             ms = float(mx[0].item())
+            inf = int(tt[2].item())
+            # payload that crosses NVLink, from the run's own infection count (upper bound: as if every day were a sharded
+            # one): per infection (world-1)/world of the hitters are remote -- an 8 B atomicMax and its 8 B answer, a 4 B
+            # list entry -- and every other GPU reads the 4 B list entry next morning (its copy of the infection days)
+            nv = inf * ((world - 1.0) / world * 20.0 + 4.0 * (world - 1))
             out[label] = {"ms_per_run": ms, "agent_days_per_sec": float(n) * (T - 1) / (ms / 1e3),
                           "e2e_ms_per_run": float(mx[1].item()) * 1e3, "one_gpu_ms_per_run": one_ms,
-                          "speedup_vs_1gpu": one_ms / ms, "infections": int(tt[2].item()),
+                          "speedup_vs_1gpu": one_ms / ms, "infections": inf,
+                          "nvlink_payload_bytes_per_run_upper_bound": nv, "nvlink_payload_bytes_per_day": nv / (T - 1),
                           "shard_bounds": [int(b) for b in bounds]}
     out["workload"] = "C3 Hubei: %d agents, T=127, ONE population sharded by whole households over %d GPUs" % (n, world)
-    out["exchange"] = "peer-memory atomics over NVLink + device-side day barrier inside seir_persistent_kernel; no NCCL call in the day loop"
+    out["exchange"] = ("inside seir_persistent_kernel, no NCCL call in the day loop: replicated (no exchange at all) while a day's lists hold "
+                       "fewer than 393216 entries; then per first hit one system-scope atomicMax in the owner's HBM over NVLink, the new "
+                       "infectees staged per CTA and appended to the owner's list with one system-scope atomic per CTA and owner; every "
+                       "morning each GPU completes its own copy of the infection days from all owners' lists (bulk reads), so the "
+                       "susceptibility test of a candidate contact is local; one device-side barrier across the GPUs per day")
     return out
 
 

@@ -45,6 +45,12 @@ def test_struct_sizes_match_the_header():
     assert list(sizes) == mine == [8 + 8 * 4 + 13 * 8, 8 + 8 + 7 * 8, 10 * 8, 8 + 8 + 8 + 8 + 8 + 8 + 8, 6 * 4]
 
 
+def test_shard_handle_count_matches_the_header():
+    # seir_shard_export writes SEIR_SHARD_HANDLES x 64 bytes; the ctypes side sizes its buffers from its own constant
+    m = re.search(r"#define\s+SEIR_SHARD_HANDLES\s+(\d+)", open(HEADER).read())
+    assert m and int(m.group(1)) == engine.SHARD_HANDLES
+
+
 def test_no_device_is_an_error_not_a_fallback():
     lib = engine.load_library()
     if lib.seir_device_count() > 0:
