@@ -284,11 +284,16 @@ def run_gpu_arm(args):
     create_s = time.perf_counter() - t0
     R = args.replicas
     n_init = int(p["initial_infected_fraction"] * n)
-    rng = np.random.default_rng(100 + rank)
     home = engine.pin(np.zeros(n, dtype=np.uint8))  # fraction_stay_home = 0 in C2 (run_simulation.py:53-54)
 
+    # Weak scaling means the SAME work per GPU at every N.  A C2 run costs 1.1-2.2 ms depending on how large its epidemic
+    # grows, so ranks that drew their own seeds would be measured by their luck (the line is the maximum over ranks).  The
+    # K timed steps therefore use the same K (seed, initial cases) pairs on every rank, rank r starting r pairs further on:
+    # every GPU runs a different trajectory at any moment and the same K trajectories over the timed region.
     def inputs(step):
-        seeds = [(rank * 100003 + step) * 64 + r for r in range(R)]
+        slot = 100000 - step if step < 0 else (step + rank) % max(1, args.steps)  # (negative: warm-up steps)
+        rng = np.random.default_rng(1000 + slot)
+        seeds = [slot * 64 + r for r in range(R)]
         init = [rng.choice(n, size=n_init, replace=False).astype(np.int64) for _ in range(R)]
         return seeds, [home] * R, init
 
@@ -376,6 +381,7 @@ def run_gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
             "config": {"workload": C2_WORKLOAD % (n, T, R * world),
                        "mode": args.mode, "launch": args.launch, "replicas_per_gpu": R,
+                       "seeds": "the same K trajectories on every rank, rank r starting r steps further on (equal work per GPU)",
                        "l2": ("explicit 256 MiB flush between steps" if args.flush_l2 else
                               "per-run working set %.2f GB (history %d x %d B + state) > 126 MB L2; state re-initialised every step"
                               % ((T * n + 110 * n) / 1e9, T, n)),
@@ -572,6 +578,12 @@ def _ensemble_leg(args, device, n, T, R, p, tabs, fsh, label, launches=3, grid=N
     runs = [dict(seeds=[5000 + k * R + r for r in range(R)], keyed=(fsh, p["initial_infected_fraction"]), overrides=overrides)
             for k in range(launches + 1)]
     out = _timed_runs(eng, runs, peak, n, T, R)
+    # no T x n history is written in this mode, so the 2 n bytes per day of SURVEY.md 8d's formula are not owed: the leg's
+    # own figure charges only the bytes of the agents and infections it touches; the survey's formula is given beside it
+    out["roofline_frac_survey_8d_formula"] = out["roofline_frac"]
+    touched = 16.0 * out["active_agent_days_per_run"] * R + 64.0 * out["infections_per_run"] * R
+    out["roofline_frac"] = touched / (out["ms_per_launch"] / 1e3) / 1e9 / peak
+    out["algorithmic_bytes_per_launch_without_row_term"] = touched
     if grid:  # (the replicas' horizons differ: count their own agent-days)
         ad = float(n) * sum(o["T"] - 1 for o in overrides)
         out["agent_days_per_sec"] = ad / (out["ms_per_launch"] / 1e3)
