@@ -33,23 +33,31 @@ def _median_from_histogram(counts):
     return 0.5 * (lo + hi)
 
 
+def _medians_from_histograms(counts):
+    """_median_from_histogram for every row of counts[T, 101] at once (rows without agents: nan)."""
+    c = np.asarray(counts, dtype=np.int64)
+    m = c.sum(axis=1)
+    cum = np.cumsum(c, axis=1)
+    # searchsorted(cum_row, k) = number of entries of the row below k
+    lo = (cum < ((m - 1) // 2 + 1)[:, None]).sum(axis=1)
+    hi = (cum < (m // 2 + 1)[:, None]).sum(axis=1)
+    return np.where(m > 0, 0.5 * (lo + hi), np.nan)
+
+
 def cohort_statistics(cohorts, fill=0.0):
     """run_simulation.py:448-453: per exposure day t (rows with no exposure keep `fill`):
     r_0_over_time, cfr_over_time, fraction_over_70_time, fraction_below_30_time, median_age_time."""
     c = np.asarray(cohorts).astype(np.float64)
-    T = c.shape[0]
-    out = {k: np.full(T, fill, dtype=np.float64) for k in
-           ("r_0_over_time", "cfr_over_time", "fraction_over_70_time", "fraction_below_30_time", "median_age_time")}
-    for t in range(T):
-        m = c[t, 0].sum()
-        if m > 0:
-            out["r_0_over_time"][t] = c[t, 1].sum() / m
-            d, r = c[t, 2].sum(), c[t, 3].sum()
-            out["cfr_over_time"][t] = d / (d + r) if (d + r) > 0 else np.nan
-            out["fraction_over_70_time"][t] = c[t, 0, 70:].sum() / m
-            out["fraction_below_30_time"][t] = c[t, 0, :30].sum() / m
-            out["median_age_time"][t] = _median_from_histogram(cohorts[t][0])
-    return out
+    m = c[:, 0].sum(axis=1)
+    has = m > 0
+    d, r = c[:, 2].sum(axis=1), c[:, 3].sum(axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        vals = {"r_0_over_time": c[:, 1].sum(axis=1) / m,
+                "cfr_over_time": np.where(d + r > 0, d / (d + r), np.nan),
+                "fraction_over_70_time": c[:, 0, 70:].sum(axis=1) / m,
+                "fraction_below_30_time": c[:, 0, :30].sum(axis=1) / m,
+                "median_age_time": _medians_from_histograms(np.asarray(cohorts)[:, 0])}
+    return {k: np.where(has, v, fill).astype(np.float64) for k, v in vals.items()}
 
 
 def r0_total(cohorts, first=1, last=20):

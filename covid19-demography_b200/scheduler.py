@@ -45,7 +45,10 @@ class FileQueue:
 
     def _owner_alive(self, path):
         try:
-            host, pid = open(path).read().strip().rsplit(":", 1)
+            text = open(path).read().strip()
+            if ":" not in text:   # created a moment ago, its owner has not written its name yet (O_EXCL create, then write)
+                return time.time() - os.path.getmtime(path) < 10.0
+            host, pid = text.rsplit(":", 1)
             if host != socket.gethostname():
                 return time.time() - os.path.getmtime(path) < self.stale_after_s
             os.kill(int(pid), 0)
@@ -142,6 +145,9 @@ def run_worker(engine, plan, directory, prologue="keyed", age_groups=None, max_j
             cursor += 1
             stem = plan.stem(job)
             if q.done(stem, plan.datatypes) or not q.claim(stem):
+                continue
+            if q.done(stem, plan.datatypes):   # (its owner finished and released it between the two tests above)
+                q.release(stem)
                 continue
             batch.append(job)
         if not batch:

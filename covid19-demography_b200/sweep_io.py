@@ -74,13 +74,28 @@ def agepolicy_job_arrays(tallies, cohorts, n, actual_deaths=None, first_day=None
     return out
 
 
+def _format_tsv(a):
+    """The bytes `pd.DataFrame(a).to_csv(sep="\t", index=False, header=False, na_rep="NA")` writes for a 1-D or 2-D numeric
+    array (parameter_sweep.py:716-729): float64 as the shortest repr ("3.0", "0.1", "1e-05", "inf"), NaN as NA, integers
+    as integers, one line per row.  pandas spends 0.4 ms per call before the first byte; a job has 19 files of a few
+    hundred numbers, and a sweep thousands of jobs (tests/test_sweep.py compares the two byte for byte)."""
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a[:, None]
+    if a.dtype.kind in "iub":
+        rows = ["\t".join(map(str, r)) for r in a.tolist()]
+    else:
+        rows = ["\t".join("NA" if x != x else repr(x) for x in r) for r in a.astype(np.float64).tolist()]
+    return ("\n".join(rows) + "\n") if rows else ""
+
+
 def write_job_files(directory, stem, arrays, datatypes=None):
     """One file per datatype, the reference's to_csv settings (:716-729).  Returns the paths."""
-    import pandas as pd
     os.makedirs(directory, exist_ok=True)
     paths = {}
     for name in (DATATYPES if datatypes is None else datatypes):
         path = os.path.join(directory, "%s_%s.csv" % (stem, name))
-        pd.DataFrame(arrays[name]).to_csv(path, sep="\t", index=False, header=False, na_rep="NA")
+        with open(path, "w") as f:
+            f.write(_format_tsv(arrays[name]))
         paths[name] = path
     return paths

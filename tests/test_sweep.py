@@ -156,3 +156,24 @@ def test_agepolicy_job_files(tmp_path):
     assert np.array_equal(back["infected"][0], c.n - S.sum(axis=1))  # :617
     assert np.array_equal(back["documented"][0], Doc.sum(axis=1))
     assert np.array_equal(back["susceptible"][0], S.sum(axis=1))
+
+
+def test_tsv_writer_is_byte_identical_to_the_reference_to_csv_call():
+    """parameter_sweep.py:716-729 writes every per-job array with pandas' to_csv(sep='\\t', index=False, header=False,
+    na_rep='NA'); sweep_io formats the same bytes itself (pandas' per-call overhead dominated a sweep's wall time)."""
+    import io
+
+    import pandas as pd
+    from covid19_demography_b200 import sweep_io
+
+    def reference_bytes(a):
+        b = io.StringIO()
+        pd.DataFrame(a).to_csv(b, sep="\t", index=False, header=False, na_rep="NA")
+        return b.getvalue()
+
+    rng = np.random.default_rng(0)
+    cases = [rng.random((3, 7)), rng.random(5), rng.integers(0, 100, (2, 5)), (rng.random((2, 365)) * 1e6).round(),
+             np.array([1.0, np.nan, np.inf, -np.inf, 1e-5, 1e22, 123456789.123, 0.0, -0.0, 3.0, 1 / 3]),
+             np.array([[np.nan] * 3] * 2), rng.random((4, 10)) / 3e-7, np.full(4, np.nan)]
+    for a in cases:
+        assert sweep_io._format_tsv(a) == reference_bytes(a)
