@@ -178,6 +178,70 @@ __global__ void __launch_bounds__(kSparseThreads, 1) seir_sparse_kernel(const __
     }
 }
 
+// The first days of a run (a handful of cases: at most one list entry per warp of EIGHT CTAs) are run by one thread-block
+// CLUSTER: the same warp-cooperative passes, but the CTAs of a day meet at the hardware cluster barrier
+// (barrier.cluster.arrive.release / wait.acquire, SASS: UCGABAR_ARV / UCGABAR_WAIT) instead of an atomic word in L2 polled
+// by 148 CTAs, and the other 140 SMs stay idle.  Launched in front of seir_sparse_kernel; hands over like the others.
+#ifndef SEIR_CLUSTER_CTAS
+#define SEIR_CLUSTER_CTAS 8   // portable cluster size; one CTA per SM (the sparse pass's 126 registers x 512 threads)
+#endif
+constexpr int kClusterCtas = SEIR_CLUSTER_CTAS;
+__global__ void __launch_bounds__(kSparseThreads, 1) seir_cluster_kernel(const __grid_constant__ DevCtx cx, int k, uint32_t cap)
+{
+    PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
+    int t = __ldcg(cx.ctl + k) + 1;
+    if (t > cx.T_loop) {  // nothing left to do: hand the word on
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.ctl[k + 1] = t - 1;
+        return;
+    }
+    stage_tables(cx, sm);
+    if (threadIdx.x < 3) sm.run_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 4) sm.cnt[threadIdx.x] = 0;
+    int bank_staged = -1;
+    if (threadIdx.x == 0) {
+        Pass<false>::fill_view(cx, sm, t, 0, false);
+        Pass<false>::load_list_lengths(cx, sm, t, 0);
+    }
+    __syncthreads();
+    for (; t <= cx.T_loop; ++t) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.day_ns[t] = global_timer_ns();
+        const int T = sm.rp.T;
+        const bool finalize = t >= T;
+        const uint32_t n_new = sm.list_n[0], n_old = finalize ? 0u : sm.list_n[1], n_pk = finalize ? 0u : sm.list_n[2];
+        if (sm.list_n[0] + sm.list_n[1] + sm.list_n[2] > cap) break;  // (cluster-uniform: the day goes to the 148-CTA kernels)
+        if (blockIdx.x == 0 && threadIdx.x == 0) cx.stage_ns[(size_t)t * 8 + 0] = global_timer_ns();
+        if (bank_staged != sm.rp.bank) {
+            const double *src = cx.bank + (size_t)sm.rp.bank * kBankStride + kBankNatEn;
+            for (int q = threadIdx.x; q < 4 * kAges; q += kSparseThreads) sm.nat_enlam[q] = src[q];
+            bank_staged = sm.rp.bank;
+            __syncthreads();
+        }
+        Pass<false>::sparse_rounds(cx, sm, t, n_new, n_old, n_pk, cx.list_new + (size_t)(t & 1) * cx.n_pad, cx.list_old + (size_t)(t & 1) * cx.n_pad,
+                                   cx.pk_pool + (size_t)(t & (kParkRing - 1)) * cx.n_pad, (int)blockIdx.x, (int)gridDim.x, finalize, false);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long now = global_timer_ns();
+            for (int q = 1; q < 8; ++q) cx.stage_ns[(size_t)t * 8 + q] = now;
+        }
+        __syncthreads();  // (every warp of this CTA is through with day t: its view may be replaced)
+        // the cluster barrier, with the next pass's set-up between arrival and wait (what needs nothing from the other CTAs)
+        if (t < cx.T_loop) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        if (threadIdx.x == 32) {
+            Pass<false>::flush_pass_counters(cx, sm, 0, true);
+            if (t < cx.T_loop) Pass<false>::fill_view(cx, sm, t + 1, 0, false);
+        }
+        if (t < cx.T_loop) {
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            if (threadIdx.x == 0) Pass<false>::load_list_lengths(cx, sm, t + 1, 0);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3 && sm.run_cnt[threadIdx.x]) atomicAdd(&cx.counters[1 + threadIdx.x], (unsigned long long)sm.run_cnt[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cx.ctl[k + 1] = t - 1;
+        if (t > cx.T_loop) cx.day_ns[cx.T + 1] = global_timer_ns();
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, kMinBlocks) seir_dense_solo_kernel(const __grid_constant__ DevCtx cx, int k, uint32_t yield_below, uint32_t yield_above)
 {
     PassSmem &sm = *reinterpret_cast<PassSmem *>(seir_smem_raw);
@@ -658,6 +722,7 @@ struct seir_handle {
     unsigned long long *counters_host = nullptr;
     bool host_results = false;  // the pinned copies hold the last run's results
     cudaStream_t copy_stream = nullptr;
+    uint32_t cluster_cap = 0;   // a day with at most this many list entries runs in the one-cluster kernel (0: never)
     DevBuf<uint32_t> tcta, tbig, tedge_off, tedge_cnt, tedge;
     uint32_t tedge_cap = 0;
     DevBuf<unsigned long long> tmark;
@@ -831,6 +896,10 @@ static void fill_ctx(seir_handle *h)
     // (2: a day with up to two entries per warp is still cheaper as two warp-cooperative rounds, 14 us, than as a staged pass, 18 us:
     //  profiles/r02/experiments.md)
     { const char *sx = getenv("SEIR_SPARSE_MAX"); c.sparse_max = sx ? (uint32_t)atoi(sx) : 0xFFFFFFFFu; }
+    {   // the one-cluster kernel takes the days with at most one entry per warp of its CTAs (SEIR_CLUSTER_CAP=0: never)
+        const char *cc = getenv("SEIR_CLUSTER_CAP");
+        h->cluster_cap = cc ? (uint32_t)atoi(cc) : (uint32_t)(kClusterCtas * (kSparseThreads / 32));
+    }
     {   // single-replica runs: the sparse-day kernel (one CTA per SM) takes the days with at most one entry per warp and round
         const unsigned long long cap = (unsigned long long)c.sparse_rounds * (unsigned long long)(h->sms * (kSparseThreads / 32));
         c.sparse_cap = (uint32_t)(cap < c.sparse_max ? cap : c.sparse_max);
@@ -1011,6 +1080,7 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         // persistent grid: every CTA must be co-resident
         int occ = 0;
         if (cudaFuncSetAttribute(seir_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
+            cudaFuncSetAttribute(seir_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
             cudaFuncSetAttribute(seir_dense_solo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
             cudaFuncSetAttribute(seir_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
             cudaFuncSetAttribute(seir_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PassSmem)) != cudaSuccess ||
@@ -1288,11 +1358,26 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
                           !(h->n_shards > 1 && h->shard_threshold == 0u);
         h->cx.start_word = -1;
         if (solo) {
-            for (int k = 0; k < 4; ++k) {
-                uint32_t yield_below = k == 3 ? 0u : h->cx.sparse_cap / 2u + 1u;  // (0: this launch never hands over)
+            // launch 0: the first days in ONE thread-block cluster (seir_cluster_kernel); then sparse, dense, sparse, dense
+            {
+                int k0 = 0;
+                uint32_t cap = h->cluster_cap < h->cx.sparse_cap ? h->cluster_cap : h->cx.sparse_cap;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(kClusterCtas); cfg.blockDim = dim3(kSparseThreads);
+                cfg.dynamicSmemBytes = sizeof(PassSmem); cfg.stream = h->stream;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                if (cap == 0u) { cfg.numAttrs = 0; cfg.gridDim = dim3(1); }  // (switched off: a one-CTA launch that hands day 1 on)
+                CK(cudaLaunchKernelEx(&cfg, seir_cluster_kernel, h->cx, k0, cap));
+                ++h->launches;
+            }
+            for (int k = 1; k < 5; ++k) {
+                uint32_t yield_below = k == 4 ? 0u : h->cx.sparse_cap / 2u + 1u;  // (0: this launch never hands over)
                 uint32_t yield_above = h->n_shards > 1 ? h->shard_threshold : 0xFFFFFFFFu;
                 void *args[] = {&h->cx, &k, &yield_below, &yield_above};
-                if (k % 2 == 0) CK(cudaLaunchCooperativeKernel((const void *)seir_sparse_kernel, dim3(h->sms), dim3(kSparseThreads), args, sizeof(PassSmem), h->stream));
+                if (k % 2 == 1) CK(cudaLaunchCooperativeKernel((const void *)seir_sparse_kernel, dim3(h->sms), dim3(kSparseThreads), args, sizeof(PassSmem), h->stream));
                 else CK(cudaLaunchCooperativeKernel((const void *)seir_dense_solo_kernel, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
                 ++h->launches;
                 if (getenv("SEIR_DEBUG_SYNC")) {  // (debugging: which launch faults)
@@ -1301,8 +1386,8 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
                 }
             }
             if (h->n_shards > 1) {
-                h->cx.start_word = 4;
-                h->cx.barrier = h->barrier.p + 5 * kBarStride;  // (its own barrier words: launches 0..3 counted in words 1..4)
+                h->cx.start_word = 5;
+                h->cx.barrier = h->barrier.p + 6 * kBarStride;  // (its own barrier words: launches 1..4 counted in words 2..5)
                 void *args[] = {&h->cx};
                 CK(cudaLaunchCooperativeKernel((const void *)seir_persistent_kernel<false>, dim3(h->grid), dim3(kThreads), args, sizeof(PassSmem), h->stream));
                 h->cx.barrier = h->barrier.p;
