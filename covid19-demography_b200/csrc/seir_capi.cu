@@ -723,6 +723,7 @@ struct seir_handle {
     bool host_results = false;  // the pinned copies hold the last run's results
     cudaStream_t copy_stream = nullptr;
     uint32_t cluster_cap = 0;   // a day with at most this many list entries runs in the one-cluster kernel (0: never)
+    bool cluster_failed = false;  // a cluster launch was refused on this device: not tried again
     DevBuf<uint32_t> tcta, tbig, tedge_off, tedge_cnt, tedge;
     uint32_t tedge_cap = 0;
     DevBuf<unsigned long long> tmark;
@@ -1369,8 +1370,15 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = kClusterCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.attrs = at; cfg.numAttrs = 1;
-                if (cap == 0u) { cfg.numAttrs = 0; cfg.gridDim = dim3(1); }  // (switched off: a one-CTA launch that hands day 1 on)
-                CK(cudaLaunchKernelEx(&cfg, seir_cluster_kernel, h->cx, k0, cap));
+                if (cap == 0u || h->cluster_failed) { cap = 0u; cfg.numAttrs = 0; cfg.gridDim = dim3(1); }  // (switched off: a one-CTA launch that hands day 1 on)
+                cudaError_t ce = cudaLaunchKernelEx(&cfg, seir_cluster_kernel, h->cx, k0, cap);
+                if (ce != cudaSuccess && cfg.numAttrs) {  // no room for the cluster on this device (partitioned, busy): the 148-CTA kernels take day 1 on
+                    (void)cudaGetLastError();
+                    h->cluster_failed = true;
+                    cap = 0u; cfg.numAttrs = 0; cfg.gridDim = dim3(1);
+                    ce = cudaLaunchKernelEx(&cfg, seir_cluster_kernel, h->cx, k0, cap);
+                }
+                CK(ce);
                 ++h->launches;
             }
             for (int k = 1; k < 5; ++k) {
