@@ -662,6 +662,29 @@ void oracle_sd_poisson(uint64_t seed, int64_t m, double enlam, int64_t *y)
 {
     for (int64_t i = 0; i < m; i++) y[i] = sd_poisson(seed, (uint32_t)i, 0, SD_SITE_NCNT, 0, enlam, SD_MAX_CONTACTS_NATIVE);
 }
+/* scalar keyed draws, one per draw site of the contract: what oracle/make_instrumented_golden.py binds (ctypes, called
+ * from numba's nopython code) in place of every np.random.* / functions.threshold_* call of the reference's run_model */
+double oracle_kd_uniform(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub, int lane)
+{
+    return sd_lane(sd_draw(seed, agent, day, site, sub), lane);
+}
+double oracle_kd_exp_days(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub, int lane, double mean)
+{
+    return sd_exp_days(sd_lane(sd_draw(seed, agent, day, site, sub), lane), mean);
+}
+double oracle_kd_lognormal_days(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub_base,
+                                double mu, double sigma)
+{
+    return sd_lognormal_days(seed, agent, day, site, sub_base, mu, sigma);
+}
+int64_t oracle_kd_poisson(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub_base, double enlam)
+{
+    return (int64_t)sd_poisson(seed, agent, day, site, sub_base, enlam, SD_MAX_CONTACTS_PER_AGE);
+}
+int64_t oracle_kd_index(uint64_t seed, uint32_t agent, uint32_t day, uint32_t site, uint32_t sub, int64_t glen)
+{
+    return (int64_t)sd_index(sd_draw(seed, agent, day, site, sub), (uint64_t)glen);
+}
 /* MT stream helpers (pin the generator restatement against numpy's identical MT19937) */
 void oracle_mt_doubles(uint32_t seed, double *y, int64_t m)
 {

@@ -1,0 +1,98 @@
+"""The reference's OWN code under the keyed draw contract (BASELINE.json: "fed the same pre-drawn uniform random
+streams as an instrumented reference run on a small population ... bit-exact").
+
+`tests/golden/ref_keyed_<case>.npz` holds the 20 outputs of `/root/reference/seir_individual.py`'s `run_model` after
+`oracle/make_instrumented_golden.py` replaced each of its random call sites -- and nothing else -- by the keyed draw of
+that site; its control flow, tracing recursion included, ran under numba as the reference wrote it.  Demanded here,
+bit for bit on all six fixtures with the fixtures' own parameters (tracing as compiled):
+
+  * CPU: oracle(provider = replay) == those outputs, and (where /root/reference exists) a live regeneration of the
+    instrumented copy on a seed / parameter set that is not frozen;
+  * `-m gpu`: the CUDA day step in replay mode, through the C ABI, == those outputs -- the GPU against the reference's
+    code without the oracle in between -- plus the per-day per-age tallies the day loop counted against the column
+    sums of the reference's histories.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import ref_shim
+import util
+from covid19_demography_b200 import tables as tables_mod
+
+
+def _frozen(name):
+    return np.load(os.path.join(util.GOLDEN, "ref_keyed_%s.npz" % name))
+
+
+@pytest.mark.parametrize("name", util.CASES)
+def test_oracle_replay_equals_instrumented_reference(name):
+    c = util.Case(name)
+    fx = _frozen(name)
+    assert int(fx["seed"]) == c.seed
+    tup, ex, home, init = c.keyed_oracle("replay", dict(c.params))
+    assert np.array_equal(util.pack_history(tup[:9]), fx["history_packed"])
+    for k in util.VECS:
+        assert np.array_equal(tup[util.VEC_INDEX[k]], fx["out_" + k], equal_nan=True), k
+    # the frozen runs are not trivial: an epidemic happened, and where tracing ran it left its mark
+    hp = fx["history_packed"]
+    assert ((hp[-1] & 7) != 0).sum() > 100
+    T = int(c.params["T"])
+    if name in ("italy_default", "italy_seeded", "italy_tracing"):
+        assert 1 <= c.params["t_tracing_start"] < T
+        done = ((hp[-1] & 7) >= 5)
+        assert (((hp[-1] >> 3) & 1).astype(bool) & done).any(), "tracing should quarantine some recovered/dead agents"
+
+
+def _numba_ok():
+    try:
+        import numba  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not (ref_shim.available() and _numba_ok()), reason="/root/reference or numba is not on this box")
+def test_live_instrumented_reference_on_an_unfrozen_run():
+    """Regenerate the instrumented copy from the reference where it lies and run a seed / parameter set that no
+    fixture holds: heavy tracing from day 8, short isolation delays, a lockdown on day 20."""
+    import make_instrumented_golden as mig
+    c = util.Case("italy_tracing")
+    params = dict(c.params)
+    params.update(t_tracing_start=8.0, t_lockdown=20.0, lockdown_factor=3.0, mean_time_to_isolate_asympt=6.0,
+                  initial_infected_fraction=0.01)
+    seed = 77
+    out = mig.run_case(c, params=params, seed=seed)
+    tup, ex, home, init = c.keyed_oracle("replay", params, seed=seed)
+    assert np.array_equal(util.pack_history(out[:9]), util.pack_history(tup[:9]))
+    for k in util.VECS:
+        assert np.array_equal(np.asarray(out[util.VEC_INDEX[k]]), tup[util.VEC_INDEX[k]], equal_nan=True), k
+    assert (np.asarray(out[15]) > 0).sum() > 300
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", util.CASES)
+@pytest.mark.parametrize("launch", ["persistent", "per_day"])
+def test_gpu_replay_equals_instrumented_reference(gpu_engine_module, name, launch):
+    c = util.Case(name)
+    fx = _frozen(name)
+    params = dict(c.params)
+    T = int(params["T"])
+    # the reference's own prologue ran in the instrumented copy (MT picks of :181, :187): the host prologue of the
+    # drop-in run_model replays exactly those
+    home, init = tables_mod.prologue(c.seed, c.age_groups, c.n, c.fraction_stay_home, params["initial_infected_fraction"])
+    eng = c.gpu_engine(gpu_engine_module, params, "replay", launch=launch)
+    eng.run([c.seed], [home], [init])
+    packed = eng.history("packed")
+    want = fx["history_packed"]
+    if not np.array_equal(packed, want):
+        bad = np.argwhere(packed != want)
+        t, i = bad[0]
+        raise AssertionError("history differs at %d agent-days; first (t=%d, i=%d): gpu=%#x reference=%#x"
+                             % (len(bad), t, i, packed[t, i], want[t, i]))
+    for k in util.VECS:
+        assert np.array_equal(eng.agent_vector(k), fx["out_" + k], equal_nan=True), k
+    assert np.array_equal(eng.tallies(0), util.tallies_from_history(util.unpack_history(want), c.age, T)), \
+        "per-day per-age counts differ"
+    eng.close()
