@@ -641,7 +641,7 @@ def dropin_leg(args, pop, device):
          tabs["p_critical_death"], tabs["mean_time_to_isolate_factor"], tabs["lockdown_factor_age"],
          np.full(n, tabs["p_infect_household"]), np.zeros(101), p)
     import contextlib, io
-    ms = []
+    ms, ms_reads, ms_eager, ms_numpy = [], [], [], []
     with contextlib.redirect_stdout(io.StringIO()):
         for seed in range(4):
             t0 = time.perf_counter()
@@ -649,11 +649,33 @@ def dropin_leg(args, pop, device):
             deaths = int(out[7].sum(axis=1)[-1])
             ms.append((time.perf_counter() - t0) * 1e3)
         dev_ms = sum(drop.last_engine.last_run_ms3())
+        for seed in range(4, 7):   # + what run_simulation.py:448-460 reads of a run: two vectors, three final rows
+            t0 = time.perf_counter()
+            out = drop.run_model(seed, *a, tracing="off")
+            te, nib = out[15], out[9]
+            early = np.logical_and(te <= 20, te > 0)
+            r0 = float(nib[early].mean()) if early.any() else 0.0
+            final = int(out[7][-1].sum()) + int(out[6][-1].sum()) + int(out[0][-1].sum())
+            ms_reads.append((time.perf_counter() - t0) * 1e3)
+        for seed in range(7, 9):   # all ten vectors as host arrays at once (the reference's contract taken literally)
+            t0 = time.perf_counter()
+            out = drop.run_model(seed, *a, tracing="off", vectors="eager")
+            ms_eager.append((time.perf_counter() - t0) * 1e3)
+        for seed in range(9, 11):  # round 2's first version of this call: NumPy replay of the picks + eager vectors
+            t0 = time.perf_counter()
+            out = drop.run_model(seed, *a, tracing="off", vectors="eager", prologue="numpy")
+            ms_numpy.append((time.perf_counter() - t0) * 1e3)
+        del out, te, nib
         drop.clear_engine_cache()
-    return {"first_call_ms": ms[0], "warm_call_ms": float(np.mean(ms[1:])), "device_ms_last_call": dev_ms,
-            "deaths_last_call": deaths,
-            "what": "seir_individual.run_model per seed: build_tables + tables.prologue (the reference's MT picks: two "
-                    "n-permutations on the host) + seir_run + 10 float64[n] result vectors D2H; engine cached after call 1"}
+    return {"first_call_ms": ms[0], "warm_call_ms": float(np.mean(ms[1:])),
+            "warm_call_plus_driver_reads_ms": float(np.mean(ms_reads)),
+            "warm_call_eager_vectors_ms": float(np.mean(ms_eager)),
+            "warm_call_eager_vectors_numpy_prologue_ms": float(np.mean(ms_numpy)),
+            "device_ms_last_call": dev_ms, "deaths_last_call": deaths, "r0_early_last_read": r0, "final_rows_sum": final,
+            "what": "seir_individual.run_model per seed: build_tables + the reference's MT19937 prologue picks "
+                    "(seir_prologue_mt, host) + seir_run + tallies; the nine histories and the ten float64[n] vectors "
+                    "come back lazy and are copied when first used (plus_driver_reads: time_exposed, num_infected_by, "
+                    "D[-1], R[-1], S[-1]); eager_vectors: all ten vectors D2H at once; engine cached after call 1"}
 
 
 def sharded_c3_leg(args, dist, rank, world, local):

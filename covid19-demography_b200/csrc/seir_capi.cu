@@ -677,6 +677,9 @@ struct seir_handle {
     DevBuf<int64_t> init_off;
     DevBuf<double> p_hh, tables, enlam, stage_d;
     DevBuf<uint8_t> hist, stage_u8, hist_prev;
+    DevBuf<AgentRec> rec_prev;          // records / infected bits / tracer words of the run set aside by seir_history_preserve:
+    DevBuf<uint32_t> inbox_prev, trc_prev;   // the per-agent vectors of that run stay readable (which | SEIR_VEC_PREVIOUS)
+    bool prev_vectors = false, prev_trc = false;
     int prev_T = 0;   // rows of the history set aside by seir_history_preserve (0: none)
     DevBuf<uint32_t> inbox, tally, home, list_old, list_new, list_cnt;
     DevBuf<uint32_t> pk_pool;   // day buckets of the parked agents
@@ -944,6 +947,10 @@ static void fill_ctx(seir_handle *h)
 extern "C" {
 
 const char *seir_last_error(void) { return g_err.c_str(); }
+
+}  // extern "C"
+#include "seir_prologue_host.cuh"   // seir_prologue_mt: the reference's MT19937 picks of one seed, host only
+extern "C" {
 
 int seir_device_count(void)
 {
@@ -1570,10 +1577,19 @@ int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out)
 {
     if (!h || !out) return fail("seir_get_agent_vector: NULL argument");
     if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
+    const bool previous = (which & SEIR_VEC_PREVIOUS) != 0;
+    which &= ~SEIR_VEC_PREVIOUS;
     if (which < 0 || which >= SEIR_VEC_COUNT) return fail("vector id out of range");
+    if (previous && !h->prev_vectors) return fail("no run has been set aside (seir_history_preserve)");
     CK(cudaSetDevice(h->device));
     CK(h->stage_d.alloc((size_t)h->n));
-    seir_agent_vector_kernel<<<h->sms * 4, 256, 0, h->stream>>>(h->cx, replica, which, h->stage_d.p);
+    DevCtx cx = h->cx;
+    if (previous) {
+        cx.rec = h->rec_prev.p;
+        cx.inbox = h->inbox_prev.p;
+        cx.trc = h->prev_trc ? h->trc_prev.p : nullptr;
+    }
+    seir_agent_vector_kernel<<<h->sms * 4, 256, 0, h->stream>>>(cx, replica, which, h->stage_d.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, h->stage_d.p, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1605,8 +1621,20 @@ int seir_history_preserve(seir_handle *h)
     const size_t bytes = (size_t)h->n_rep * h->prm.T * h->n_pad;
     CK(h->hist_prev.alloc(bytes));
     CK(cudaMemcpyAsync(h->hist_prev.p, h->hist.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    // the per-agent vectors (:392) are functions of the records, the ever-infected bits and the tracer's words
+    const size_t cells = (size_t)h->n_rep * h->n_pad;
+    CK(h->rec_prev.alloc(cells));
+    CK(h->inbox_prev.alloc(cells / 16));
+    CK(cudaMemcpyAsync(h->rec_prev.p, h->rec.p, cells * sizeof(AgentRec), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->inbox_prev.p, h->inbox.p, cells / 16 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    h->prev_trc = h->trace_alloc && h->trc.p != nullptr;
+    if (h->prev_trc) {
+        CK(h->trc_prev.alloc(cells));
+        CK(cudaMemcpyAsync(h->trc_prev.p, h->trc.p, cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->prev_T = h->prm.T;
+    h->prev_vectors = true;
     return 0;
 }
 
@@ -1800,7 +1828,7 @@ void seir_destroy(seir_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     h->stat.release(); h->grp_off.release(); h->grp_members.release(); h->init_ids.release(); h->init_off.release();
-    h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release();
+    h->p_hh.release(); h->tables.release(); h->enlam.release(); h->stage_d.release(); h->hist.release(); h->rec_prev.release(); h->inbox_prev.release(); h->trc_prev.release();
     h->stage_u8.release(); h->inbox.release(); h->tally.release(); h->home.release(); h->winner.release(); h->xday.release();
     h->counters.release(); h->rec.release(); h->seeds.release(); h->barrier.release(); h->ctl.release();
     for (int g = 0; g < kMaxShards; ++g)

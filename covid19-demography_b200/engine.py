@@ -23,6 +23,7 @@ VEC = {"num_infected_by": 0, "time_documented": 1, "time_to_activation": 2, "tim
        "time_to_critical": 12, "num_infected_by_outside": 13}
 PLANE = {"S": 0, "E": 1, "Mild": 2, "Documented": 3, "Severe": 4, "Critical": 5, "R": 6, "D": 7, "Q": 8,
          "packed": 9}
+VEC_PREVIOUS = 256   # include/seir_b200.h SEIR_VEC_PREVIOUS
 PLANES_IN_ORDER = ("S", "E", "Mild", "Documented", "Severe", "Critical", "R", "D", "Q")
 
 EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "seir_get_tallies",
@@ -31,7 +32,7 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
            "seir_get_stage_times", "seir_get_cohorts", "seir_shard_export", "seir_shard_attach", "seir_get_visits",
            "seir_history_preserve", "seir_run_ex", "seir_set_table_bank", "seir_get_prologue", "seir_abi_sizes",
-           "seir_shard_set_threshold")
+           "seir_shard_set_threshold", "seir_prologue_mt")
 
 
 SHARD_HANDLES = 6   # include/seir_b200.h SEIR_SHARD_HANDLES
@@ -111,6 +112,8 @@ def load_library():
     lib.seir_device_count.restype = C.c_int
     lib.seir_host_register.argtypes = [C.c_void_p, C.c_uint64]
     lib.seir_host_unregister.argtypes = [C.c_void_p]
+    lib.seir_prologue_mt.argtypes = [C.c_uint32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.seir_probe_draws.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -184,6 +187,7 @@ class Engine:
         if offs.shape[0] != _tables.N_AGES + 1:
             raise ValueError("age_groups must have %d entries" % _tables.N_AGES)
         self.group_sizes = np.diff(offs)
+        self.group_csr = (offs, members)   # kept for prologue_mt (the reference's picks per seed, host only)
         arrs = [hh, np.ascontiguousarray(age, dtype=np.int64), np.ascontiguousarray(diabetes, dtype=np.int64),
                 np.ascontiguousarray(hypertension, dtype=np.int64), offs, members,
                 np.ascontiguousarray(p_infect_household, dtype=np.float64)]
@@ -349,11 +353,20 @@ class Engine:
         device-to-device copy); views of the run before that, if still alive, take a host copy."""
         live = [v for v in (r() for r in self._views) if v is not None]
         older = [v for v in live if v._serial == self.prev_serial and v._host is None]
-        if older:
-            packed = self.history("packed", previous=True, rows=older[0].shape[0])
-            for v in older:
+        planes = [v for v in older if v.ndim == 2]
+        if planes:
+            packed = self.history("packed", previous=True, rows=planes[0].shape[0])
+            for v in planes:
                 v._host = packed
+        for v in older:
+            if v.ndim == 1:       # a per-agent vector nobody has used yet: it takes its host copy now
+                v._get()
         last = [v for v in live if v._serial == self.run_serial and v._host is None]
+        if last and self.history_mode != "eager":   # (nothing is set aside on the device in this mode)
+            for v in last:
+                if v.ndim == 1:
+                    v._get()
+            last = [v for v in last if v._host is None]
         if last:
             _check(self.lib.seir_history_preserve(self._h))
             self.prev_serial = self.run_serial
@@ -383,10 +396,11 @@ class Engine:
         _check(self.lib.seir_get_cohorts(self._h, replica, _ptr(out)))
         return out
 
-    def agent_vector(self, which, replica=0):
+    def agent_vector(self, which, replica=0, previous=False):
+        """float64[n]; previous: of the run set aside by the last seir_history_preserve (see _keep_live_histories)."""
         out = np.empty(self.n, dtype=np.float64)
-        _check(self.lib.seir_get_agent_vector(self._h, replica, VEC[which] if isinstance(which, str) else which,
-                                              _ptr(out)))
+        code = (VEC[which] if isinstance(which, str) else which) | (VEC_PREVIOUS if previous else 0)
+        _check(self.lib.seir_get_agent_vector(self._h, replica, code, _ptr(out)))
         return out
 
     def history(self, which, t0=0, t1=None, replica=0, previous=False, rows=None):
@@ -430,6 +444,45 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def group_csr(age_groups):
+    """The reference's `age_groups` tuple (seir_individual.py:36) as (offsets int64[n_ages+1], members int64[n])."""
+    lens = np.array([len(g) for g in age_groups], dtype=np.int64)
+    offs = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    members = (np.concatenate([np.asarray(g, dtype=np.int64) for g in age_groups]) if offs[-1] > 0
+               else np.zeros(0, dtype=np.int64))
+    return offs, np.ascontiguousarray(members, dtype=np.int64)
+
+
+def prologue_mt(seed, csr, n, fraction_stay_home, initial_infected_fraction):
+    """The reference's prologue picks for `seed` (seir_individual.py:163, 176-187) through the library's host routine
+    `seir_prologue_mt`: the same (home_real bool[n], initial_infected int64[k]) as `tables.prologue` -- which replays them
+    with two NumPy RandomState permutations, 0.3 s at n = 10 M -- without shuffling: the Mersenne-Twister draws are
+    consumed in the reference's order and only the k picked positions are followed through the swaps.  `csr` is
+    `group_csr(age_groups)` (an Engine keeps its own as `engine.group_csr`).  No device is touched."""
+    lib = load_library()
+    offs, members = csr
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    members = np.ascontiguousarray(members, dtype=np.int64)
+    if members.shape != (n,) or int(offs[-1]) != n:
+        raise ValueError("age_groups must partition the n agents")
+    fsh = None
+    if fraction_stay_home is not None:
+        fsh = np.ascontiguousarray(fraction_stay_home, dtype=np.float64)
+        if fsh.shape != (offs.shape[0] - 1,):
+            raise ValueError("fraction_stay_home must have one entry per age")
+        if not fsh.any():
+            fsh = None
+    k0 = int(initial_infected_fraction * n)
+    home = np.empty(n, dtype=np.uint8)
+    init = np.empty(max(k0, 1), dtype=np.int64)
+    got = np.zeros(1, dtype=np.int64)
+    _check(lib.seir_prologue_mt(int(seed) & 0xFFFFFFFF, n, offs.shape[0] - 1, _ptr(offs), _ptr(members), _ptr(fsh),
+                                float(initial_infected_fraction), _ptr(home), _ptr(init), init.size, _ptr(got)))
+    assert int(got[0]) == k0
+    return home.view(np.bool_), init[:k0]
 
 
 def pin(array):

@@ -1,4 +1,5 @@
-"""Lazy stand-ins for the nine bool[T, n] history arrays `run_model` returns (seir_individual.py:392).
+"""Lazy stand-ins for the nine bool[T, n] history arrays and the ten float64[n] vectors `run_model` returns
+(seir_individual.py:392).
 
 The reference materialises 9 x T x n bools on the host (5.4 GB at n = 10 M, T = 60).  Here the
 history stays on the device as ONE packed byte per agent-day; a `HistoryPlane` fetches only what is
@@ -89,6 +90,79 @@ class HistoryPlane:
 
     def __repr__(self):
         return "HistoryPlane(%s, shape=%s, device-resident)" % (self._plane, self.shape)
+
+
+class AgentVector(np.lib.mixins.NDArrayOperatorsMixin):
+    """Lazy stand-in for one of the ten float64[n] vectors of the reference's result tuple (seir_individual.py:392).
+
+    The reference hands back ten fresh n-vectors per call (0.8 GB at n = 10 M: a fifth of a second of PCIe and page
+    faults per seed) of which a driver reads two or three (`time_exposed`, `num_infected_by`: run_simulation.py:448-453).
+    Here a vector is computed from the device-resident records and copied when it is first USED: arithmetic and
+    comparisons (NumPy ufuncs), indexing, `np.asarray`, any ndarray method or attribute (`.mean()`, `.astype`, ...),
+    iteration, pickling.  After that it IS a host float64 array.  Like the histories it survives the next run on the same
+    device-resident population (the records of the last run are set aside on the device) and takes its host copy when
+    a second run would overwrite it."""
+    __array_priority__ = 100
+
+    def __init__(self, engine, which, replica=0):
+        self._e, self._which, self._rep = engine, which, replica
+        self._host = None
+        self.shape = (engine.n,)
+        self.dtype = np.dtype(np.float64)
+        self.ndim = 1
+        self.size = engine.n
+        self._serial = getattr(engine, "run_serial", 0)
+        if hasattr(engine, "register_view"):
+            engine.register_view(self)
+
+    def _get(self):
+        if self._host is None:
+            cur = getattr(self._e, "run_serial", 0)
+            if cur == self._serial:
+                self._host = self._e.agent_vector(self._which, self._rep)
+            elif getattr(self._e, "prev_serial", -1) == self._serial:
+                self._host = self._e.agent_vector(self._which, self._rep, previous=True)
+            else:
+                raise RuntimeError("this vector was overwritten by a later run on the same device-resident population")
+            self._e = None
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._get()
+        if dtype is not None and np.dtype(dtype) != a.dtype:
+            return a.astype(dtype)
+        return a.copy() if copy else a
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        unwrap = lambda x: x._get() if isinstance(x, AgentVector) else x  # noqa: E731
+        if "out" in kwargs:
+            kwargs["out"] = tuple(unwrap(x) for x in kwargs["out"])
+        return getattr(ufunc, method)(*[unwrap(x) for x in inputs], **kwargs)
+
+    def __getitem__(self, key):
+        return self._get()[key]
+
+    def __setitem__(self, key, value):
+        self._get()[key] = value
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getattr__(self, name):   # (only reached for names not set above: the ndarray's own methods and attributes)
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self._get(), name)
+
+    def __reduce__(self):
+        return (np.asarray, (self._get(),))
+
+    def __repr__(self):
+        if self._host is None:
+            return "AgentVector(%s, shape=%s, device-resident)" % (self._which, self.shape)
+        return repr(self._host)
 
 
 _PLANE_INDEX = {"S": 0, "E": 1, "Mild": 2, "Documented": 3, "Severe": 4, "Critical": 5, "R": 6, "D": 7, "Q": 8}

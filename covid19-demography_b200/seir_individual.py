@@ -8,7 +8,9 @@ kernels on a B200 through libseir_b200.so; there is no CPU fallback.
 
 Differences a caller can see (DESIGN.md has the full list):
   * the nine histories come back as lazy `HistoryPlane` objects over the device-resident packed
-    history (`np.asarray(X)` materialises the reference's bool[T, n]);
+    history (`np.asarray(X)` materialises the reference's bool[T, n]), the ten per-agent vectors as lazy
+    `AgentVector` objects that turn into host float64 arrays when first used (`SEIR_B200_VECTORS=eager`:
+    plain ndarrays at once);
   * draws inside the day loop are keyed Philox draws (include/seir_draws.h), not the reference's
     single Mersenne-Twister stream, so trajectories agree with the reference in distribution,
     not per seed; Home_real and initial_infected ARE the reference's for the same seed;
@@ -30,13 +32,18 @@ if os.path.dirname(_HERE) not in sys.path:
 
 from covid19_demography_b200 import engine as _engine  # noqa: E402
 from covid19_demography_b200 import tables as _tables  # noqa: E402
-from covid19_demography_b200.history import HistoryPlane  # noqa: E402
+from covid19_demography_b200.history import AgentVector, HistoryPlane  # noqa: E402
 
 OPTIONS = {
     "mode": os.environ.get("SEIR_B200_MODE", "native"),          # "native" | "replay"
     "launch": os.environ.get("SEIR_B200_LAUNCH", "persistent"),  # "persistent" | "per_day"
     "tracing": os.environ.get("SEIR_B200_TRACING", "as_reference"),  # "as_reference" | "off"
     "device": int(os.environ.get("SEIR_B200_DEVICE", "0")),
+    # the ten float64[n] result vectors: "lazy" (computed and copied when first used, history.AgentVector) | "eager"
+    "vectors": os.environ.get("SEIR_B200_VECTORS", "lazy"),
+    # the reference's Mersenne-Twister picks of Home_real / initial_infected (:176-187): "native" (the library's host
+    # routine seir_prologue_mt) | "numpy" (tables.prologue: two RandomState permutations) -- the same picks either way
+    "prologue": os.environ.get("SEIR_B200_PROLOGUE", "native"),
 }
 last_engine = None
 """The Engine of the most recent run_model call (its histories stay valid until the next call on the same population)."""
@@ -130,8 +137,6 @@ def run_model(seed, households, age, age_groups, diabetes, hypertension, contact
     group_sizes = np.array([len(g) for g in age_groups], dtype=np.int64)
     tb = _tables.build_tables(contact_matrix, group_sizes, p, mean_time_to_isolate_factor, p_mild_severe,
                               p_severe_critical, p_critical_death, with_replay=(opt["mode"] == "replay"))
-    home_real, initial_infected = _tables.prologue(seed, age_groups, n, fraction_stay_home,
-                                                   p["initial_infected_fraction"])
     # the population stays resident on the device between calls (the drivers call once per seed with the same
     # arrays): only the scalars, the tables and the per-run picks travel
     key = _population_key(households, age, diabetes, hypertension, p_infect_household, opt)
@@ -140,12 +145,21 @@ def run_model(seed, households, age, age_groups, diabetes, hypertension, contact
         device=opt["device"], mode=opt["mode"], launch=opt["launch"], tracing_enabled=tracing_enabled))
     if not fresh:
         eng.set_params(p, tb, tracing_enabled=tracing_enabled)
+    if opt["prologue"] == "numpy":
+        home_real, initial_infected = _tables.prologue(seed, age_groups, n, fraction_stay_home,
+                                                       p["initial_infected_fraction"])
+    else:
+        home_real, initial_infected = _engine.prologue_mt(seed, eng.group_csr, n, fraction_stay_home,
+                                                          p["initial_infected_fraction"])
     print('run_model')
     eng.run([seed], [home_real], [initial_infected])
     last_engine = eng
     tal = eng.tallies(0)
     planes = tuple(HistoryPlane(eng, k, tallies=tal) for k in _engine.PLANES_IN_ORDER)
-    v = eng.agent_vector
+    if opt["vectors"] == "eager":
+        v = eng.agent_vector
+    else:
+        v = lambda which: AgentVector(eng, which)  # noqa: E731
     return planes + (v("num_infected_by"), v("time_documented"), v("time_to_activation"), v("time_to_death"),
                      v("time_to_recovery"), v("time_critical"), v("time_exposed"), v("num_infected_asympt"),
                      age, v("time_infected"), v("time_to_severe"))

@@ -146,6 +146,7 @@ enum {
 enum { SEIR_H_S = 0, SEIR_H_E, SEIR_H_MILD, SEIR_H_DOCUMENTED, SEIR_H_SEVERE, SEIR_H_CRITICAL,
        SEIR_H_R, SEIR_H_D, SEIR_H_Q, SEIR_H_PACKED /* raw byte: bits0-2 compartment, bit3 Q, bit4 Documented */ };
 #define SEIR_H_PREVIOUS 16         /* OR into `which`: read the history set aside by seir_history_preserve */
+#define SEIR_VEC_PREVIOUS 256      /* OR into the vector id: read the per-agent vector of the run set aside by seir_history_preserve */
 
 typedef struct seir_handle seir_handle;
 
@@ -202,14 +203,15 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out);
  * age fractions, median age, CFR by age group) follows from these counts. */
 int seir_get_cohorts(seir_handle *h, int replica, int64_t *out);
 
-/* One per-agent vector, out[n] doubles. */
+/* One per-agent vector, out[n] doubles (`which` = SEIR_VEC_*, optionally | SEIR_VEC_PREVIOUS). */
 int seir_get_agent_vector(seir_handle *h, int replica, int which, double *out);
 
 /* History plane `which` for days [t0, t1), out[(t1-t0)*n] bytes (0/1, or the packed byte). */
 int seir_get_history(seir_handle *h, int replica, int which, int t0, int t1, uint8_t *out);
 /* The reference returns fresh arrays from every run_model call; here the T x n history lives on the device and the next
  * seir_run overwrites it.  seir_history_preserve sets the packed history of the LAST run aside (one device-to-device
- * copy, 0.2 ms at n = 10 M, T = 60) so that it stays readable (which | SEIR_H_PREVIOUS) across the next run. */
+ * copy, 0.2 ms at n = 10 M, T = 60) so that it stays readable (which | SEIR_H_PREVIOUS) across the next run; the records
+ * behind the per-agent vectors are set aside with it (32 B per agent; seir_get_agent_vector with which | SEIR_VEC_PREVIOUS). */
 int seir_history_preserve(seir_handle *h);
 
 /* Counters of the last run: out[0]=kernels launched, out[1]=sum over days of active agents
@@ -230,6 +232,16 @@ int seir_get_stage_times(seir_handle *h, int64_t *out);
 /* debug: raw copy of one of the parallel tracer's per-replica arrays of the last tracing day
  * (0 ctl {n_roots, n_reached, alloc, n_big}, 1 roots, 2 representatives, 3 component sizes, 4 reached, 5 leaders, 6 parents) */
 int seir_debug_trace_array(seir_handle *h, int which, int replica, void *out, uint64_t bytes);
+
+/* HOST ONLY (no device is touched): the prologue picks the reference makes for `seed` -- seir_individual.py:163 seeds
+ * numba's MT19937, :178-182 draw np.random.choice(matches, int(fraction_stay_home[a]*len), replace=False) per non-empty
+ * age group, :187 np.random.choice(n, int(initial_infected_fraction*n), replace=False) -- so that the drop-in run_model
+ * infects and shelters the very agents the reference would.  group_offsets[n_ages+1] / group_members[n]: the age_groups
+ * tuple (:36) in CSR form, members ascending (np.where order).  fraction_stay_home may be NULL (all zero).
+ * home_real[n] (0/1) and initial_infected[*n_initial] are written; initial_cap is the room in initial_infected. */
+int seir_prologue_mt(uint32_t seed, int64_t n, int n_ages, const int64_t *group_offsets, const int64_t *group_members,
+                     const double *fraction_stay_home, double initial_infected_fraction, uint8_t *home_real,
+                     int64_t *initial_infected, int64_t initial_cap, int64_t *n_initial);
 
 /* Page-lock / unlock a caller-owned host buffer so the per-run copies in seir_run are DMA transfers. */
 int seir_host_register(void *ptr, uint64_t bytes);

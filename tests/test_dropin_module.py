@@ -131,8 +131,58 @@ def test_histories_of_earlier_calls_stay_valid_and_the_engine_is_reused(gpu_engi
             assert np.array_equal(np.asarray(out[k]), np.asarray(tup[k])), k
             assert np.array_equal(out[k].sum(axis=1), np.asarray(tup[k]).sum(axis=1))
         assert np.array_equal(out[7][-1], np.asarray(tup[7])[-1]) and np.array_equal(out[15], tup[15])
+        for name, k in util.VEC_INDEX.items():   # the ten lazy vectors: set aside on the device / host copies
+            assert np.array_equal(np.asarray(out[k]), tup[k], equal_nan=True), name
     # a different population gets its own engine; the cache keeps the two most recent
     c2 = util.Case("china_default")
     m.run_model(5, *c2.model_args(c2.no_tracing_params()))
     assert len(m._engine_cache) == 2
+    m.clear_engine_cache()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vectors", ["lazy", "eager"])
+def test_result_vectors_lazy_and_eager_with_tracing(gpu_engine_module, vectors):
+    """The ten per-agent vectors of :392 as lazy AgentVectors (default) and as plain arrays (SEIR_B200_VECTORS=eager),
+    with tracing as compiled (time_documented then also depends on the tracer's words, which are set aside too), read
+    only after later runs have overwritten the device state."""
+    from covid19_demography_b200.history import AgentVector
+    m = _module()
+    m.clear_engine_cache()
+    c = util.Case("italy_tracing")
+    params = dict(c.params)
+    outs, oracles = [], []
+    for seed in (4, 5, 6):
+        outs.append(m.run_model(seed, *c.model_args(params), vectors=vectors))
+        oracles.append(c.keyed_oracle("native", params, seed=seed)[0])
+    for out, tup in zip(outs, oracles):
+        for name, k in util.VEC_INDEX.items():
+            assert isinstance(out[k], AgentVector if vectors == "lazy" else np.ndarray)
+            assert np.array_equal(np.asarray(out[k]), tup[k], equal_nan=True), name
+        assert (np.asarray(out[10]) > 0).sum() > 50   # documented cases: the tracer ran
+    # a used vector is a host array from then on, whatever runs later
+    te = outs[2][15]
+    first = te[te >= 0].copy()
+    m.run_model(9, *c.model_args(params), vectors=vectors)
+    m.run_model(10, *c.model_args(params), vectors=vectors)
+    assert np.array_equal(te[te >= 0], first)
+    m.clear_engine_cache()
+
+
+@pytest.mark.gpu
+def test_native_prologue_gives_the_numpy_replays_run(gpu_engine_module):
+    """run_model's default prologue (seir_prologue_mt) and the NumPy replay (prologue="numpy") pick the same agents:
+    the two runs are the same run."""
+    m = _module()
+    m.clear_engine_cache()
+    c = util.Case("italy_policy")   # shelter in place for the 60+: Home_real matters
+    params = c.no_tracing_params()
+    a = m.run_model(c.seed, *c.model_args(params), prologue="native")
+    b = m.run_model(c.seed, *c.model_args(params), prologue="numpy")
+    for k in range(20):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k]), equal_nan=True), k
+    home, init = m.last_engine.prologue_picks()
+    h0, i0 = __import__("covid19_demography_b200.tables", fromlist=["prologue"]).prologue(
+        c.seed, c.age_groups, c.n, c.fraction_stay_home, params["initial_infected_fraction"])
+    assert np.array_equal(home, h0) and np.array_equal(np.sort(init), np.sort(i0))
     m.clear_engine_cache()
