@@ -19,7 +19,6 @@ import pytest
 
 import ref_shim
 import util
-from covid19_demography_b200 import tables as tables_mod
 
 
 def _frozen(name):
@@ -74,14 +73,22 @@ def test_live_instrumented_reference_on_an_unfrozen_run():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", util.CASES)
 @pytest.mark.parametrize("launch", ["persistent", "per_day"])
-def test_gpu_replay_equals_instrumented_reference(gpu_engine_module, name, launch):
+@pytest.mark.parametrize("passes", ["default", "staged_only", "mixed"])
+def test_gpu_replay_equals_instrumented_reference(gpu_engine_module, monkeypatch, name, launch, passes):
+    # both pass forms of the day loop against the reference's code: the fixtures are small, so by default their days run
+    # as warp-cooperative passes; staged_only / mixed force the staged (dense-day) pass on all / on the longer days
+    if passes == "staged_only":
+        monkeypatch.setenv("SEIR_SPARSE_ROUNDS", "0")
+    elif passes == "mixed":
+        monkeypatch.setenv("SEIR_SPARSE_MAX", "40")
     c = util.Case(name)
     fx = _frozen(name)
     params = dict(c.params)
     T = int(params["T"])
     # the reference's own prologue ran in the instrumented copy (MT picks of :181, :187): the host prologue of the
-    # drop-in run_model replays exactly those
-    home, init = tables_mod.prologue(c.seed, c.age_groups, c.n, c.fraction_stay_home, params["initial_infected_fraction"])
+    # drop-in run_model (seir_prologue_mt) makes exactly those
+    home, init = gpu_engine_module.prologue_mt(c.seed, gpu_engine_module.group_csr(c.age_groups), c.n,
+                                               c.fraction_stay_home, params["initial_infected_fraction"])
     eng = c.gpu_engine(gpu_engine_module, params, "replay", launch=launch)
     eng.run([c.seed], [home], [init])
     packed = eng.history("packed")
