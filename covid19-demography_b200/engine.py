@@ -372,6 +372,22 @@ class Engine:
             self.prev_serial = self.run_serial
         self._views = [r for r in self._views if r() is not None and r()._host is None]
 
+    def keep_views_on_host(self):
+        """Before the handle goes away while somebody still holds lazy results of its last two runs (the drop-in
+        module's engine cache evicting a population): every live history takes a host copy of its run's packed
+        history, every live vector becomes the host array it stands for."""
+        live = [v for v in (r() for r in self._views) if v is not None and v._host is None]
+        for serial, previous in ((self.run_serial, False), (self.prev_serial, True)):
+            planes = [v for v in live if v.ndim == 2 and v._serial == serial]
+            if planes and (not previous or serial != self.run_serial):
+                packed = self.history("packed", previous=previous, rows=planes[0].shape[0] if previous else None)
+                for v in planes:
+                    v._host = packed
+        for v in live:
+            if v.ndim == 1:
+                v._get()
+        self._views = []
+
     def last_run_ms(self):
         a, b = C.c_float(), C.c_float()
         _check(self.lib.seir_last_run_ms(self._h, C.byref(a), C.byref(b)))

@@ -75,7 +75,9 @@ def _engine_for(key, build):
         return build(), True   # no cache: every call owns its engine (earlier histories stay readable)
     if fresh:
         while len(_engine_cache) >= max(1, ENGINE_CACHE_SIZE):
-            _engine_cache.pop(next(iter(_engine_cache))).close()
+            old = _engine_cache.pop(next(iter(_engine_cache)))
+            old.keep_views_on_host()   # results of that population somebody still holds stay readable
+            old.close()
         eng = build()
     _engine_cache[key] = eng
     return eng, fresh
@@ -84,6 +86,7 @@ def _engine_for(key, build):
 def clear_engine_cache():
     global last_engine
     for eng in _engine_cache.values():
+        eng.keep_views_on_host()
         eng.close()
     _engine_cache.clear()
     last_engine = None

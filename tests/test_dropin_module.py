@@ -186,3 +186,23 @@ def test_native_prologue_gives_the_numpy_replays_run(gpu_engine_module):
         c.seed, c.age_groups, c.n, c.fraction_stay_home, params["initial_infected_fraction"])
     assert np.array_equal(home, h0) and np.array_equal(np.sort(init), np.sort(i0))
     m.clear_engine_cache()
+
+
+@pytest.mark.gpu
+def test_results_outlive_an_evicted_engine(gpu_engine_module):
+    """The engine cache closes the least recently used population; lazy histories and vectors of its last two runs that
+    somebody still holds take host copies first (the reference's arrays never expire)."""
+    m = _module()
+    m.clear_engine_cache()
+    c = util.Case("italy_seeded")
+    params = c.no_tracing_params()
+    a = m.run_model(1, *c.model_args(params))
+    b = m.run_model(2, *c.model_args(params))
+    m.clear_engine_cache()            # closes the handle
+    for out, seed in ((a, 1), (b, 2)):
+        tup = c.keyed_oracle("native", params, seed=seed)[0]
+        for k in (0, 3, 7, 8):
+            assert np.array_equal(np.asarray(out[k]), np.asarray(tup[k])), k
+        assert np.array_equal(out[7][-1], np.asarray(tup[7])[-1])
+        for name, k in util.VEC_INDEX.items():
+            assert np.array_equal(np.asarray(out[k]), tup[k], equal_nan=True), name

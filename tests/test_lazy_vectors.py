@@ -15,6 +15,7 @@ class FakeEngine:
     """The part of engine.Engine an AgentVector touches; `vectors[serial]` is what run `serial` produced."""
     _keep_live_histories = engine_mod.Engine._keep_live_histories
     register_view = engine_mod.Engine.register_view
+    keep_views_on_host = engine_mod.Engine.keep_views_on_host
 
     def __init__(self, n, history_mode="eager"):
         self.n, self.T = n, 5
@@ -122,3 +123,16 @@ def test_history_on_demand_engines_take_host_copies_before_the_next_run():
     e.run(_values(2, n))
     assert e.preserves == 0 and e.fetches == [("time_exposed", False)]
     assert np.array_equal(v, a["time_exposed"])
+
+
+def test_vectors_outlive_their_engine():
+    n = 200
+    e = FakeEngine(n)
+    a, b = _values(1, n), _values(2, n)
+    e.run(a)
+    va = AgentVector(e, "time_exposed")
+    e.run(b)
+    vb = AgentVector(e, "num_infected_by")
+    e.keep_views_on_host()          # what the drop-in module does before it closes an evicted engine
+    e.vectors, e.set_aside = None, None
+    assert np.array_equal(va, a["time_exposed"]) and np.array_equal(vb, b["num_infected_by"])
