@@ -46,6 +46,9 @@ constexpr int kAges = SEIR_N_AGES;
 #ifndef SEIR_MIN_BLOCKS
 #define SEIR_MIN_BLOCKS 2
 #endif
+#ifndef SEIR_EVE_PARK
+#define SEIR_EVE_PARK 1   // staged passes: agents with a progression step due tomorrow go through tomorrow's day bucket (agent_day)
+#endif
 constexpr int kThreads = SEIR_THREADS;   // threads per CTA of the day-step kernels
 constexpr int kMinBlocks = SEIR_MIN_BLOCKS;
 constexpr int kVec = 16;                 // agents per 16 B vector of state bytes
@@ -901,6 +904,15 @@ static __device__ __forceinline__ int agent_day(const DevCtx &cx, PassSmem &sm, 
     }
     SEIR_FINE(7);
     if (!active) return DAY_DROP;
+#if SEIR_EVE_PARK
+    // An agent whose activation (:256-272) or Mild -> Severe step (:291-311) is due TOMORROW goes through tomorrow's day
+    // bucket instead of the transmitting list: there every lane of its warp has an event, while among 32 transmitting
+    // agents two or three have one and the whole warp walks through their draws (two Philox blocks, three exponential
+    // times) at a tenth of its lanes.  Where an agent is listed changes nothing about what happens to it.
+    if (!nq && t + 1 < v.T &&
+        ((ncomp == C_E && due(t + 1, r.t_exposed(), r.tt_activation())) || (ncomp == C_MILD && due(t + 1, t_infected_of(r), r.tt_severe()))))
+        return DAY_KEEP_Q;  // (wake day offset 0)
+#endif
     if (!nq) return DAY_KEEP;
     // An agent that turned quarantined TODAY sits in a warp of transmitting agents: it is looked at again tomorrow, among
     // the parked agents due that day -- warps in which every lane works out its wake day (the scan of the documentation
@@ -1477,6 +1489,9 @@ static __device__ __noinline__ void sparse_rounds(const DevCtx &cx, PassSmem &sm
                 if (kind == 1) atomicAdd(&sm.cnt[1], 1u);
             }
         }
+        // (an agent a staged pass routed through today's bucket on the eve of its progression step -- agent_day -- and that
+        // may transmit tomorrow: the bucket list has no slot in tomorrow's transmitting list, it goes on through the buckets)
+        if (kind == 0 && keep == DAY_KEEP) keep = t + 1 < v.T ? DAY_KEEP_Q : DAY_DROP;
         if (lane == 0u && !finalize) {
             // tomorrow's transmitting list keeps today's slots: the list's entries first, then the new infectees
             if (kind != 0) v.next_old[kind == 2 ? idx : n_old + idx] = keep == DAY_KEEP ? i : kHole;
