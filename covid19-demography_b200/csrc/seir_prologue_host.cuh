@@ -20,6 +20,9 @@
 #include <cstring>
 #include <unordered_map>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace seir_host {
 
@@ -75,6 +78,28 @@ struct Mt19937 {   // numba/_random.c:40-75 (init_genrand / genrand_int32 of Mat
             while (i > lo) {
                 if (index >= 624) refill();
                 int idx = index;
+#if defined(__SSE2__)
+                // counting only: 32 words at a time.  Over a batch i falls by at most 32, so a word is accepted whatever
+                // happened before it if it is <= i - 32 and rejected if it is > i; a word in between (probability 32 / i)
+                // sends the batch to the scalar loop below.  (signed compares: the operands stay below 2^31)
+                if (!STORE && mask < 0x80000000u) {
+                    static const unsigned char bits4[16] = {0, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
+                    const __m128i vmask = _mm_set1_epi32((int)mask);
+                    while (idx + 32 <= 624 && i - 32 > lo) {
+                        const __m128i vhi = _mm_set1_epi32((int)i), vlo = _mm_set1_epi32((int)(i - 32));
+                        int accepted = 0, unsure = 0;
+                        for (int b = 0; b < 8; ++b) {
+                            const __m128i r = _mm_and_si128(_mm_loadu_si128(reinterpret_cast<const __m128i *>(out + idx + 4 * b)), vmask);
+                            const __m128i above_lo = _mm_cmpgt_epi32(r, vlo), above_hi = _mm_cmpgt_epi32(r, vhi);
+                            accepted += bits4[15 ^ _mm_movemask_ps(_mm_castsi128_ps(above_lo))];
+                            unsure |= _mm_movemask_ps(_mm_castsi128_ps(_mm_andnot_si128(above_hi, above_lo)));
+                        }
+                        if (unsure) break;
+                        i -= accepted;
+                        idx += 32;
+                    }
+                }
+#endif
                 while (idx < 624 && i > lo) {
                     const uint32_t r = out[idx++] & mask;
                     if (STORE) J[i] = r;
@@ -99,7 +124,7 @@ inline void first_k_of_shuffle(Mt19937 &g, int64_t len, int64_t k, int64_t *out,
         return;
     }
     if (k > len / 4) {                   // a real shuffle
-        J.resize((size_t)len);
+        if (J.size() < (size_t)len) J.resize((size_t)len);   // (never shrunk: growing a vector zero-fills)
         g.shuffle_draws<true>(len - 1, J.data());
         std::vector<uint32_t> x((size_t)len);
         for (int64_t i = 0; i < len; i++) x[(size_t)i] = (uint32_t)i;
@@ -111,7 +136,7 @@ inline void first_k_of_shuffle(Mt19937 &g, int64_t len, int64_t k, int64_t *out,
         for (int64_t r = 0; r < k; r++) out[r] = (int64_t)x[(size_t)r];
         return;
     }
-    J.resize((size_t)len);
+    if (J.size() < (size_t)len) J.resize((size_t)len);
     g.shuffle_draws<true>(len - 1, J.data());
     bits.assign((size_t)((len + 63) / 64), 0);
     std::unordered_map<uint32_t, int64_t> slot_at;   // tracked position -> which output it becomes
@@ -161,8 +186,9 @@ extern "C" int seir_prologue_mt(uint32_t seed, int64_t n, int n_ages, const int6
     if (k0 > n) return fail("seir_prologue_mt: more initial cases than agents");   // np.random.choice raises
     try {
         seir_host::Mt19937 g(seed);                                           // :163
-        std::vector<uint32_t> J;
-        std::vector<uint64_t> bits;
+        // scratch kept between calls (40 MB at n = 10 M: its page faults cost more than the draws that fill it)
+        static thread_local std::vector<uint32_t> J;
+        static thread_local std::vector<uint64_t> bits;
         std::vector<int64_t> picks;
         std::memset(home_real, 0, (size_t)n);
         for (int a = 0; a < n_ages; a++) {                                     // :178-182

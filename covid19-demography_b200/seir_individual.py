@@ -57,14 +57,46 @@ def _population_key(households, age, diabetes, hypertension, p_infect_household,
     A few hundred kB are read: microseconds against the 1.5 s an engine takes to create at n = 10 M."""
     import zlib
 
-    def sig(a):
+    def sig(a, samples):
         a = np.asarray(a)
         flat = a.reshape(-1)
-        step = max(1, flat.shape[0] // 65536)
+        step = max(1, flat.shape[0] // samples)
         return (a.shape, str(a.dtype), zlib.crc32(np.ascontiguousarray(flat[::step]).tobytes()),
                 zlib.crc32(np.ascontiguousarray(flat[-4096:]).tobytes()))
-    return (sig(households), sig(age), sig(diabetes), sig(hypertension), sig(p_infect_household),
-            opt["mode"], opt["launch"], opt["device"])
+    arrays = (households, age, diabetes, hypertension, p_infect_household)
+    # the same array objects at the same addresses as in the last call (the usual case): a sixteenth of the samples
+    # confirms the key that call computed
+    ident = tuple((id(a), np.asarray(a).__array_interface__["data"][0], np.asarray(a).shape) for a in arrays)
+    light = tuple(sig(a, 4096) for a in arrays)
+    global _last_population
+    if _last_population is not None and _last_population[0] == ident and _last_population[1] == light:
+        full = _last_population[2]
+    else:
+        full = tuple(sig(a, 65536) for a in arrays)
+        _last_population = (ident, light, full)
+    return full + (opt["mode"], opt["launch"], opt["device"])
+
+
+_last_population = None
+
+
+_tables_cache = {}
+
+
+def _tables_for(contact_matrix, group_sizes, p, iso_factor, p_ms, p_sc, p_cd, with_replay):
+    """tables.build_tables, remembered by the CONTENT of its inputs: the drivers call run_model seed after seed with the
+    same matrices and parameters (run_simulation.py:437-444), and the alias tables are a Python loop of ten milliseconds."""
+    import zlib
+    arrays = [np.ascontiguousarray(a) for a in (contact_matrix, group_sizes, iso_factor, p_ms, p_sc, p_cd)]
+    key = (tuple((a.shape, str(a.dtype), zlib.crc32(a.tobytes()), zlib.adler32(a.tobytes())) for a in arrays),
+           tuple(sorted(p.items())), with_replay)
+    tb = _tables_cache.get(key)
+    if tb is None:
+        if len(_tables_cache) >= 8:
+            _tables_cache.pop(next(iter(_tables_cache)))
+        tb = _tables_cache[key] = _tables.build_tables(contact_matrix, group_sizes, p, iso_factor, p_ms, p_sc, p_cd,
+                                                       with_replay=with_replay)
+    return tb
 
 
 def _engine_for(key, build):
@@ -138,8 +170,8 @@ def run_model(seed, households, age, age_groups, diabetes, hypertension, contact
         raise ValueError("n_ages must be %d" % _tables.N_AGES)
     tracing_enabled = 0 if opt["tracing"] == "off" else 1
     group_sizes = np.array([len(g) for g in age_groups], dtype=np.int64)
-    tb = _tables.build_tables(contact_matrix, group_sizes, p, mean_time_to_isolate_factor, p_mild_severe,
-                              p_severe_critical, p_critical_death, with_replay=(opt["mode"] == "replay"))
+    tb = _tables_for(contact_matrix, group_sizes, p, mean_time_to_isolate_factor, p_mild_severe, p_severe_critical,
+                     p_critical_death, opt["mode"] == "replay")
     # the population stays resident on the device between calls (the drivers call once per seed with the same
     # arrays): only the scalars, the tables and the per-run picks travel
     key = _population_key(households, age, diabetes, hypertension, p_infect_household, opt)
