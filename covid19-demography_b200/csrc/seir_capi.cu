@@ -298,24 +298,22 @@ __global__ void seir_init_state_kernel(DevCtx cx, uint32_t *barrier_words, int n
         for (int64_t k = tid; k < n_barrier_words; k += nth) barrier_words[k] = 0u;
         for (int64_t k = tid; k <= kMaxLaunches; k += nth) cx.ctl[k] = 0;
     }
-    const int64_t nvec = cx.n_pad / kVec;
-    const int64_t total = nvec * cx.n_rep;
+    // every warp instruction stores 512 consecutive bytes (lane l the l-th 16 B of them)
+    const int64_t cells = cx.n_pad * (int64_t)cx.n_rep;   // (n_pad is a multiple of kVec = 16 agents)
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        cx.inbox[g] = 0;
-        uint4 *wz = reinterpret_cast<uint4 *>(cx.winner + g * kVec);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) __stcs(wz + k, z);
-        if (cx.n_shards > 1) {  // (the infection days every GPU of a sharded run keeps)
-            uint4 *xz = reinterpret_cast<uint4 *>(cx.xday + g * kVec);
-            __stcs(xz, z);
-            __stcs(xz + 1, z);
-        }
-        if (cx.log_head) {  // tracing state: log heads (the tracer's marks are stamped with the run number)
-            uint4 *hz = reinterpret_cast<uint4 *>(cx.log_head + g * kVec);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) __stcs(hz + k, z);
-        }
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    uint4 *wz = reinterpret_cast<uint4 *>(cx.winner);
+    for (int64_t g = tid; g < cells / 2; g += nth) __stcs(wz + g, z);             // 8 B per agent
+    uint4 *iz = reinterpret_cast<uint4 *>(cx.inbox);
+    for (int64_t g = tid; g < cells / 64; g += nth) __stcs(iz + g, z);            // 2 bits per agent
+    for (int64_t g = cells / 64 * 4 + tid; g < cells / 16; g += nth) cx.inbox[g] = 0u;   // (the words behind the last whole 16 B)
+    if (cx.n_shards > 1) {  // (the infection days every GPU of a sharded run keeps)
+        uint4 *xz = reinterpret_cast<uint4 *>(cx.xday);
+        for (int64_t g = tid; g < cells / 8; g += nth) __stcs(xz + g, z);         // 2 B per agent
+    }
+    if (cx.log_head) {  // tracing state: log heads (the tracer's marks are stamped with the run number)
+        uint4 *hz = reinterpret_cast<uint4 *>(cx.log_head);
+        for (int64_t g = tid; g < cells / 4; g += nth) __stcs(hz + g, z);         // 4 B per agent
     }
 }
 
