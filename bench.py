@@ -341,12 +341,13 @@ def run_gpu_arm(args):
     clocks = sampler.finish()
     # ---- end to end through the C ABI with host buffers (wall clock): per-run inputs from pinned host memory, the
     # tallies and counters of every run back on the host; the algorithmic bytes of every step come from those tallies
+    tal_out = [[np.zeros((T, 9, 101), dtype=np.int64) for _ in range(R)] for _ in range(args.steps)]  # host result buffers of the K steps
     sync_all()
     e0 = time.perf_counter()
     tals = []
     for k in range(args.steps):
         eng.run(*ins[k])
-        tals.append([eng.tallies(r) for r in range(R)])
+        tals.append([eng.tallies(r, out=tal_out[k][r]) for r in range(R)])
     sync_all()
     e2e_s = time.perf_counter() - e0
     for step in tals:

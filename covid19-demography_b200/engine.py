@@ -399,9 +399,14 @@ class Engine:
         _check(self.lib.seir_last_run_ms3(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def tallies(self, replica=0):
-        """int64[T, 9, 101]: per-day counts by age, planes S,E,Mild,Documented,Severe,Critical,R,D,Q."""
-        out = np.empty((self.T, 9, _tables.N_AGES), dtype=np.int64)
+    def tallies(self, replica=0, out=None):
+        """int64[T, 9, 101]: per-day counts by age, planes S,E,Mild,Documented,Severe,Critical,R,D,Q.
+        out: a C-contiguous int64[T, 9, 101] buffer of the caller's to fill (a loop over many runs then touches no
+        fresh memory per run)."""
+        if out is None:
+            out = np.empty((self.T, 9, _tables.N_AGES), dtype=np.int64)
+        elif out.shape != (self.T, 9, _tables.N_AGES) or out.dtype != np.int64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous int64[T, 9, 101] array")
         _check(self.lib.seir_get_tallies(self._h, replica, _ptr(out)))
         return out[:self.T_rep[replica]]
 
