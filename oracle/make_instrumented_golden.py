@@ -186,7 +186,45 @@ def freeze(name):
           "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
+LARGE = ("ensemble_tracing_italy_n20000", 9)   # (fixture whose population is used, seed): 20 000 agents, tracing from day 25
+
+
+def large_summary(out, age, T):
+    """What is frozen of a large run: per-day per-age counts, a digest of the packed history, the ten vectors (their
+    values are small integers, -1 and inf: exact in float32)."""
+    import hashlib
+    import util
+    packed = util.pack_history(out[:9])
+    fx = {"tallies": util.tallies_from_history(out[:9], age, T).astype(np.int32),
+          "history_sha256": np.array(hashlib.sha256(np.ascontiguousarray(packed).tobytes()).hexdigest())}
+    for k in util.VECS:
+        v = np.asarray(out[util.VEC_INDEX[k]])
+        assert np.array_equal(v.astype(np.float32).astype(np.float64), v, equal_nan=True)
+        fx["out_" + k] = v.astype(np.float32)
+    return fx
+
+
+def freeze_large():
+    """One run large enough for the staged (dense-day) pass to run over many CTAs: thousands of list entries a day."""
+    import util
+    name, seed = LARGE
+    c = util.Case(name)
+    out = run_case(c, seed=seed)
+    T = int(c.params["T"])
+    fx = large_summary(out, c.age, T)
+    fx["seed"] = np.int64(seed)
+    path = os.path.join(GOLDEN, "ref_keyed_large_italy_n20000.npz")
+    np.savez_compressed(path, **fx)
+    tal = fx["tallies"]
+    print("large: n", c.n, "T", T, "infected", int(c.n - tal[-1, 0].sum()), "peak active", int(tal[:, [1, 2, 4, 5]].sum(axis=(1, 2)).max()),
+          "Q end", int(tal[-1, 8].sum()), "%.0f kB" % (os.path.getsize(path) / 1e3))
+
+
 if __name__ == "__main__":
     import util
-    for name in (sys.argv[1:] or util.CASES):
-        freeze(name)
+    which = sys.argv[1:] or (list(util.CASES) + ["large"])
+    for name in which:
+        if name == "large":
+            freeze_large()
+        else:
+            freeze(name)

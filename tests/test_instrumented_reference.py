@@ -103,3 +103,44 @@ def test_gpu_replay_equals_instrumented_reference(gpu_engine_module, monkeypatch
     assert np.array_equal(eng.tallies(0), util.tallies_from_history(util.unpack_history(want), c.age, T)), \
         "per-day per-age counts differ"
     eng.close()
+
+
+# ---- one large run: 20 000 agents, 12 208 infections, thousands of list entries a day (the staged pass over many CTAs),
+# tracing from day 25 as compiled.  Frozen: per-day per-age counts, a digest of the packed history, the ten vectors.
+def _large():
+    import make_instrumented_golden as mig
+    name, seed = mig.LARGE
+    return util.Case(name), seed, np.load(os.path.join(util.GOLDEN, "ref_keyed_large_italy_n20000.npz")), mig
+
+
+def _check_large(fx, packed, tallies, vector_of):
+    import hashlib
+    assert np.array_equal(tallies, fx["tallies"].astype(np.int64)), "per-day per-age counts differ"
+    assert hashlib.sha256(np.ascontiguousarray(packed).tobytes()).hexdigest() == str(fx["history_sha256"]), "history differs"
+    for k in util.VECS:
+        assert np.array_equal(vector_of(k), fx["out_" + k].astype(np.float64), equal_nan=True), k
+
+
+def test_oracle_replay_equals_large_instrumented_run():
+    c, seed, fx, _ = _large()
+    assert int(fx["seed"]) == seed and c.n == 20000
+    tup, ex, home, init = c.keyed_oracle("replay", dict(c.params), seed=seed)
+    T = int(c.params["T"])
+    _check_large(fx, util.pack_history(tup[:9]), util.tallies_from_history(tup[:9], c.age, T), lambda k: tup[util.VEC_INDEX[k]])
+    assert c.n - fx["tallies"][-1, 0].sum() > 10000 and fx["tallies"][:, [1, 2, 4, 5]].sum(axis=(1, 2)).max() > 4000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("passes", ["default", "staged_only"])
+def test_gpu_replay_equals_large_instrumented_run(gpu_engine_module, monkeypatch, passes):
+    if passes == "staged_only":
+        monkeypatch.setenv("SEIR_SPARSE_ROUNDS", "0")
+    c, seed, fx, _ = _large()
+    params = dict(c.params)
+    home, init = gpu_engine_module.prologue_mt(seed, gpu_engine_module.group_csr(c.age_groups), c.n,
+                                               c.fraction_stay_home, params["initial_infected_fraction"])
+    eng = c.gpu_engine(gpu_engine_module, params, "replay")
+    eng.run([seed], [home], [init])
+    _check_large(fx, eng.history("packed"), eng.tallies(0), eng.agent_vector)
+    assert eng.counters()["infections"] > 10000
+    eng.close()
