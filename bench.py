@@ -356,7 +356,7 @@ def run_gpu_arm(args):
             balg += b_; a_sum += a_; i_sum += i_
     home_used = 1 <= p["t_stayhome_start"] < T  # (C2: stay-home never starts, Home_real is never read nor copied)
     h2d = R * ((n if home_used else 0) + 8 * n_init + 8)
-    d2h = R * (T * TAL_ROWS_DEVICE * 101 * 4 + 32)  # the device's tally rows per day and age (uint32) + the run counters, to pinned host memory
+    d2h = R * (T * 9 * 101 * 8 + 32)  # the run's [T, 9, 101] int64 counts (accumulated on the device) + the run counters, to pinned host memory
 
     agent_days_step = float(n) * (T - 1) * R
     local_ms = {"dev": dev_ms, "loop": loop_ms, "mat": mat_sum, "init": init_sum}  # the roofline line describes rank 0's own kernels

@@ -517,6 +517,59 @@ __global__ void __launch_bounds__(kMatThreads) seir_materialize_kernel(const __g
     }
 }
 
+// The reference's [T][9][101] daily counts (:392 planes S,E,Mild,Documented,Severe,Critical,R,D,Q summed by age -- what the
+// drivers' X.sum(axis=1) and age masks compute) from the day loop's per-day CHANGES: one thread per (plane, age) runs through
+// the days.  Launched behind the day loop on the copy stream, next to the history materialisation; its int64 output goes to
+// pinned host memory, so seir_get_tallies is one memcpy.  One CTA per replica.
+__global__ void __launch_bounds__(1024) seir_tally_accumulate_kernel(const uint32_t *raw_all, long long *out_all, const long long *gs, int T)
+{
+    const int k = threadIdx.x;  // plane * kAges + age
+    if (k >= SEIR_N_TALLY * kAges) return;
+    const int plane = k / kAges, a = k % kAges;
+    const uint32_t *raw = raw_all + (size_t)blockIdx.x * T * TAL_ROWS * kAges + a;
+    long long *out = out_all + (size_t)blockIdx.x * T * SEIR_N_TALLY * kAges + k;
+    int r0 = 0, r1 = -1, r2 = -1;
+    long long base = 0, sign = 1;
+    switch (plane) {
+        case 0: r0 = TAL_NEW_E; base = gs[a]; sign = -1; break;          // S = group size - infections so far
+        case 1: r0 = TAL_NEW_E; r1 = TAL_D_E; break;
+        case 2: r0 = TAL_D_MILD; break;
+        case 3: r0 = TAL_NEW_DOC; break;
+        case 4: r0 = TAL_D_SEV; break;
+        case 5: r0 = TAL_D_CRIT; break;
+        case 6: r0 = TAL_NEW_R; break;
+        case 7: r0 = TAL_NEW_D; break;
+        default: r0 = TAL_NEW_QE; r1 = TAL_D_Q; r2 = TAL_NEW_Q2; break;
+    }
+    // (a missing row reads row r0 again with weight 0: every load is unconditional, and 16 days of them are in flight
+    // together -- the kernel runs next to the materialisation kernel, which keeps the memory system busy, so it is the
+    // number of dependent round trips that counts)
+    const int w1 = r1 >= 0 ? 1 : 0, w2 = r2 >= 0 ? 1 : 0;
+    const uint32_t *p0 = raw + r0 * kAges, *p1 = raw + (w1 ? r1 : r0) * kAges, *p2 = raw + (w2 ? r2 : r0) * kAges;
+    long long acc = 0;
+    int t = 0;
+    for (; t + 16 <= T; t += 16) {
+        int32_t v0[16], v1[16], v2[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const size_t o = (size_t)(t + u) * TAL_ROWS * kAges;
+            v0[u] = (int32_t)__ldcg(p0 + o);  // (signed rows wrap around 2^32)
+            v1[u] = (int32_t)__ldcg(p1 + o);
+            v2[u] = (int32_t)__ldcg(p2 + o);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            acc += (long long)v0[u] + (long long)(w1 * v1[u]) + (long long)(w2 * v2[u]);
+            out[(size_t)(t + u) * SEIR_N_TALLY * kAges] = base + sign * acc;
+        }
+    }
+    for (; t < T; ++t) {
+        const size_t o = (size_t)t * TAL_ROWS * kAges;
+        acc += (long long)(int32_t)__ldcg(p0 + o) + (long long)(w1 * (int32_t)__ldcg(p1 + o)) + (long long)(w2 * (int32_t)__ldcg(p2 + o));
+        out[(size_t)t * SEIR_N_TALLY * kAges] = base + sign * acc;
+    }
+}
+
 __global__ void seir_pack_home_kernel(const uint8_t *home_u8, uint32_t *bitmap, int64_t n, int64_t n_words)
 {
     for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
@@ -720,8 +773,11 @@ struct seir_handle {
     unsigned char *in_host = nullptr;  // pinned staging of a run's small inputs
     size_t in_host_bytes = 0;
     uint32_t *tally_host = nullptr;
+    DevBuf<long long> tally64, gs_dev;     // the accumulated [T][9][101] counts of every replica (seir_tally_accumulate_kernel); group sizes
+    long long *tally64_host = nullptr;     // ... and their pinned host copy, filled by the run itself
     unsigned long long *counters_host = nullptr;
     bool host_results = false;  // the pinned copies hold the last run's results
+    bool raw_home = false;      // ... including the raw per-day tally changes (tally_host)
     cudaStream_t copy_stream = nullptr;
     uint32_t cluster_cap = 0;   // a day with at most this many list entries runs in the one-cluster kernel (0: never)
     bool cluster_failed = false;  // a cluster launch was refused on this device: not tried again
@@ -858,9 +914,13 @@ static int alloc_state(seir_handle *h)
         h->host_results = false;
         if (h->tally_host) { cudaFreeHost(h->tally_host); h->tally_host = nullptr; }  // (re-allocation for a longer T)
         if (h->counters_host) { cudaFreeHost(h->counters_host); h->counters_host = nullptr; }
+        if (h->tally64_host) { cudaFreeHost(h->tally64_host); h->tally64_host = nullptr; }
         if (tb <= ((size_t)256 << 20)) {  // (beyond that the getters copy on demand)
             CK(cudaHostAlloc((void **)&h->tally_host, tb, cudaHostAllocDefault));
             CK(cudaHostAlloc((void **)&h->counters_host, R * 4 * 8, cudaHostAllocDefault));
+            const size_t cells64 = (size_t)R * T * SEIR_N_TALLY * kAges;
+            CK(h->tally64.alloc(cells64));
+            CK(cudaHostAlloc((void **)&h->tally64_host, cells64 * 8, cudaHostAllocDefault));
         }
     }
     CK(h->fine_ns.alloc((T + 2) * 16));
@@ -1040,6 +1100,12 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
                 gmem[(size_t)k] = (int32_t)m;
             }
         if (!gok) { fail("seir_population.group_offsets/group_members do not partition the agents by age"); break; }
+        {   // group sizes for the device-side accumulation of the tallies (S = group size - infections so far)
+            long long gs64[kAges];
+            for (int a = 0; a < kAges; ++a) gs64[a] = (long long)h->group_sizes[a];
+            if (h->gs_dev.alloc(kAges) != cudaSuccess ||
+                cudaMemcpy(h->gs_dev.p, gs64, sizeof gs64, cudaMemcpyHostToDevice) != cudaSuccess) { fail("group sizes: device allocation failed"); break; }
+        }
         h->p_hh_scalar = pop->p_infect_household[0];
         h->p_hh_uniform = true;
         for (int64_t i = 1; i < n; ++i)
@@ -1050,7 +1116,11 @@ int seir_create(const seir_params *params, const seir_population *pop, const sei
         CKB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CKB(cudaEventCreate(&h->ev0)); CKB(cudaEventCreate(&h->ev1)); CKB(cudaEventCreate(&h->ev2));
         CKB(cudaEventCreate(&h->ev3));
-        CKB(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        {
+            int least = 0, greatest = 0;
+            CKB(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CKB(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, greatest));
+        }
         CKB(h->stat.alloc((size_t)h->n_pad));
         CKB(cudaMemcpy(h->stat.p, stat.data(), (size_t)h->n_pad * 2, cudaMemcpyHostToDevice));
         CKB(h->grp_off.alloc(kAges + 1));
@@ -1158,6 +1228,12 @@ int seir_shard_attach(seir_handle *h, int rank, int world, const uint8_t *all_ha
     for (int g = 0; g <= world; ++g) h->shard_lo[g] = bounds[g];
     h->shard_group_sizes.assign(kAges, 0);
     for (int64_t i = bounds[rank]; i < bounds[rank + 1]; ++i) h->shard_group_sizes[h->age8[(size_t)i]] += 1;
+    {   // (a shard counts its own agents: the tallies of the ranks add up to the population's)
+        long long gs64[kAges];
+        for (int a = 0; a < kAges; ++a) gs64[a] = (long long)h->shard_group_sizes[(size_t)a];
+        CK(h->gs_dev.alloc(kAges));
+        CK(cudaMemcpy(h->gs_dev.p, gs64, sizeof gs64, cudaMemcpyHostToDevice));
+    }
     fill_ctx(h);
     return 0;
 }
@@ -1458,8 +1534,17 @@ int seir_run_ex(seir_handle *h, const seir_replica *reps, const seir_overrides *
     h->host_results = false;
     if (h->tally_host) {  // tallies and counters are final here: bring them home while the history is written
         CK(cudaStreamWaitEvent(h->copy_stream, h->ev2, 0));
+        // (the copy stream has the higher priority and its kernel is queued first: a CTA that becomes ready together with
+        // the materialisation kernel's gets its SM before that kernel fills every thread slot of the device)
+        if (h->tally64_host && h->gs_dev.p) {
+            seir_tally_accumulate_kernel<<<R, 1024, 0, h->copy_stream>>>(h->tally.p, h->tally64.p, h->gs_dev.p, h->prm.T);
+            ++h->launches;
+            CK(cudaMemcpyAsync(h->tally64_host, h->tally64.p, (size_t)R * h->prm.T * SEIR_N_TALLY * kAges * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
         CK(cudaMemcpyAsync(h->counters_host, h->counters.p, (size_t)R * 4 * 8, cudaMemcpyDeviceToHost, h->copy_stream));
-        CK(cudaMemcpyAsync(h->tally_host, h->tally.p, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+        h->raw_home = !(h->tally64_host && h->gs_dev.p);   // (the raw per-day changes travel only when nothing accumulated them here)
+        if (h->raw_home)
+            CK(cudaMemcpyAsync(h->tally_host, h->tally.p, (size_t)R * h->prm.T * TAL_ROWS * kAges * 4, cudaMemcpyDeviceToHost, h->copy_stream));
     }
     if (h->history_mode == SEIR_HISTORY_EAGER) {
         seir_materialize_kernel<<<h->sms * 8, kMatThreads, 0, h->stream>>>(h->cx);
@@ -1529,7 +1614,7 @@ int seir_last_run_ms3(seir_handle *h, float *init_ms, float *day_loop_ms, float 
 static int raw_tallies(seir_handle *h, int replica, std::vector<uint32_t> &own, const uint32_t **raw_p)
 {
     const size_t per = (size_t)h->prm.T * TAL_ROWS * kAges;
-    if (h->host_results) {
+    if (h->host_results && h->raw_home) {
         *raw_p = h->tally_host + (size_t)replica * per;
     } else {
         own.resize(per);
@@ -1545,6 +1630,11 @@ int seir_get_tallies(seir_handle *h, int replica, int64_t *out)
     if (replica < 0 || replica >= h->n_rep) return fail("replica out of range");
     CK(cudaSetDevice(h->device));
     const int T = h->prm.T;
+    if (h->host_results && h->tally64_host && h->gs_dev.p) {  // accumulated on the device, brought home by the run itself
+        const size_t per64 = (size_t)T * SEIR_N_TALLY * kAges;
+        memcpy(out, h->tally64_host + (size_t)replica * per64, per64 * 8);
+        return 0;
+    }
     std::vector<uint32_t> own;
     const uint32_t *raw_p;
     if (raw_tallies(h, replica, own, &raw_p)) return 1;
@@ -1848,6 +1938,8 @@ void seir_destroy(seir_handle *h)
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->in_host) cudaFreeHost(h->in_host);
     if (h->tally_host) cudaFreeHost(h->tally_host);
+    if (h->tally64_host) cudaFreeHost(h->tally64_host);
+    h->tally64.release(); h->gs_dev.release();
     if (h->counters_host) cudaFreeHost(h->counters_host);
     delete h;
 }

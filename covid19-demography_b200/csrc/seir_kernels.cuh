@@ -60,7 +60,7 @@ constexpr int kDocScan = 8;              // days of documentation draws (:280-28
 
 // device tally rows (per day, per age)
 // Every row is a per-day CHANGE (an agent is only visited on days on which something may happen to it, so nothing
-// is recounted): the host accumulates them into the reference's daily counts (seir_get_tallies).
+// is recounted): seir_tally_accumulate_kernel accumulates them into the reference's daily counts (read by seir_get_tallies).
 enum { TAL_NEW_E = 0,  // infections of the day (S -> E)
        TAL_NEW_QE,     // of them quarantined on infection (:353-354, or reached by a tracer the same day)
        TAL_D_E, TAL_D_MILD, TAL_D_SEV, TAL_D_CRIT,  // signed: change of the E / Mild / Severe / Critical head counts by the day's transitions
