@@ -51,6 +51,16 @@ def test_shard_handle_count_matches_the_header():
     assert m and int(m.group(1)) == engine.SHARD_HANDLES
 
 
+def test_flag_constants_match_the_header():
+    src = open(HEADER).read()
+    m = re.search(r"#define\s+SEIR_VEC_PREVIOUS\s+(\d+)", src)
+    assert m and int(m.group(1)) == engine.VEC_PREVIOUS
+    m = re.search(r"SEIR_VEC_COUNT\s*=\s*(\d+)", src)
+    assert m and int(m.group(1)) == len(engine.VEC) and engine.VEC_PREVIOUS > max(engine.VEC.values())
+    m = re.search(r"#define\s+SEIR_H_PREVIOUS\s+(\d+)", src)
+    assert m and int(m.group(1)) == 16
+
+
 def test_no_device_is_an_error_not_a_fallback():
     lib = engine.load_library()
     if lib.seir_device_count() > 0:
