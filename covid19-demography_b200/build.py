@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libseir_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", "seir_capi.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "seir_kernels.cuh"), os.path.join(HERE, "csrc", "seir_prologue_host.cuh"),
+DEPS = SOURCES + [os.path.join(HERE, "csrc", "seir_kernels.cuh"), os.path.join(HERE, "csrc", "seir_prologue_host.cuh"), os.path.join(HERE, "csrc", "seir_tsv_host.cuh"),
                   os.path.join(ROOT, "include", "seir_b200.h"),
                   os.path.join(ROOT, "include", "seir_draws.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1008,6 +1008,7 @@ const char *seir_last_error(void) { return g_err.c_str(); }
 
 }  // extern "C"
 #include "seir_prologue_host.cuh"   // seir_prologue_mt: the reference's MT19937 picks of one seed, host only
+#include "seir_tsv_host.cuh"        // seir_format_tsv: the drivers' per-job TSV files, host only
 extern "C" {
 
 int seir_device_count(void)

@@ -32,7 +32,7 @@ EXPORTS = ("seir_create", "seir_set_params", "seir_run", "seir_last_run_ms", "se
            "seir_host_register", "seir_host_unregister", "seir_last_run_ms3", "seir_get_day_times",
            "seir_get_stage_times", "seir_get_cohorts", "seir_shard_export", "seir_shard_attach", "seir_get_visits",
            "seir_history_preserve", "seir_run_ex", "seir_set_table_bank", "seir_get_prologue", "seir_abi_sizes",
-           "seir_shard_set_threshold", "seir_prologue_mt")
+           "seir_shard_set_threshold", "seir_prologue_mt", "seir_format_tsv")
 
 
 SHARD_HANDLES = 6   # include/seir_b200.h SEIR_SHARD_HANDLES
@@ -114,6 +114,7 @@ def load_library():
     lib.seir_host_unregister.argtypes = [C.c_void_p]
     lib.seir_prologue_mt.argtypes = [C.c_uint32, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.seir_format_tsv.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     lib.seir_probe_draws.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -504,6 +505,25 @@ def prologue_mt(seed, csr, n, fraction_stay_home, initial_infected_fraction):
                                 float(initial_infected_fraction), _ptr(home), _ptr(init), init.size, _ptr(got)))
     assert int(got[0]) == k0
     return home.view(np.bool_), init[:k0]
+
+
+_tsv_buf = None
+
+
+def format_tsv(a):
+    """bytes: a float64 matrix as the reference's `to_csv(sep="\\t", index=False, header=False, na_rep="NA")` writes it
+    (the library's host routine seir_format_tsv; sweep_io falls back on nothing -- this is its float path)."""
+    global _tsv_buf
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a[:, None]
+    rows, cols = a.shape
+    cap = rows * cols * 27 + rows + 1
+    if _tsv_buf is None or len(_tsv_buf) < cap:
+        _tsv_buf = C.create_string_buffer(max(cap, 1 << 16))
+    n = C.c_int64()
+    _check(load_library().seir_format_tsv(_ptr(a) if a.size else None, rows, cols, _tsv_buf, len(_tsv_buf), C.byref(n)))
+    return C.string_at(_tsv_buf, n.value)
 
 
 def pin(array):

@@ -84,8 +84,28 @@ def _format_tsv(a):
         a = a[:, None]
     if a.dtype.kind in "iub":
         rows = ["\t".join(map(str, r)) for r in a.tolist()]
-    else:
-        rows = ["\t".join("NA" if x != x else repr(x) for x in r) for r in a.astype(np.float64).tolist()]
+        return ("\n".join(rows) + "\n") if rows else ""
+    # floats: the library's host routine (seir_format_tsv) -- formatted value by value in Python this took longer than
+    # the device run of the job; _format_tsv_py below is the same in Python (tests compare the two and pandas)
+    from . import engine as _engine
+    return _engine.format_tsv(a).decode("ascii")
+
+
+def _format_tsv_bytes(a):
+    """_format_tsv as bytes (what goes into the file)."""
+    a = np.asarray(a)
+    if a.dtype.kind in "iub":
+        return _format_tsv(a).encode("ascii")
+    from . import engine as _engine
+    return _engine.format_tsv(a)
+
+
+def _format_tsv_py(a):
+    """_format_tsv for floats in plain Python (the checked alternative of seir_format_tsv)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a[:, None]
+    rows = ["\t".join("NA" if x != x else repr(x) for x in r) for r in a.tolist()]
     return ("\n".join(rows) + "\n") if rows else ""
 
 
@@ -95,7 +115,13 @@ def write_job_files(directory, stem, arrays, datatypes=None):
     paths = {}
     for name in (DATATYPES if datatypes is None else datatypes):
         path = os.path.join(directory, "%s_%s.csv" % (stem, name))
-        with open(path, "w") as f:
-            f.write(_format_tsv(arrays[name]))
+        data = _format_tsv_bytes(arrays[name])
+        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)  # (no buffered text layer: one write per file)
+        try:
+            view = memoryview(data)
+            while len(view):
+                view = view[os.write(fd, view):]
+        finally:
+            os.close(fd)
         paths[name] = path
     return paths

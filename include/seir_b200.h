@@ -243,6 +243,12 @@ int seir_prologue_mt(uint32_t seed, int64_t n, int n_ages, const int64_t *group_
                      const double *fraction_stay_home, double initial_infected_fraction, uint8_t *home_real,
                      int64_t *initial_infected, int64_t initial_cap, int64_t *n_initial);
 
+/* HOST ONLY: the bytes `pd.DataFrame(a).to_csv(sep="\t", index=False, header=False, na_rep="NA")` writes for a float64
+ * matrix a[rows][cols] -- what parameter_sweep.py:716-729 and simulate_agepolicies.py:646-716 write per job and datatype:
+ * every value as Python's repr (shortest round-trip digits; "3.0", "0.1", "1e-05", "inf"), NaN as NA, tab-separated, one
+ * line per row.  out must hold 27 bytes per value + 1 per row + 1; *written is the length. */
+int seir_format_tsv(const double *a, int64_t rows, int64_t cols, char *out, int64_t cap, int64_t *written);
+
 /* Page-lock / unlock a caller-owned host buffer so the per-run copies in seir_run are DMA transfers. */
 int seir_host_register(void *ptr, uint64_t bytes);
 int seir_host_unregister(void *ptr);

@@ -177,3 +177,24 @@ def test_tsv_writer_is_byte_identical_to_the_reference_to_csv_call():
              np.array([[np.nan] * 3] * 2), rng.random((4, 10)) / 3e-7, np.full(4, np.nan)]
     for a in cases:
         assert sweep_io._format_tsv(a) == reference_bytes(a)
+        if np.asarray(a).dtype.kind == "f":
+            assert sweep_io._format_tsv_py(a) == reference_bytes(a)
+
+
+def test_native_tsv_formatter_equals_pythons_repr_on_random_doubles():
+    """seir_format_tsv (host routine of the library: shortest round-trip digits from std::to_chars, laid out by Python's
+    repr rules) against Python itself on every kind of double: random bit patterns (subnormals, huge exponents, NaN
+    payloads), powers of ten around the fixed / scientific switch-over, counts, ratios."""
+    from covid19_demography_b200 import engine, sweep_io
+    rng = np.random.default_rng(5)
+    special = np.array([0.0, -0.0, 1e-5, 1e-4, 9.999e-5, 1e15, 1e16, 1e17, 5e-324, 1.7976931348623157e308, np.inf, -np.inf,
+                        np.nan, 0.30000000000000004, 1e22, 1e23, 9007199254740993.0, 123456789012345678.0, 1e100, 1e-100])
+    pieces = [special, rng.integers(0, 2**64, size=200000, dtype=np.uint64).view(np.float64),
+              rng.integers(0, 10**7, 50000).astype(np.float64), rng.random(50000),
+              rng.integers(0, 5000, 50000) / rng.integers(1, 300, 50000),
+              10.0 ** rng.integers(-30, 30, 50000) * rng.random(50000),
+              np.concatenate([10.0 ** np.arange(-320, 309.0), -(10.0 ** np.arange(-20, 20.0))])]
+    for a in pieces:
+        a = a[: len(a) // 5 * 5].reshape(-1, 5) if len(a) >= 5 else a
+        assert engine.format_tsv(a).decode("ascii") == sweep_io._format_tsv_py(a)
+    assert engine.format_tsv(np.zeros((0, 3))) == b"" and engine.format_tsv(np.zeros(0)) == b""
