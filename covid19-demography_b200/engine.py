@@ -495,8 +495,12 @@ def prologue_mt(seed, csr, n, fraction_stay_home, initial_infected_fraction):
         fsh = np.ascontiguousarray(fraction_stay_home, dtype=np.float64)
         if fsh.shape != (offs.shape[0] - 1,):
             raise ValueError("fraction_stay_home must have one entry per age")
+        if not np.isfinite(fsh).all() or (fsh < 0).any():
+            raise ValueError("fraction_stay_home must be finite and non-negative")   # (int(nan * len) raises in the reference, :181)
         if not fsh.any():
             fsh = None
+    if not np.isfinite(initial_infected_fraction) or initial_infected_fraction < 0:
+        raise ValueError("initial_infected_fraction must be finite and non-negative")
     k0 = int(initial_infected_fraction * n)
     home = np.empty(n, dtype=np.uint8)
     init = np.empty(max(k0, 1), dtype=np.int64)

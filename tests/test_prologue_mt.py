@@ -54,6 +54,10 @@ def test_argument_errors():
         engine.prologue_mt(0, csr, 49, None, 0.0)            # the groups do not partition 49 agents
     with pytest.raises(ValueError):
         engine.prologue_mt(0, csr, 50, np.zeros(7), 0.0)     # one fraction per age
+    with pytest.raises(ValueError):
+        engine.prologue_mt(0, csr, 50, np.full(101, np.nan), 0.0)
+    with pytest.raises(ValueError):
+        engine.prologue_mt(0, csr, 50, None, -0.5)
     with pytest.raises(RuntimeError, match="above 1"):
         engine.prologue_mt(0, csr, 50, np.full(101, 2.5), 0.0)
     with pytest.raises(RuntimeError, match="more initial cases"):
