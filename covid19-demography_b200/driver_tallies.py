@@ -17,8 +17,8 @@ AGE_GROUPS_SWEEP = ((0, 14), (15, 24), (25, 39), (40, 69), (70, 100))  # paramet
 
 def per_time(tallies):
     """{plane: X.sum(axis=1)} -- S_per_time ... Q_per_time (parameter_sweep.py:556-565)."""
-    t = np.asarray(tallies)
-    return {k: t[:, j, :].sum(axis=1) for j, k in enumerate(PLANES)}
+    s = np.asarray(tallies).sum(axis=2)   # [T, 9]: one reduction for the nine planes
+    return {k: s[:, j] for j, k in enumerate(PLANES)}
 
 
 def _median_from_histogram(counts):
@@ -47,16 +47,16 @@ def _medians_from_histograms(counts):
 def cohort_statistics(cohorts, fill=0.0):
     """run_simulation.py:448-453: per exposure day t (rows with no exposure keep `fill`):
     r_0_over_time, cfr_over_time, fraction_over_70_time, fraction_below_30_time, median_age_time."""
-    c = np.asarray(cohorts).astype(np.float64)
-    m = c[:, 0].sum(axis=1)
+    ci = np.asarray(cohorts)
+    tot = ci.sum(axis=2).astype(np.float64)   # [T, 4] (counts: exact in float64 whatever the order of the sums)
+    m, d, r = tot[:, 0], tot[:, 2], tot[:, 3]
     has = m > 0
-    d, r = c[:, 2].sum(axis=1), c[:, 3].sum(axis=1)
     with np.errstate(invalid="ignore", divide="ignore"):
-        vals = {"r_0_over_time": c[:, 1].sum(axis=1) / m,
+        vals = {"r_0_over_time": tot[:, 1] / m,
                 "cfr_over_time": np.where(d + r > 0, d / (d + r), np.nan),
-                "fraction_over_70_time": c[:, 0, 70:].sum(axis=1) / m,
-                "fraction_below_30_time": c[:, 0, :30].sum(axis=1) / m,
-                "median_age_time": _medians_from_histograms(np.asarray(cohorts)[:, 0])}
+                "fraction_over_70_time": ci[:, 0, 70:].sum(axis=1).astype(np.float64) / m,
+                "fraction_below_30_time": ci[:, 0, :30].sum(axis=1).astype(np.float64) / m,
+                "median_age_time": _medians_from_histograms(ci[:, 0])}
     return {k: np.where(has, v, fill).astype(np.float64) for k, v in vals.items()}
 
 
@@ -80,10 +80,21 @@ def by_age_group(tallies, cohorts, groups=AGE_GROUPS_SWEEP):
     """parameter_sweep.py:582-600: per age group and day -- infected (group size - S[t]), group size,
     CFR of the day's exposure cohort, dead (D[t])."""
     t = np.asarray(tallies)
-    c = np.asarray(cohorts).astype(np.float64)
     T = t.shape[0]
     G = len(groups)
     size_by_age = t[0, [0, 1, 2, 4, 5, 6, 7]].sum(axis=0)  # the compartments partition the agents
+    if all(groups[g][1] + 1 == groups[g + 1][0] for g in range(G - 1)) and groups[-1][1] == t.shape[2] - 1:
+        # consecutive age bands up to the last age (the sweep's): one segmented reduction per quantity
+        starts = [lo for lo, _ in groups]
+        size_g = np.add.reduceat(size_by_age, starts).astype(np.float64)
+        dr = np.add.reduceat(np.asarray(cohorts)[:, 2:4, :], starts, axis=2).astype(np.float64)   # [T, 2, G]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cfr = dr[:, 0, :] / (dr[:, 0, :] + dr[:, 1, :])
+        return {"infected_by_age_by_time": size_g[:, None] - np.add.reduceat(t[:, 0, :], starts, axis=1).T,
+                "total_age_by_time": np.repeat(size_g[:, None], T, axis=1),
+                "CFR_by_age_by_time": np.ascontiguousarray(cfr.T),
+                "dead_by_age_by_time": np.add.reduceat(t[:, 7, :], starts, axis=1).T.astype(np.float64)}
+    c = np.asarray(cohorts).astype(np.float64)
     out = {"infected_by_age_by_time": np.zeros((G, T)), "total_age_by_time": np.zeros((G, T)),
            "CFR_by_age_by_time": np.full((G, T), np.nan), "dead_by_age_by_time": np.zeros((G, T))}
     for g, (lo, hi) in enumerate(groups):
