@@ -455,7 +455,7 @@ int oracle_run_model(const oracle_params *p, const oracle_inputs *in, oracle_out
         const uint8_t *Sp = S + (t - 1) * n, *Ep = E + (t - 1) * n, *Mp = Mild + (t - 1) * n;
         const uint8_t *Dp = Documented + (t - 1) * n, *Sevp = Severe + (t - 1) * n;
         const uint8_t *Cp = Critical + (t - 1) * n, *Qp = Q + (t - 1) * n;
-        uint8_t *Sn = S + t * n, *En = E + t * n, *Mn = Mild + t * n, *Dn = Documented + t * n;
+        uint8_t *En = E + t * n, *Mn = Mild + t * n, *Dn = Documented + t * n;   /* (S[t] is written by infect()) */
         uint8_t *Sevn = Severe + t * n, *Cn = Critical + t * n, *Rn = R + t * n, *Deadn = D + t * n, *Qn = Q + t * n;
         const double td = (double)t;
 
