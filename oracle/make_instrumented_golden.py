@@ -23,7 +23,6 @@ oracle(keyed draws); this script closes the triangle without the oracle's contro
 `tests/test_instrumented_reference.py` then demands, bit for bit: oracle(replay) == these outputs (CPU, plus a live
 regeneration where /root/reference exists) and GPU(replay mode, through the C ABI) == these outputs (`-m gpu`).
 """
-import ctypes
 import importlib.util
 import os
 import sys
