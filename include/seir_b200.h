@@ -238,7 +238,8 @@ int seir_debug_trace_array(seir_handle *h, int which, int replica, void *out, ui
  * age group, :187 np.random.choice(n, int(initial_infected_fraction*n), replace=False) -- so that the drop-in run_model
  * infects and shelters the very agents the reference would.  group_offsets[n_ages+1] / group_members[n]: the age_groups
  * tuple (:36) in CSR form, members ascending (np.where order).  fraction_stay_home may be NULL (all zero).
- * home_real[n] (0/1) and initial_infected[*n_initial] are written; initial_cap is the room in initial_infected. */
+ * home_real[n] (0/1) and initial_infected[*n_initial] are written; initial_cap is the room in initial_infected.
+ * Thread-safe; each calling thread keeps 4 B per agent of scratch between calls (its page faults cost more than the draws). */
 int seir_prologue_mt(uint32_t seed, int64_t n, int n_ages, const int64_t *group_offsets, const int64_t *group_members,
                      const double *fraction_stay_home, double initial_infected_fraction, uint8_t *home_real,
                      int64_t *initial_infected, int64_t initial_cap, int64_t *n_initial);
